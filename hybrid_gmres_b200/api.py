@@ -1,0 +1,510 @@
+"""Host-side mirror of the reference's solver interface.
+
+The reference's drop-in boundary is the MATLAB function signature (SURVEY.md
+§8b); this module keeps the same function names, positional argument order,
+argument meaning and output order, and forwards to the C ABI
+(``include/hgmres.h``).  All arithmetic on vectors and matrices happens in the
+CUDA kernels of ``libhgmres.so``; nothing here computes.
+
+    [x,error_norm,residual_norm,niters] = hybrid_ab_gmres_rtp(A,B,b,x_true,tol,maxit,lambda)
+        -> x, error_norm, residual_norm, niters = hybrid_ab_gmres_rtp(A, B, b, x_true, tol, maxit, lam)
+
+``A``/``B`` may be a :class:`DeviceMatrix`, a ``scipy.sparse`` matrix (CSR is
+uploaded as is, CSC goes through the device transposition, anything else is
+converted to CSR first) or a full ``numpy`` array — the three input kinds the
+reference's callers pass (SURVEY.md §8b "Input types").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import HgExtras, HgSolverOpts, check
+
+__all__ = [
+    "Context", "DeviceMatrix", "Arnoldi", "GcvProblem", "default_context",
+    "hybrid_ab_gmres_rtp", "hybrid_ba_gmres_rtp", "hybrid_lsqr_solver", "hybrid_lsmr_solver",
+    "lsqr_solver", "lsmr_solver", "gcv_function", "gcv_prepare", "fminbnd_gcv",
+    "KERNEL_CLASSES",
+]
+
+KERNEL_CLASSES = {"spmv": 0, "multidot": 1, "lincomb": 2, "vector": 3, "reduce": 4, "setup": 5}
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _vec(a, n=None, name="vector"):
+    v = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+    if n is not None and v.shape[0] != n:
+        raise ValueError(f"{name}: expected length {n}, got {v.shape[0]}")
+    return v
+
+
+class Context:
+    """One device + one stream (``hg_ctx``)."""
+
+    def __init__(self, device: int | None = None, stream: int | None = None):
+        lib = _lib.load()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = C.c_void_p()
+        check(lib.hg_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hg_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self._lib.hg_ctx_sync(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        out = C.c_uint64()
+        check(self._lib.hg_ctx_launch_count(self._h, C.byref(out)))
+        return int(out.value)
+
+    def timing_enable(self, on: bool = True):
+        check(self._lib.hg_ctx_timing_enable(self._h, 1 if on else 0))
+
+    def timing_reset(self):
+        check(self._lib.hg_ctx_timing_reset(self._h))
+
+    def timing(self) -> dict:
+        """{class: (ms, launches, algorithmic_bytes)} since the last reset."""
+        out = {}
+        for name, k in KERNEL_CLASSES.items():
+            ms, cnt, by = C.c_double(), C.c_uint64(), C.c_double()
+            check(self._lib.hg_ctx_timing_get(self._h, k, C.byref(ms), C.byref(cnt), C.byref(by)))
+            out[name] = (ms.value, int(cnt.value), by.value)
+        return out
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+class DeviceMatrix:
+    """Device-resident CSR matrix (``hg_matrix``)."""
+
+    def __init__(self, handle, ctx: Context):
+        self._h = handle
+        self.ctx = ctx
+        r, c, z = C.c_int64(), C.c_int64(), C.c_int64()
+        check(ctx._lib.hg_matrix_info(handle, C.byref(r), C.byref(c), C.byref(z)))
+        self.shape = (int(r.value), int(c.value))
+        self.nnz = int(z.value)
+
+    # -- constructors ------------------------------------------------------
+    @classmethod
+    def from_csr(cls, indptr, indices, data, shape, ctx: Context | None = None):
+        ctx = ctx or default_context()
+        indptr = np.ascontiguousarray(indptr)
+        if indptr.dtype not in (np.int32, np.int64):
+            indptr = indptr.astype(np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        h = C.c_void_p()
+        check(ctx._lib.hg_matrix_from_csr(ctx._h, int(shape[0]), int(shape[1]), int(data.shape[0]),
+                                          _ptr(indptr), 32 if indptr.dtype == np.int32 else 64,
+                                          _ptr(indices), _ptr(data), C.byref(h)))
+        return cls(h, ctx)
+
+    @classmethod
+    def from_csc(cls, indptr, indices, data, shape, ctx: Context | None = None):
+        """MATLAB-style sparse input (``Jc``, ``Ir``, ``Pr``)."""
+        ctx = ctx or default_context()
+        indptr = np.ascontiguousarray(indptr)
+        indices = np.ascontiguousarray(indices)
+        bits = 64 if indices.dtype.itemsize == 8 else 32
+        want = np.int64 if bits == 64 else np.int32
+        if indices.dtype.kind == "u":  # mwIndex is unsigned; same bits for valid indices
+            indices = indices.view(want)
+        indptr = indptr.astype(want, copy=False) if indptr.dtype.itemsize * 8 != bits else indptr
+        if indptr.dtype.kind == "u":
+            indptr = indptr.view(want)
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        h = C.c_void_p()
+        check(ctx._lib.hg_matrix_from_csc(ctx._h, int(shape[0]), int(shape[1]), int(data.shape[0]),
+                                          _ptr(indptr), _ptr(indices), bits, _ptr(data), C.byref(h)))
+        return cls(h, ctx)
+
+    @classmethod
+    def from_dense(cls, a, ctx: Context | None = None):
+        ctx = ctx or default_context()
+        a = np.asfortranarray(np.asarray(a, dtype=np.float64))
+        if a.ndim != 2:
+            raise ValueError("from_dense: need a 2-D array")
+        h = C.c_void_p()
+        check(ctx._lib.hg_matrix_from_dense(ctx._h, a.shape[0], a.shape[1], _ptr(a), max(a.shape[0], 1),
+                                            C.byref(h)))
+        return cls(h, ctx)
+
+    @classmethod
+    def from_any(cls, M, ctx: Context | None = None):
+        if isinstance(M, DeviceMatrix):
+            return M
+        fmt = getattr(M, "format", None)
+        if fmt is not None and hasattr(M, "indptr"):
+            if fmt == "csr":
+                return cls.from_csr(M.indptr, M.indices, M.data, M.shape, ctx)
+            if fmt == "csc":
+                return cls.from_csc(M.indptr, M.indices, M.data, M.shape, ctx)
+        if fmt is not None and hasattr(M, "tocsr"):
+            M = M.tocsr()
+            return cls.from_csr(M.indptr, M.indices, M.data, M.shape, ctx)
+        return cls.from_dense(M, ctx)
+
+    # -- operations ----------------------------------------------------------
+    def transpose(self) -> "DeviceMatrix":
+        h = C.c_void_p()
+        check(self.ctx._lib.hg_matrix_transpose(self.ctx._h, self._h, C.byref(h)))
+        return DeviceMatrix(h, self.ctx)
+
+    def download(self):
+        """Return ``(indptr[int64], indices[int32], data[float64])``."""
+        indptr = np.empty(self.shape[0] + 1, dtype=np.int64)
+        indices = np.empty(self.nnz, dtype=np.int32)
+        data = np.empty(self.nnz, dtype=np.float64)
+        check(self.ctx._lib.hg_matrix_download_csr(self.ctx._h, self._h, _ptr(indptr), _ptr(indices), _ptr(data)))
+        return indptr, indices, data
+
+    def matvec(self, x):
+        x = _vec(x, self.shape[1], "x")
+        y = np.empty(self.shape[0])
+        check(self.ctx._lib.hg_spmv(self.ctx._h, self._h, _ptr(x), _ptr(y)))
+        return y
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.hg_matrix_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Uploaded:
+    """Uploads host matrices for the duration of one solver call."""
+
+    def __init__(self, ctx, *mats):
+        self.ctx = ctx
+        self.owned = []
+        self.out = []
+        for M in mats:
+            if M is None or isinstance(M, DeviceMatrix):
+                self.out.append(M)
+            else:
+                d = DeviceMatrix.from_any(M, ctx)
+                self.owned.append(d)
+                self.out.append(d)
+
+    def __enter__(self):
+        return self.out
+
+    def __exit__(self, *exc):
+        for d in self.owned:
+            d.close()
+        return False
+
+
+def _ctx_of(ctx, *mats):
+    if ctx is not None:
+        return ctx
+    for M in mats:
+        if isinstance(M, DeviceMatrix):
+            return M.ctx
+    return default_context()
+
+
+def _extras(maxit, n, want, want_x=True, aux=False):
+    if not want:
+        return None, None
+    bufs = {"H": np.zeros((maxit + 1, maxit), order="F"), "beta": np.zeros(1)}
+    ex = HgExtras()
+    ex.H = bufs["H"].ctypes.data_as(_lib.c_double_p)
+    ex.beta = bufs["beta"].ctypes.data_as(_lib.c_double_p)
+    if want_x:
+        bufs["X"] = np.zeros((n, maxit), order="F")
+        ex.X_hist = bufs["X"].ctypes.data_as(_lib.c_double_p)
+    if aux:
+        bufs["aux"] = np.zeros(2 * (maxit + 1))
+        ex.aux = bufs["aux"].ctypes.data_as(_lib.c_double_p)
+    return ex, bufs
+
+
+def _rtp(fn_name, A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras):
+    ctx = _ctx_of(ctx, A, B)
+    maxit = int(maxit)
+    with _Uploaded(ctx, A, B) as (dA, dB):
+        m, n = dA.shape
+        b = _vec(b, m, "b")
+        x_true = _vec(x_true, n, "x_true")
+        x = np.zeros(n)
+        err = np.zeros(maxit)
+        res = np.zeros(maxit)
+        niters, x_valid = C.c_int(), C.c_int()
+        opts = HgSolverOpts()
+        opts.residual_mode = int(residual_mode)
+        ex, bufs = _extras(maxit, n, extras is not None)
+        check(getattr(ctx._lib, fn_name)(ctx._h, dA._h, dB._h, _ptr(b), _ptr(x_true), float(tol), maxit,
+                                         float(lam), _ptr(x), _ptr(err), _ptr(res), C.byref(niters),
+                                         C.byref(x_valid), C.byref(opts), C.byref(ex) if ex else None))
+    k = niters.value
+    if extras is not None:
+        extras.update(H=bufs["H"], beta=float(bufs["beta"][0]), X=bufs["X"][:, :k])
+    return (x if x_valid.value else None), err[:k], res[:k], k
+
+
+def hybrid_ab_gmres_rtp(A, B, b, x_true, tol, maxit, lam, *, ctx=None, residual_mode=0, extras=None):
+    """``hybrid_ab_gmres_rtp.m:1`` — same positional arguments and outputs.
+    ``x`` is ``None`` exactly when the reference leaves it unassigned (``:25``)."""
+    return _rtp("hg_hybrid_ab_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras)
+
+
+def hybrid_ba_gmres_rtp(A, B, b, x_true, tol, maxit, lam, *, ctx=None, residual_mode=0, extras=None):
+    """``hybrid_ba_gmres_rtp.m:1`` — same positional arguments and outputs."""
+    return _rtp("hg_hybrid_ba_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras)
+
+
+def _gkb(fn_name, A, b, x_true, tol, maxit, lam, ctx, At, extras, five_outputs=False):
+    ctx = _ctx_of(ctx, A, At)
+    with _Uploaded(ctx, A, At) as (dA, dAt):
+        m, n = dA.shape
+        if maxit is None:
+            maxit = min(m, n)  # lsmr_solver.m:5
+        maxit = int(maxit)
+        b = _vec(b, m, "b")
+        have_true = x_true is not None and np.size(x_true) > 0
+        xt = _vec(x_true, n, "x_true") if have_true else None
+        x = np.zeros(n)
+        err = np.zeros(maxit)
+        res = np.zeros(maxit)
+        ar = np.zeros(maxit)
+        niters = C.c_int()
+        ex, bufs = _extras(maxit, n, extras is not None, aux=True)
+        at_h = dAt._h if dAt is not None else None
+        f = getattr(ctx._lib, fn_name)
+        exr = C.byref(ex) if ex else None
+        if five_outputs:
+            check(f(ctx._h, dA._h, at_h, _ptr(b), _ptr(xt), float(tol), maxit, _ptr(x), _ptr(err), _ptr(res),
+                    _ptr(ar), C.byref(niters), exr))
+        elif lam is None:
+            if not have_true:
+                raise ValueError("x_true is required")
+            check(f(ctx._h, dA._h, at_h, _ptr(b), _ptr(xt), float(tol), maxit, _ptr(x), _ptr(err), _ptr(res),
+                    C.byref(niters), exr))
+        else:
+            if not have_true:
+                raise ValueError("x_true is required")
+            check(f(ctx._h, dA._h, at_h, _ptr(b), _ptr(xt), float(tol), maxit, float(lam), _ptr(x), _ptr(err),
+                    _ptr(res), C.byref(niters), exr))
+    k = niters.value
+    if extras is not None:
+        extras.update(X=bufs["X"][:, :k], aux=bufs["aux"])
+    if five_outputs:
+        return x, err[:k], res[:k], ar[:k], k
+    return x, err[:k], res[:k], k
+
+
+def hybrid_lsqr_solver(A, b, x_true, tol, maxit, lam, *, ctx=None, At=None, extras=None):
+    """``hybrid_lsqr_solver.m:1``.  ``At`` optionally passes an already
+    uploaded ``A'`` (MATLAB's CSC of ``A`` is the CSR of ``A'``)."""
+    return _gkb("hg_hybrid_lsqr_solver", A, b, x_true, tol, maxit, lam, ctx, At, extras)
+
+
+def hybrid_lsmr_solver(A, b, x_true, tol, maxit, lam, *, ctx=None, At=None, extras=None):
+    """``hybrid_lsmr_solver.m:1``."""
+    return _gkb("hg_hybrid_lsmr_solver", A, b, x_true, tol, maxit, lam, ctx, At, extras)
+
+
+def lsqr_solver(A, b, x_true, tol, maxit, *, ctx=None, At=None, extras=None):
+    """``lsqr_solver.m:1``."""
+    return _gkb("hg_lsqr_solver", A, b, x_true, tol, maxit, None, ctx, At, extras)
+
+
+def lsmr_solver(A, b, x_true=None, tol=None, maxit=None, *, ctx=None, At=None, extras=None):
+    """``lsmr_solver.m:1`` — five outputs ``(x, err_hist, res_hist, ar_hist,
+    iters)``; ``tol`` defaults to 1e-6 and ``maxit`` to ``min(m,n)`` (``:3-5``)."""
+    if tol is None:
+        tol = 1e-6
+    return _gkb("hg_lsmr_solver", A, b, x_true, tol, maxit, None, ctx, At, extras, five_outputs=True)
+
+
+# ---------------------------------------------------------------------------
+# Arnoldi handle (device-resident; used by the bench and the parity tests)
+# ---------------------------------------------------------------------------
+class Arnoldi:
+    """``hg_arnoldi``: CGS2 Arnoldi on ``B*A + shift*I`` (space 'n') or
+    ``A*B + shift*I`` (space 'm') with everything resident in HBM."""
+
+    def __init__(self, A: DeviceMatrix, B: DeviceMatrix, space: str, kmax: int):
+        self.ctx = A.ctx
+        self.A, self.B = A, B  # keep the matrices alive
+        self.kmax = int(kmax)
+        h = C.c_void_p()
+        check(self.ctx._lib.hg_arnoldi_create(self.ctx._h, A._h, B._h, 0 if space == "n" else 1, self.kmax,
+                                              C.byref(h)))
+        self._h = h
+        self.dim = A.shape[1] if space == "n" else A.shape[0]
+
+    def set_rhs(self, b):
+        b = _vec(b, self.A.shape[0], "b")
+        check(self.ctx._lib.hg_arnoldi_set_rhs(self._h, _ptr(b)))
+
+    def reset(self, shift: float):
+        check(self.ctx._lib.hg_arnoldi_reset(self._h, float(shift)))
+
+    def steps(self, n: int):
+        check(self.ctx._lib.hg_arnoldi_steps(self._h, int(n)))
+
+    def get(self):
+        H = np.zeros((self.kmax + 1, self.kmax), order="F")
+        beta = C.c_double()
+        k = C.c_int()
+        check(self.ctx._lib.hg_arnoldi_get(self._h, _ptr(H), self.kmax + 1, C.byref(beta), C.byref(k)))
+        return H, beta.value, k.value
+
+    def q(self, j: int):
+        q = np.empty(self.dim)
+        check(self.ctx._lib.hg_arnoldi_get_q(self._h, int(j), _ptr(q)))
+        return q
+
+    def step_bytes(self, k: int) -> float:
+        out = C.c_double()
+        check(self.ctx._lib.hg_arnoldi_step_bytes(self._h, int(k), C.byref(out)))
+        return out.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.hg_arnoldi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------
+# gcv_function
+# ---------------------------------------------------------------------------
+class GcvProblem:
+    """The lambda-independent Arnoldi of ``gcv_function.m:4-32`` run once on the
+    device; :meth:`eval` is the projected part (``:33-58``)."""
+
+    def __init__(self, handle, lib):
+        self._h = handle
+        self._lib = lib
+
+    @classmethod
+    def from_H(cls, H, beta, trace_m):
+        lib = _lib.load()
+        H = np.asfortranarray(np.asarray(H, dtype=np.float64))
+        k = H.shape[1]
+        if H.shape[0] != k + 1:
+            raise ValueError("H must be (k+1) x k")
+        h = C.c_void_p()
+        check(lib.hg_gcv_from_H(_ptr(H), k + 1, k, float(beta), float(trace_m), C.byref(h)))
+        return cls(h, lib)
+
+    def eval(self, lam: float) -> float:
+        out = C.c_double()
+        check(self._lib.hg_gcv_eval(self._h, float(lam), C.byref(out)))
+        return out.value
+
+    def get(self, k: int):
+        H = np.zeros((k + 1, k), order="F")
+        beta = C.c_double()
+        check(self._lib.hg_gcv_get(self._h, _ptr(H), C.byref(beta)))
+        return H, beta.value
+
+    def fminbnd(self, lo, hi, tolx=1e-4, trace_cap=600):
+        """MATLAB ``fminbnd(@(l) gcv_function(l,...), lo, hi, optimset('TolX',tolx))``.
+        Returns ``(lambda, fval, funccount, trace)``."""
+        lam, fval, cnt = C.c_double(), C.c_double(), C.c_int()
+        trace = np.zeros(trace_cap)
+        check(self._lib.hg_gcv_fminbnd(self._h, float(lo), float(hi), float(tolx), C.byref(lam), C.byref(fval),
+                                       C.byref(cnt), _ptr(trace), trace_cap))
+        return lam.value, fval.value, cnt.value, trace[: min(cnt.value, trace_cap)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hg_gcv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gcv_prepare(A, B, b, m, k_gcv, gcv_type, *, ctx=None) -> GcvProblem:
+    ctx = _ctx_of(ctx, A, B)
+    t = {"ab": 0, "ba": 1}[gcv_type]
+    with _Uploaded(ctx, A, B) as (dA, dB):
+        b = _vec(b, dA.shape[0], "b")
+        h = C.c_void_p()
+        check(ctx._lib.hg_gcv_prepare(ctx._h, dA._h, dB._h, _ptr(b), int(m), int(k_gcv), t, C.byref(h)))
+    return GcvProblem(h, ctx._lib)
+
+
+_gcv_cache: dict = {}
+_GCV_CACHE_MAX = 8
+
+
+def gcv_function(lam, A, B, b, m, k_gcv, gcv_type, *, ctx=None):
+    """``gcv_val = gcv_function(lambda,A,B,b,m,k_gcv,gcv_type)`` (``gcv_function.m:1``).
+
+    ``fminbnd`` calls this ~30 times with the same ``(A,B,b,m,k_gcv,gcv_type)``;
+    the device Arnoldi is memoised on the identity of ``A``/``B`` and the bytes
+    of ``b`` so it runs once (the MEX gateway does the same)."""
+    b_arr = np.ascontiguousarray(np.asarray(b, dtype=np.float64).reshape(-1))
+    key = (id(A), id(B), hash(b_arr.tobytes()), int(m), int(k_gcv), gcv_type)
+    hit = _gcv_cache.get(key)
+    if hit is not None and hit[1]() is A and hit[2]() is B:
+        return hit[0].eval(lam)
+    prob = gcv_prepare(A, B, b_arr, m, k_gcv, gcv_type, ctx=ctx)
+    try:
+        entry = (prob, weakref.ref(A), weakref.ref(B))
+    except TypeError:  # numpy arrays / objects without weakref support: hold a strong ref
+        entry = (prob, (lambda o=A: o), (lambda o=B: o))
+    if len(_gcv_cache) >= _GCV_CACHE_MAX:
+        _gcv_cache.pop(next(iter(_gcv_cache)))
+    _gcv_cache[key] = entry
+    return prob.eval(lam)
+
+
+def fminbnd_gcv(A, B, b, m, k_gcv, gcv_type, lo=1e-9, hi=1e-1, tolx=1e-8, *, ctx=None):
+    """``fminbnd(@(l) gcv_function(l,A,B,b,m,k_gcv,type), lo, hi, optimset('TolX',tolx))``
+    as used at ``analyze_regularization.m:37-46``.  Returns ``(lambda, fval, funccount)``."""
+    prob = gcv_prepare(A, B, b, m, k_gcv, gcv_type, ctx=ctx)
+    lam, fval, cnt, _ = prob.fminbnd(lo, hi, tolx)
+    prob.close()
+    return lam, fval, cnt

@@ -1,0 +1,574 @@
+// Device Arnoldi (CGS2) and the solvers built on it:
+//   hybrid_ab_gmres_rtp.m, hybrid_ba_gmres_rtp.m, gcv_function.m
+#include <algorithm>
+#include <memory>
+
+#include "common.cuh"
+#include "dense_host.h"
+
+int hg_multidot_nslabs(const hg_ctx* ctx, int64_t n);
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+struct hg_arnoldi {
+    hg_ctx* ctx = nullptr;
+    const hg_matrix* A = nullptr;
+    const hg_matrix* B = nullptr;
+    const hg_matrix* M1 = nullptr;  // applied first
+    const hg_matrix* M2 = nullptr;  // applied second; basis lives in rows(M2)
+    int space = HG_SPACE_N;
+    int kmax = 0;
+    int64_t nq = 0, nt = 0, ldq = 0, ldt = 0, mb = 0;
+    bool store_t = false;
+    double* Q = nullptr;   // nq x (kmax+1)
+    double* T = nullptr;   // n-space: m x (kmax+1), column 0 = b, column k = A*q_k
+                           // m-space: one scratch column of length n
+    double* d_b = nullptr; // m-space: b (length m); n-space: alias of T column 0
+    double* w0 = nullptr;
+    double* w1 = nullptr;
+    double* d_H = nullptr;  // (kmax+1) x kmax, ld = kmax+1
+    double* d_hcur = nullptr;
+    double* d_beta = nullptr;
+    double* h_H = nullptr;  // pinned mirror
+    double* h_beta = nullptr;
+    double* partials = nullptr;  // multidot partials
+    double* stat = nullptr;      // norm partials
+    double shift = 0.0;
+    int k = 0;
+    bool have_rhs = false, started = false;
+    int ldh() const { return kmax + 1; }
+};
+
+extern "C" int hg_arnoldi_destroy(hg_arnoldi* a) {
+    if (!a) return HG_OK;
+    cudaStreamSynchronize(a->ctx->stream);
+    cudaFree(a->Q);
+    cudaFree(a->T);
+    if (a->space == HG_SPACE_M) cudaFree(a->d_b);
+    cudaFree(a->w0);
+    cudaFree(a->w1);
+    cudaFree(a->d_H);
+    cudaFree(a->d_hcur);
+    cudaFree(a->d_beta);
+    cudaFree(a->partials);
+    cudaFree(a->stat);
+    if (a->h_H) cudaFreeHost(a->h_H);
+    if (a->h_beta) cudaFreeHost(a->h_beta);
+    delete a;
+    return HG_OK;
+}
+
+extern "C" int hg_arnoldi_create(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, int space,
+                                 int kmax, hg_arnoldi** out) {
+    HG_REQUIRE(ctx && A && B && out, "hg_arnoldi_create: NULL argument");
+    HG_REQUIRE(space == HG_SPACE_N || space == HG_SPACE_M, "hg_arnoldi_create: bad space");
+    HG_REQUIRE(kmax >= 1, "hg_arnoldi_create: kmax must be >= 1");
+    HG_REQUIRE(A->rows == B->cols && A->cols == B->rows,
+               "hg_arnoldi_create: B must be n x m for A m x n (A %lld x %lld, B %lld x %lld)",
+               (long long)A->rows, (long long)A->cols, (long long)B->rows, (long long)B->cols);
+    HG_CUDA(cudaSetDevice(ctx->device));
+    *out = nullptr;
+    hg_arnoldi* a = new (std::nothrow) hg_arnoldi();
+    if (!a) {
+        hg_set_error("hg_arnoldi_create: out of host memory");
+        return HG_ERR_NOMEM;
+    }
+    a->ctx = ctx;
+    a->A = A;
+    a->B = B;
+    a->space = space;
+    a->kmax = kmax;
+    a->mb = A->rows;
+    if (space == HG_SPACE_N) {
+        a->M1 = A;
+        a->M2 = B;
+        a->store_t = true;
+    } else {
+        a->M1 = B;
+        a->M2 = A;
+        a->store_t = false;
+    }
+    a->nq = a->M2->rows;
+    a->nt = a->M1->rows;
+    a->ldq = round_up(std::max<int64_t>(a->nq, 1), 32);
+    a->ldt = round_up(std::max<int64_t>(a->nt, 1), 32);
+    const int nslabs = hg_multidot_nslabs(ctx, std::max(a->nq, a->nt));
+    const size_t npart = (size_t)(kmax + 2) * (size_t)(nslabs + 1);
+    const size_t nstat = (size_t)std::max(a->nq, a->nt) / 8 + 1024;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](double** p, size_t n) {
+        if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(n, 1) * sizeof(double));
+    };
+    alloc(&a->Q, (size_t)a->ldq * (kmax + 1));
+    alloc(&a->T, a->store_t ? (size_t)a->ldt * (kmax + 1) : (size_t)a->ldt);
+    if (space == HG_SPACE_M) alloc(&a->d_b, (size_t)a->mb);
+    else a->d_b = a->T;
+    alloc(&a->w0, (size_t)a->ldq);
+    alloc(&a->w1, (size_t)a->ldq);
+    alloc(&a->d_H, (size_t)a->ldh() * kmax);
+    alloc(&a->d_hcur, (size_t)kmax + 1);
+    alloc(&a->d_beta, 8);
+    alloc(&a->partials, npart);
+    alloc(&a->stat, nstat);
+    if (e == cudaSuccess) e = cudaMallocHost(&a->h_H, (size_t)a->ldh() * kmax * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost(&a->h_beta, 8 * sizeof(double));
+    if (e != cudaSuccess) {
+        hg_set_error("hg_arnoldi_create: allocation failed (basis %lld x %d): %s",
+                     (long long)a->nq, kmax + 1, cudaGetErrorString(e));
+        hg_arnoldi_destroy(a);
+        return HG_ERR_NOMEM;
+    }
+    // padding rows of Q/T are never read by the kernels (all loops are bounded by n)
+    *out = a;
+    return HG_OK;
+}
+
+// device-resident rhs (no host copy): used by the solvers and the bench
+int hg_arnoldi_set_rhs_device(hg_arnoldi* a, const double* d_b) {
+    HG_CUDA(cudaMemcpyAsync(a->d_b, d_b, (size_t)a->mb * 8, cudaMemcpyDeviceToDevice, a->ctx->stream));
+    a->have_rhs = true;
+    return HG_OK;
+}
+
+extern "C" int hg_arnoldi_set_rhs(hg_arnoldi* a, const double* b) {
+    HG_REQUIRE(a && b, "hg_arnoldi_set_rhs: NULL argument");
+    HG_CUDA(cudaSetDevice(a->ctx->device));
+    HG_CUDA(cudaMemcpyAsync(a->d_b, b, (size_t)a->mb * 8, cudaMemcpyHostToDevice, a->ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(a->ctx->stream));  // caller may free b
+    a->have_rhs = true;
+    return HG_OK;
+}
+
+extern "C" int hg_arnoldi_reset(hg_arnoldi* a, double shift) {
+    HG_REQUIRE(a, "hg_arnoldi_reset: NULL");
+    if (!a->have_rhs) {
+        hg_set_error("hg_arnoldi_reset: right-hand side not set");
+        return HG_ERR_STATE;
+    }
+    hg_ctx* ctx = a->ctx;
+    HG_CUDA(cudaSetDevice(ctx->device));
+    a->shift = shift;
+    a->k = 0;
+    // reuse of the pinned mirror: make sure earlier async copies have landed
+    HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    memset(a->h_H, 0, (size_t)a->ldh() * a->kmax * sizeof(double));
+    HG_CUDA(cudaMemsetAsync(a->d_H, 0, (size_t)a->ldh() * a->kmax * sizeof(double), ctx->stream));
+    double* q0 = a->Q;
+    if (a->space == HG_SPACE_N) {
+        // r0 = B*b - M(0) = B*b      (hybrid_ba_gmres_rtp.m:7-9; gcv_function.m:8)
+        hg_spmv_epilogue ep;
+        HG_TRY(hg_k_spmv(ctx, a->B, a->d_b, q0, ep, nullptr));
+    } else {
+        // r0 = b                      (gcv_function.m:5)
+        HG_CUDA(cudaMemcpyAsync(q0, a->d_b, (size_t)a->nq * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    int np = 0;
+    HG_TRY(hg_k_sumsq(ctx, q0, a->nq, a->stat, &np));
+    HG_TRY(hg_k_reduce(ctx, a->stat, np, 1, a->d_beta, false, nullptr, true));  // beta = norm(r0)
+    HG_TRY(hg_k_scale_div(ctx, q0, a->nq, a->d_beta));                          // Q(:,1) = r0/beta
+    HG_CUDA(cudaMemcpyAsync(a->h_beta, a->d_beta, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    a->started = true;
+    return HG_OK;
+}
+
+// one CGS2 Arnoldi step; kk is the 1-based column being produced
+static int arnoldi_step(hg_arnoldi* a, int kk) {
+    hg_ctx* ctx = a->ctx;
+    const double* q = a->Q + (size_t)(kk - 1) * a->ldq;
+    double* tcol = a->store_t ? a->T + (size_t)kk * a->ldt : a->T;
+    double* qnext = a->Q + (size_t)kk * a->ldq;
+    double* Hcol = a->d_H + (size_t)(kk - 1) * a->ldh();
+    // v = M2*(M1*q) + shift*q          (hybrid_ab_gmres_rtp.m:6,19; gcv_function.m:20,22)
+    {
+        hg_spmv_epilogue ep;
+        HG_TRY(hg_k_spmv(ctx, a->M1, q, tcol, ep, nullptr));
+    }
+    {
+        hg_spmv_epilogue ep;
+        if (a->shift != 0.0) {
+            ep.z1 = q;
+            ep.g1 = a->shift;
+        }
+        HG_TRY(hg_k_spmv(ctx, a->M2, tcol, a->w0, ep, nullptr));
+    }
+    // CGS2: h1 = Q_k' v ; v -= Q_k h1 ; h2 = Q_k' v ; v -= Q_k h2 ; H(1:k,k) = h1 + h2
+    // (the reference's MGS sweep, hybrid_ab_gmres_rtp.m:20-23, in its two-pass
+    //  classical form mandated by the north star)
+    int ns = 0, np = 0;
+    HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->nq, kk, a->w0, a->partials, &ns));
+    HG_TRY(hg_k_reduce(ctx, a->partials, ns, kk, Hcol, false, a->d_hcur, false));
+    HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr,
+                        nullptr, nullptr));
+    HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->nq, kk, a->w1, a->partials, &ns));
+    HG_TRY(hg_k_reduce(ctx, a->partials, ns, kk, Hcol, true, a->d_hcur, false));
+    HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, -1.0, a->w1, qnext, nullptr,
+                        a->stat, &np));
+    // H(k+1,k) = norm(v) ; Q(:,k+1) = v / H(k+1,k)       (:24,26)
+    HG_TRY(hg_k_reduce(ctx, a->stat, np, 1, Hcol + kk, false, nullptr, true));
+    HG_TRY(hg_k_scale_div(ctx, qnext, a->nq, Hcol + kk));
+    HG_CUDA(cudaMemcpyAsync(a->h_H + (size_t)(kk - 1) * a->ldh(), Hcol, (size_t)(kk + 1) * 8,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    return HG_OK;
+}
+
+extern "C" int hg_arnoldi_steps(hg_arnoldi* a, int nsteps) {
+    HG_REQUIRE(a, "hg_arnoldi_steps: NULL");
+    if (!a->started) {
+        hg_set_error("hg_arnoldi_steps: call hg_arnoldi_reset first");
+        return HG_ERR_STATE;
+    }
+    HG_REQUIRE(nsteps >= 0 && a->k + nsteps <= a->kmax, "hg_arnoldi_steps: %d steps from k=%d exceeds kmax=%d",
+               nsteps, a->k, a->kmax);
+    HG_CUDA(cudaSetDevice(a->ctx->device));
+    for (int i = 0; i < nsteps; ++i) {
+        HG_TRY(arnoldi_step(a, a->k + 1));
+        a->k += 1;
+    }
+    return HG_OK;
+}
+
+extern "C" int hg_arnoldi_get(hg_arnoldi* a, double* H, int ldh, double* beta, int* ksteps) {
+    HG_REQUIRE(a, "hg_arnoldi_get: NULL");
+    HG_CUDA(cudaStreamSynchronize(a->ctx->stream));
+    if (H) {
+        HG_REQUIRE(ldh >= a->ldh(), "hg_arnoldi_get: ldh too small");
+        for (int j = 0; j < a->kmax; ++j)
+            memcpy(H + (size_t)j * ldh, a->h_H + (size_t)j * a->ldh(), (size_t)a->ldh() * 8);
+    }
+    if (beta) *beta = a->h_beta[0];
+    if (ksteps) *ksteps = a->k;
+    return HG_OK;
+}
+
+extern "C" int hg_arnoldi_get_q(hg_arnoldi* a, int j, double* q) {
+    HG_REQUIRE(a && q, "hg_arnoldi_get_q: NULL");
+    HG_REQUIRE(j >= 0 && j <= a->kmax, "hg_arnoldi_get_q: column out of range");
+    HG_CUDA(cudaMemcpyAsync(q, a->Q + (size_t)j * a->ldq, (size_t)a->nq * 8, cudaMemcpyDeviceToHost,
+                            a->ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(a->ctx->stream));
+    return HG_OK;
+}
+
+extern "C" int hg_arnoldi_step_bytes(hg_arnoldi* a, int k, double* bytes) {
+    HG_REQUIRE(a && bytes, "hg_arnoldi_step_bytes: NULL");
+    // S(k) = 12(nnzA+nnzB) + pw(m+n+2) + 16 m + 88 n + 32 k n  (n-space;
+    // m-space swaps the vector terms), pw = 8.
+    const double nq = (double)a->nq, nt = (double)a->nt;
+    *bytes = 12.0 * ((double)a->A->nnz + (double)a->B->nnz) + 8.0 * (nq + nt + 2.0) + 16.0 * nt +
+             88.0 * nq + 32.0 * (double)k * nq;
+    return HG_OK;
+}
+
+// ===========================================================================
+// RTP solvers
+// ===========================================================================
+namespace {
+
+struct DBuf {
+    double* p = nullptr;
+    ~DBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t n) {
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double));
+        if (e != cudaSuccess) {
+            hg_set_error("device allocation of %zu doubles failed: %s", n, cudaGetErrorString(e));
+            return HG_ERR_NOMEM;
+        }
+        return HG_OK;
+    }
+};
+
+struct PinBuf {
+    double* p = nullptr;
+    ~PinBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    int alloc(size_t n) {
+        cudaError_t e = cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(double));
+        if (e != cudaSuccess) {
+            hg_set_error("pinned allocation of %zu doubles failed: %s", n, cudaGetErrorString(e));
+            return HG_ERR_NOMEM;
+        }
+        return HG_OK;
+    }
+};
+
+struct ArnoldiHolder {
+    hg_arnoldi* a = nullptr;
+    ~ArnoldiHolder() { hg_arnoldi_destroy(a); }
+};
+
+enum RtpKind { RTP_AB, RTP_BA };
+
+int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, const double* b,
+               const double* x_true, double tol, int maxit, double lambda, double* x,
+               double* error_norm, double* residual_norm, int* niters, int* x_valid,
+               const hg_solver_opts* opts, hg_extras* extras) {
+    HG_REQUIRE(ctx && A && B && b && x_true && x && error_norm && residual_norm && niters,
+               "rtp solver: NULL argument");
+    HG_REQUIRE(maxit >= 1, "rtp solver: maxit must be >= 1");
+    HG_CUDA(cudaSetDevice(ctx->device));
+    const int residual_mode = opts ? opts->residual_mode : 0;
+    const int64_t n = A->cols, m = A->rows;
+    ArnoldiHolder holder;
+    HG_TRY(hg_arnoldi_create(ctx, A, B, HG_SPACE_N, maxit, &holder.a));
+    hg_arnoldi* a = holder.a;
+    DBuf d_x, d_xt, d_y, d_g, stat_e, stat_r;
+    PinBuf h_y, h_g, h_s;
+    HG_TRY(d_x.alloc((size_t)n));
+    HG_TRY(d_xt.alloc((size_t)n));
+    HG_TRY(d_y.alloc((size_t)maxit + 1));
+    HG_TRY(d_g.alloc((size_t)maxit + 2));
+    HG_TRY(stat_e.alloc((size_t)std::max(n, m) / 8 + 1024));
+    HG_TRY(stat_r.alloc((size_t)std::max(n, m) / 8 + 1024));
+    HG_TRY(h_y.alloc((size_t)maxit + 1));
+    HG_TRY(h_g.alloc((size_t)maxit + 2));
+    HG_TRY(h_s.alloc(8));
+    HG_CUDA(cudaMemsetAsync(d_x.p, 0, (size_t)n * 8, ctx->stream));
+    HG_CUDA(cudaMemcpyAsync(d_xt.p, x_true, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    HG_TRY(hg_arnoldi_set_rhs(a, b));
+    double nb2 = 0, nx2 = 0;
+    HG_TRY(hg_norm2_sync(ctx, a->d_b, m, &nb2));
+    HG_TRY(hg_norm2_sync(ctx, d_xt.p, n, &nx2));
+    const double norm_b = std::sqrt(nb2), norm_xt = std::sqrt(nx2);
+    HG_TRY(hg_arnoldi_reset(a, lambda));
+    HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double beta = a->h_beta[0];
+
+    for (int i = 0; i < maxit; ++i) error_norm[i] = residual_norm[i] = 0.0;
+    hgd::HessenbergLS ls;
+    hgd::BorderedCholesky chol;
+    std::vector<double> Gfull, rhs;
+    bool chol_ok = true;
+    if (kind == RTP_BA) ls.reset(maxit, beta);
+    else {
+        chol.reset(maxit, lambda);
+        Gfull.assign((size_t)maxit * maxit, 0.0);
+        rhs.assign(maxit, 0.0);
+    }
+    bool have_x = (kind == RTP_BA);  // BA initialises x = zeros (hybrid_ba_gmres_rtp.m:4)
+    int k = 0;
+    const int ldh = a->ldh();
+    for (k = 1; k <= maxit; ++k) {
+        HG_TRY(hg_arnoldi_steps(a, 1));
+        if (kind == RTP_AB) {
+            // Gram column of W = A*Q_k against [b, W]: one stream over the cached columns
+            // replaces `AQk = A*Qk; AQk'*AQk; AQk'*b` (hybrid_ab_gmres_rtp.m:31-32)
+            int ns = 0;
+            HG_TRY(hg_k_multidot(ctx, a->T, a->ldt, m, k + 1, a->T + (size_t)k * a->ldt, a->partials, &ns));
+            HG_TRY(hg_k_reduce(ctx, a->partials, ns, k + 1, d_g.p, false, nullptr, false));
+            HG_CUDA(cudaMemcpyAsync(h_g.p, d_g.p, (size_t)(k + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        HG_CUDA(cudaStreamSynchronize(ctx->stream));
+        const double* hcol = a->h_H + (size_t)(k - 1) * ldh;
+        if (hcol[k] == 0.0) break;  // :25 — leaves before x / histories are touched
+        if (kind == RTP_BA) {
+            ls.add_column(hcol);  // yk = H(1:k+1,1:k) \ [beta;0]   (hybrid_ba_gmres_rtp.m:28-29)
+            ls.solve(h_y.p);
+        } else {
+            rhs[k - 1] = h_g.p[0];
+            for (int j = 0; j < k; ++j) {
+                Gfull[(size_t)(k - 1) * maxit + j] = h_g.p[1 + j];
+                Gfull[(size_t)j * maxit + (k - 1)] = h_g.p[1 + j];
+            }
+            if (chol_ok) chol_ok = chol.add_row(h_g.p + 1);
+            if (chol_ok) {
+                chol.solve(rhs.data(), h_y.p);
+            } else {  // mldivide's non-SPD path
+                std::vector<double> M((size_t)k * k);
+                for (int j = 0; j < k; ++j)
+                    for (int i2 = 0; i2 < k; ++i2)
+                        M[(size_t)j * k + i2] = Gfull[(size_t)j * maxit + i2] + (i2 == j ? lambda : 0.0);
+                hgd::solve_square(k, M.data(), k, rhs.data(), h_y.p);
+            }
+        }
+        HG_CUDA(cudaMemcpyAsync(d_y.p, h_y.p, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+        // x = Q(:,1:k)*yk fused with ||x - x_true||^2          (:33,36 / :30,33)
+        int np_e = 0, np_r = 0;
+        HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n, k, d_y.p, 1.0, nullptr, d_x.p, d_xt.p, stat_e.p, &np_e));
+        if (residual_mode == 0) {
+            // ||b - A*x|| with A*x = (A*Q_k) yk from the cached columns
+            HG_TRY(hg_k_lincomb(ctx, a->T + a->ldt, a->ldt, m, k, d_y.p, -1.0, a->d_b, nullptr, nullptr,
+                                stat_r.p, &np_r));
+        } else {
+            hg_spmv_epilogue ep;  // literal: norm(b - A*x)       (:35 / :32)
+            ep.alpha = -1.0;
+            ep.z1 = a->d_b;
+            ep.g1 = 1.0;
+            ep.stat = stat_r.p;
+            HG_TRY(hg_k_spmv(ctx, A, d_x.p, nullptr, ep, &np_r));
+        }
+        HG_TRY(hg_k_reduce(ctx, stat_e.p, np_e, 1, ctx->d_scalars + 1, false, nullptr, true));
+        HG_TRY(hg_k_reduce(ctx, stat_r.p, np_r, 1, ctx->d_scalars + 2, false, nullptr, true));
+        HG_CUDA(cudaMemcpyAsync(h_s.p, ctx->d_scalars + 1, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (extras && extras->X_hist)
+            HG_CUDA(cudaMemcpyAsync(extras->X_hist + (size_t)(k - 1) * n, d_x.p, (size_t)n * 8,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+        HG_CUDA(cudaStreamSynchronize(ctx->stream));
+        have_x = true;
+        residual_norm[k - 1] = h_s.p[1] / norm_b;
+        error_norm[k - 1] = h_s.p[0] / norm_xt;
+        if (residual_norm[k - 1] <= tol) break;  // :38 / :35
+    }
+    if (k > maxit) k = maxit;  // MATLAB leaves k at its last value
+    *niters = k;
+    HG_CUDA(cudaMemcpyAsync(x, d_x.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (x_valid) *x_valid = have_x ? 1 : 0;
+    if (extras) {
+        if (extras->beta) *extras->beta = beta;
+        if (extras->H) memcpy(extras->H, a->h_H, (size_t)ldh * maxit * 8);
+    }
+    return HG_OK;
+}
+
+}  // namespace
+
+extern "C" int hg_hybrid_ab_gmres_rtp(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B,
+                                      const double* b, const double* x_true, double tol, int maxit,
+                                      double lambda, double* x, double* error_norm,
+                                      double* residual_norm, int* niters, int* x_valid,
+                                      const hg_solver_opts* opts, hg_extras* extras) {
+    return rtp_solver(RTP_AB, ctx, A, B, b, x_true, tol, maxit, lambda, x, error_norm, residual_norm,
+                      niters, x_valid, opts, extras);
+}
+
+extern "C" int hg_hybrid_ba_gmres_rtp(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B,
+                                      const double* b, const double* x_true, double tol, int maxit,
+                                      double lambda, double* x, double* error_norm,
+                                      double* residual_norm, int* niters, int* x_valid,
+                                      const hg_solver_opts* opts, hg_extras* extras) {
+    return rtp_solver(RTP_BA, ctx, A, B, b, x_true, tol, maxit, lambda, x, error_norm, residual_norm,
+                      niters, x_valid, opts, extras);
+}
+
+// ===========================================================================
+// gcv_function
+// ===========================================================================
+struct hg_gcv {
+    int k = 0;
+    double beta = 0.0;
+    double trace_m = 0.0;
+    std::vector<double> H;   // (k+1) x k
+    std::vector<double> sv;  // singular values of H(1:k,1:k)
+};
+
+static void gcv_fill_sv(hg_gcv* g);
+
+extern "C" int hg_gcv_prepare(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, const double* b,
+                              int64_t m, int k_gcv, int gcv_type, hg_gcv** out) {
+    HG_REQUIRE(ctx && A && B && b && out, "hg_gcv_prepare: NULL argument");
+    HG_REQUIRE(gcv_type == 0 || gcv_type == 1, "hg_gcv_prepare: gcv_type must be 0 ('ab') or 1 ('ba')");
+    HG_REQUIRE(k_gcv >= 1, "hg_gcv_prepare: k_gcv must be >= 1");
+    HG_REQUIRE(gcv_type == 1 || m == A->rows,
+               "hg_gcv_prepare: m (%lld) must equal size(A,1) (%lld) for 'ab' (gcv_function.m:6,13)",
+               (long long)m, (long long)A->rows);
+    *out = nullptr;
+    ArnoldiHolder holder;
+    HG_TRY(hg_arnoldi_create(ctx, A, B, gcv_type == 0 ? HG_SPACE_M : HG_SPACE_N, k_gcv, &holder.a));
+    hg_arnoldi* a = holder.a;
+    HG_TRY(hg_arnoldi_set_rhs(a, b));
+    HG_TRY(hg_arnoldi_reset(a, 0.0));  // unshifted operator (gcv_function.m:20,22)
+    for (int k = 1; k <= k_gcv; ++k) {
+        HG_TRY(hg_arnoldi_steps(a, 1));
+        HG_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (a->h_H[(size_t)(k - 1) * a->ldh() + k] < 1e-12) break;  // :30
+    }
+    hg_gcv* g = new (std::nothrow) hg_gcv();
+    if (!g) {
+        hg_set_error("hg_gcv_prepare: out of host memory");
+        return HG_ERR_NOMEM;
+    }
+    g->k = k_gcv;  // :33 k = size(H,2): trailing zero columns are kept after an early break
+    g->beta = a->h_beta[0];
+    g->trace_m = gcv_type == 0 ? (double)m : (double)A->cols;  // :46-50
+    g->H.assign(a->h_H, a->h_H + (size_t)(k_gcv + 1) * k_gcv);
+    gcv_fill_sv(g);  // :42
+    *out = g;
+    return HG_OK;
+}
+
+static void gcv_fill_sv(hg_gcv* g) {
+    const int k = g->k;
+    std::vector<double> sq((size_t)k * k);
+    for (int j = 0; j < k; ++j)
+        for (int i = 0; i < k; ++i) sq[(size_t)j * k + i] = g->H[(size_t)j * (k + 1) + i];
+    g->sv.resize(k);
+    hgd::singular_values(k, sq.data(), k, g->sv.data());  // gcv_function.m:42
+}
+
+extern "C" int hg_gcv_from_H(const double* H, int ldh, int k, double beta, double trace_m,
+                             hg_gcv** out) {
+    HG_REQUIRE(H && out, "hg_gcv_from_H: NULL argument");
+    HG_REQUIRE(k >= 1 && ldh >= k + 1, "hg_gcv_from_H: bad shape");
+    hg_gcv* g = new (std::nothrow) hg_gcv();
+    if (!g) {
+        hg_set_error("hg_gcv_from_H: out of host memory");
+        return HG_ERR_NOMEM;
+    }
+    g->k = k;
+    g->beta = beta;
+    g->trace_m = trace_m;
+    g->H.resize((size_t)(k + 1) * k);
+    for (int j = 0; j < k; ++j) memcpy(&g->H[(size_t)j * (k + 1)], H + (size_t)j * ldh, (size_t)(k + 1) * 8);
+    gcv_fill_sv(g);
+    *out = g;
+    return HG_OK;
+}
+
+extern "C" int hg_host_hessenberg_ls(const double* H, int ldh, int k, double beta, double* y) {
+    HG_REQUIRE(H && y && k >= 1 && ldh >= k + 1, "hg_host_hessenberg_ls: bad argument");
+    hgd::HessenbergLS ls;
+    ls.reset(k, beta);
+    for (int j = 0; j < k; ++j) ls.add_column(H + (size_t)j * ldh);
+    ls.solve(y);
+    return HG_OK;
+}
+
+extern "C" int hg_host_solve_square(int n, const double* M, int ld, const double* rhs, double* y) {
+    HG_REQUIRE(M && rhs && y && n >= 1 && ld >= n, "hg_host_solve_square: bad argument");
+    std::vector<double> W((size_t)n * n);
+    for (int j = 0; j < n; ++j) memcpy(&W[(size_t)j * n], M + (size_t)j * ld, (size_t)n * 8);
+    hgd::solve_square(n, W.data(), n, rhs, y);
+    return HG_OK;
+}
+
+extern "C" int hg_host_singular_values(int n, const double* M, int ld, double* s) {
+    HG_REQUIRE(M && s && n >= 1 && ld >= n, "hg_host_singular_values: bad argument");
+    std::vector<double> W((size_t)n * n);
+    for (int j = 0; j < n; ++j) memcpy(&W[(size_t)j * n], M + (size_t)j * ld, (size_t)n * 8);
+    hgd::singular_values(n, W.data(), n, s);
+    return HG_OK;
+}
+
+extern "C" int hg_gcv_eval(const hg_gcv* g, double lambda, double* gcv_val) {
+    HG_REQUIRE(g && gcv_val, "hg_gcv_eval: NULL argument");
+    *gcv_val = hgd::gcv_value(lambda, g->H.data(), g->k + 1, g->k, g->beta, g->trace_m, g->sv.data());
+    return HG_OK;
+}
+
+extern "C" int hg_gcv_get(const hg_gcv* g, double* H, double* beta) {
+    HG_REQUIRE(g, "hg_gcv_get: NULL argument");
+    if (H) memcpy(H, g->H.data(), g->H.size() * 8);
+    if (beta) *beta = g->beta;
+    return HG_OK;
+}
+
+extern "C" int hg_gcv_fminbnd(const hg_gcv* g, double lo, double hi, double tolx, double* lambda,
+                              double* fval, int* funccount, double* trace, int trace_cap) {
+    HG_REQUIRE(g && lambda, "hg_gcv_fminbnd: NULL argument");
+    auto f = [&](double l) {
+        return hgd::gcv_value(l, g->H.data(), g->k + 1, g->k, g->beta, g->trace_m, g->sv.data());
+    };
+    hgd::FminResult r = hgd::fminbnd(f, lo, hi, tolx, 500, 500, trace, trace_cap);
+    *lambda = r.x;
+    if (fval) *fval = r.fval;
+    if (funccount) *funccount = r.funccount;
+    return HG_OK;
+}
+
+extern "C" int hg_gcv_destroy(hg_gcv* g) {
+    delete g;
+    return HG_OK;
+}

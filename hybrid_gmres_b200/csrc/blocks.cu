@@ -1,0 +1,95 @@
+// Building-block entry points on HOST vectors (tests and setup): each copies its
+// operands to the device, runs the same kernels the solvers use, and copies back.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+struct DBuf {
+    double* p = nullptr;
+    ~DBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t n) {
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double));
+        if (e != cudaSuccess) {
+            hg_set_error("device allocation of %zu doubles failed: %s", n, cudaGetErrorString(e));
+            return HG_ERR_NOMEM;
+        }
+        return HG_OK;
+    }
+};
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+}  // namespace
+
+extern "C" int hg_spmv(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y) {
+    HG_REQUIRE(ctx && m && x && y, "hg_spmv: NULL argument");
+    HG_CUDA(cudaSetDevice(ctx->device));
+    DBuf dx, dy;
+    HG_TRY(dx.alloc((size_t)m->cols));
+    HG_TRY(dy.alloc((size_t)m->rows));
+    HG_CUDA(cudaMemcpyAsync(dx.p, x, (size_t)m->cols * 8, cudaMemcpyHostToDevice, ctx->stream));
+    hg_spmv_epilogue ep;
+    HG_TRY(hg_k_spmv(ctx, m, dx.p, dy.p, ep, nullptr));
+    HG_CUDA(cudaMemcpyAsync(y, dy.p, (size_t)m->rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HG_OK;
+}
+
+static int upload_basis(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, DBuf& dV,
+                        int64_t* ldd) {
+    *ldd = round_up(std::max<int64_t>(n, 1), 32);
+    HG_TRY(dV.alloc((size_t)(*ldd) * std::max(k, 1)));
+    if (k > 0 && n > 0)
+        HG_CUDA(cudaMemcpy2DAsync(dV.p, (size_t)(*ldd) * 8, V, (size_t)ld * 8, (size_t)n * 8, (size_t)k,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    return HG_OK;
+}
+
+extern "C" int hg_multidot(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld,
+                           const double* w, double* h) {
+    HG_REQUIRE(ctx && V && w && h, "hg_multidot: NULL argument");
+    HG_REQUIRE(k >= 0 && n >= 0 && ld >= n, "hg_multidot: bad shape");
+    HG_CUDA(cudaSetDevice(ctx->device));
+    DBuf dV, dw, dh, dp;
+    int64_t ldd = 0;
+    HG_TRY(upload_basis(ctx, n, k, V, ld, dV, &ldd));
+    HG_TRY(dw.alloc((size_t)n));
+    HG_TRY(dh.alloc((size_t)k));
+    HG_TRY(dp.alloc((size_t)(k + 1) * ((size_t)n / 256 + 2)));
+    HG_CUDA(cudaMemcpyAsync(dw.p, w, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int ns = 0;
+    HG_TRY(hg_k_multidot(ctx, dV.p, ldd, n, k, dw.p, dp.p, &ns));
+    HG_TRY(hg_k_reduce(ctx, dp.p, ns, k, dh.p, false, nullptr, false));
+    if (k > 0) HG_CUDA(cudaMemcpyAsync(h, dh.p, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HG_OK;
+}
+
+extern "C" int hg_lincomb(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld,
+                          const double* c, double s, const double* z, double* out,
+                          double* out_norm2) {
+    HG_REQUIRE(ctx && V && c && out, "hg_lincomb: NULL argument");
+    HG_REQUIRE(k >= 0 && n >= 0 && ld >= n, "hg_lincomb: bad shape");
+    HG_CUDA(cudaSetDevice(ctx->device));
+    DBuf dV, dc, dz, dout, dstat;
+    int64_t ldd = 0;
+    HG_TRY(upload_basis(ctx, n, k, V, ld, dV, &ldd));
+    HG_TRY(dc.alloc((size_t)k));
+    HG_TRY(dz.alloc((size_t)n));
+    HG_TRY(dout.alloc((size_t)n));
+    HG_TRY(dstat.alloc((size_t)n / 256 + 16));
+    if (k > 0) HG_CUDA(cudaMemcpyAsync(dc.p, c, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (z) HG_CUDA(cudaMemcpyAsync(dz.p, z, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int np = 0;
+    HG_TRY(hg_k_lincomb(ctx, dV.p, ldd, n, k, dc.p, s, z ? dz.p : nullptr, dout.p, nullptr,
+                        out_norm2 ? dstat.p : nullptr, &np));
+    if (out_norm2) {
+        HG_TRY(hg_k_reduce(ctx, dstat.p, np, 1, ctx->d_scalars, false, nullptr, false));
+        HG_CUDA(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    HG_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out_norm2) *out_norm2 = ctx->h_scalars[0];
+    return HG_OK;
+}

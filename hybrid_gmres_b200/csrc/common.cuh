@@ -1,0 +1,154 @@
+// Internal declarations shared by the libhgmres translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "hgmres.h"
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+void hg_set_error(const char* fmt, ...);
+
+#define HG_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            hg_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,       \
+                         __LINE__, cudaGetErrorString(_e));                                  \
+            return HG_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+#define HG_TRY(call)                   \
+    do {                               \
+        int _s = (call);               \
+        if (_s != HG_OK) return _s;    \
+    } while (0)
+
+#define HG_REQUIRE(cond, ...)            \
+    do {                                 \
+        if (!(cond)) {                   \
+            hg_set_error(__VA_ARGS__);   \
+            return HG_ERR_INVALID;       \
+        }                                \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct hg_timed_launch {
+    int klass;
+    cudaEvent_t e0, e1;
+};
+
+struct hg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    // timing
+    bool timing = false;
+    std::vector<hg_timed_launch> pending;
+    std::vector<cudaEvent_t> event_pool;
+    double t_ms[HG_K_NCLASSES] = {0};
+    uint64_t t_count[HG_K_NCLASSES] = {0};
+    double t_bytes[HG_K_NCLASSES] = {0};
+    // scratch for deterministic two-stage reductions
+    double* d_partials = nullptr;  // device
+    size_t partials_cap = 0;       // in doubles
+    double* d_scalars = nullptr;   // 64 device doubles
+    double* h_scalars = nullptr;   // 64 pinned doubles
+};
+
+struct hg_matrix {
+    hg_ctx* ctx = nullptr;
+    int64_t rows = 0, cols = 0, nnz = 0;
+    int64_t* rowptr = nullptr;  // device, rows+1
+    int32_t* colind = nullptr;  // device, nnz
+    double* vals = nullptr;     // device, nnz
+    int tpr = 32;               // threads per row chosen at upload
+};
+
+int hg_ensure_partials(hg_ctx* ctx, size_t ndoubles);
+int hg_matrix_alloc(hg_ctx* ctx, int64_t rows, int64_t cols, int64_t nnz, hg_matrix** out);
+void hg_matrix_pick_tpr(hg_matrix* m);
+
+// RAII-less launch bracket: counts the launch and, when timing is on, records
+// CUDA events on the launch stream around it.
+struct hg_launch_scope {
+    hg_ctx* ctx;
+    int klass;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    hg_launch_scope(hg_ctx* c, int k, double bytes);
+    ~hg_launch_scope();
+};
+
+// ---------------------------------------------------------------------------
+// device kernels' host wrappers (kernels.cu).  All pointers are device pointers.
+// ---------------------------------------------------------------------------
+
+// y[r] = alpha * (M x)[r] + g1 * z1[r] + g2 * z2[r]; optional stat:
+// partials <- per-block sum of (y[r] - ref[r])^2 (ref may be null -> y[r]^2);
+// returns the number of partials written in *nparts (0 if stat == nullptr).
+// If y == nullptr the result is not stored (stat only).
+struct hg_spmv_epilogue {
+    double alpha = 1.0;
+    const double* z1 = nullptr;
+    double g1 = 0.0;
+    const double* z2 = nullptr;
+    double g2 = 0.0;
+    const double* ref = nullptr;
+    double* stat = nullptr;
+};
+int hg_k_spmv(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
+              const hg_spmv_epilogue& ep, int* nparts);
+
+// partials[j*nslabs + slab] = sum over slab rows V[r,j]*w[r];  returns nslabs
+int hg_k_multidot(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* w,
+                  double* partials, int* nslabs);
+
+// out[j] (+)= sum_i partials[j*np + i]  for j<k; if out2 != null also out2[j] = that sum
+// (not accumulated); if do_sqrt, out[j] = sqrt(sum) (no accumulate).
+int hg_k_reduce(hg_ctx* ctx, const double* partials, int np, int k, double* out, bool accumulate,
+                double* out2, bool do_sqrt);
+
+// out[r] = (z ? z[r] : 0) + s * sum_j V[r,j]*c[j];  c is a DEVICE array of k
+// doubles.  Optional stat partials of (out[r]-ref[r])^2 (ref null -> out^2).
+// out may be null (stat only).
+int hg_k_lincomb(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* c,
+                 double s, const double* z, double* out, const double* ref, double* stat,
+                 int* nparts);
+
+// v[i] = v[i] / *d_div   (division, as `v / H(k+1,k)` in the reference)
+int hg_k_scale_div(hg_ctx* ctx, double* v, int64_t n, const double* d_div);
+// out = a*x + b*y (y may be null); optional stat of (out-ref)^2
+int hg_k_axpby(hg_ctx* ctx, int64_t n, double a, const double* x, double b, const double* y,
+               double* out, const double* ref, double* stat, int* nparts);
+// LSQR: x += c1*w ; w = v - c2*w ; stat of (x - ref)^2   (hybrid_lsqr_solver.m:39-42)
+int hg_k_lsqr_update(hg_ctx* ctx, int64_t n, double* x, double* w, const double* v, double c1,
+                     double c2, const double* ref, double* stat, int* nparts);
+// LSMR: hbar = h - c0*hbar (or hbar = h when first); x += c1*hbar; h = v - c2*h
+// (lsmr_solver.m:61-67)
+int hg_k_lsmr_update(hg_ctx* ctx, int64_t n, double* x, double* h, double* hbar, const double* v,
+                     int first, double c0, double c1, double c2, const double* ref, double* stat,
+                     int* nparts);
+// partials of sum x[i]^2 over a plain array (norms, Frobenius norm of vals)
+int hg_k_sumsq(hg_ctx* ctx, const double* x, int64_t n, double* stat, int* nparts);
+
+// convenience: full norm^2 of a device vector into a host double (synchronises)
+int hg_norm2_sync(hg_ctx* ctx, const double* x, int64_t n, double* out);
+// reduce `np` partials at ctx->d_partials into d_scalars[slot] (optionally sqrt)
+int hg_reduce_to_scalar(hg_ctx* ctx, int np, int slot, bool do_sqrt);
+
+// transposition (matrix.cu)
+int hg_transpose_device(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out);

@@ -1,0 +1,229 @@
+/*
+ * hgmres.h — C ABI of libhgmres.so, the B200-native (sm_100a) implementation of
+ * the Arnoldi / Golub-Kahan hot path of luisayang-malaxiangguo/Hybrid-GMRES.
+ *
+ * The reference has no FFI layer: its drop-in boundary is the MATLAB function
+ * signature.  Each "whole solver" entry point below therefore
+ * carries exactly the arguments and outputs of one reference function, as raw
+ * pointers + sizes; a MEX gateway or the ctypes binding in
+ * hybrid_gmres_b200/_lib.py unpacks its arrays and calls it.
+ *
+ *   reference function (file:line)                         entry point
+ *   hybrid_ab_gmres_rtp.m:1                                hg_hybrid_ab_gmres_rtp
+ *   hybrid_ba_gmres_rtp.m:1                                hg_hybrid_ba_gmres_rtp
+ *   gcv_function.m:1   (Arnoldi :4-32 / projected :33-58)  hg_gcv_prepare / hg_gcv_eval
+ *   MATLAB fminbnd over gcv_function
+ *     (analyze_regularization.m:37-46)                     hg_gcv_fminbnd
+ *   hybrid_lsqr_solver.m:1                                 hg_hybrid_lsqr_solver
+ *   hybrid_lsmr_solver.m:1                                 hg_hybrid_lsmr_solver
+ *   lsqr_solver.m:1                                        hg_lsqr_solver
+ *   lsmr_solver.m:1                                        hg_lsmr_solver
+ *
+ * Conventions
+ *   - every function returns an hg_status; hg_last_error() gives the message of
+ *     the calling thread's last failure.  No C++ exception crosses this ABI.
+ *   - all floating point data is IEEE double; dense arrays are column-major
+ *     (MATLAB layout).  "host" pointers are ordinary (or pinned) CPU memory,
+ *     never written unless documented as outputs.
+ *   - matrices live on the device as CSR (int64 row pointers, int32 column
+ *     indices, double values).  B is always a separately stored matrix — there
+ *     is no atomics-based transposed product anywhere.
+ *   - numerical breakdowns are not errors; they follow the reference's own
+ *     semantics (e.g. hybrid_ab_gmres_rtp.m:25,41-43).
+ *   - there is no CPU fallback: every entry point that computes fails with
+ *     HG_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef HGMRES_H
+#define HGMRES_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum hg_status {
+    HG_OK = 0,
+    HG_ERR_INVALID = 1, /* bad argument                                    */
+    HG_ERR_CUDA = 2,    /* CUDA runtime failure / no usable device         */
+    HG_ERR_NOMEM = 3,   /* host or device allocation failed                */
+    HG_ERR_NCCL = 4,    /* NCCL failure (multi-GPU path)                   */
+    HG_ERR_STATE = 5    /* call sequence error (e.g. rhs not set)          */
+} hg_status;
+
+typedef struct hg_ctx hg_ctx;         /* one device + one stream + scratch   */
+typedef struct hg_matrix hg_matrix;   /* device-resident CSR matrix          */
+typedef struct hg_arnoldi hg_arnoldi; /* device Krylov basis + Hessenberg    */
+typedef struct hg_gcv hg_gcv;         /* memoised gcv_function Arnoldi       */
+
+/* ---- library ------------------------------------------------------------ */
+const char* hg_last_error(void);
+int hg_version(void);
+
+/* ---- context ------------------------------------------------------------ */
+/* `stream` is a cudaStream_t to launch on (e.g. torch's current stream), or
+ * NULL to let the library create its own non-blocking stream. */
+int hg_ctx_create(int device, void* stream, hg_ctx** out);
+int hg_ctx_destroy(hg_ctx* ctx);
+int hg_ctx_sync(hg_ctx* ctx);
+/* number of hand-written kernels launched by this context so far */
+int hg_ctx_launch_count(hg_ctx* ctx, uint64_t* out);
+
+/* Per-kernel-class device timing (CUDA events recorded on the launch stream
+ * around every launch of that class while enabled). */
+typedef enum hg_kernel_class {
+    HG_K_SPMV = 0,     /* CSR SpMV (all epilogues)                           */
+    HG_K_MULTIDOT = 1, /* h = V^T w                                          */
+    HG_K_LINCOMB = 2,  /* out = z + s * V c  (CGS update, iterate, residual) */
+    HG_K_VECTOR = 3,   /* scale / axpby / fused LSQR-LSMR vector updates     */
+    HG_K_REDUCE = 4,   /* second-stage deterministic reductions              */
+    HG_K_SETUP = 5,    /* transpose / conversion / generators                */
+    HG_K_NCLASSES = 6
+} hg_kernel_class;
+int hg_ctx_timing_enable(hg_ctx* ctx, int on);
+/* Synchronises, folds pending events, returns totals since the last reset:
+ * summed device milliseconds, launches, and algorithmic bytes. */
+int hg_ctx_timing_get(hg_ctx* ctx, int kernel_class, double* ms, uint64_t* launches, double* bytes);
+int hg_ctx_timing_reset(hg_ctx* ctx);
+
+/* Page-lock / unlock a caller-owned host range so uploads run at PCIe rate. */
+int hg_host_register(void* ptr, size_t bytes);
+int hg_host_unregister(void* ptr);
+
+/* ---- matrices (SURVEY.md §8b "Input types") ------------------------------ */
+/* CSR upload.  ptr_bits is 32 or 64 (width of rowptr entries, signed). */
+int hg_matrix_from_csr(hg_ctx* ctx, int64_t rows, int64_t cols, int64_t nnz, const void* rowptr,
+                       int ptr_bits, const int32_t* colind, const double* vals, hg_matrix** out);
+/* MATLAB sparse (CSC: Jc cols+1 entries, Ir nnz entries, Pr values).  idx_bits
+ * is 64 for mwIndex arrays, 32 for scipy.  The CSC arrays are uploaded as the
+ * CSR of the transpose and transposed on the device (deterministic). */
+int hg_matrix_from_csc(hg_ctx* ctx, int64_t rows, int64_t cols, int64_t nnz, const void* jc,
+                       const void* ir, int idx_bits, const double* pr, hg_matrix** out);
+/* Full column-major matrix (every reference script with n=32 passes full A,B). */
+int hg_matrix_from_dense(hg_ctx* ctx, int64_t rows, int64_t cols, const double* a, int64_t lda,
+                         hg_matrix** out);
+/* out = M^T as a new CSR matrix, column indices sorted within each row. */
+int hg_matrix_transpose(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out);
+int hg_matrix_info(const hg_matrix* m, int64_t* rows, int64_t* cols, int64_t* nnz);
+int hg_matrix_download_csr(hg_ctx* ctx, const hg_matrix* m, int64_t* rowptr, int32_t* colind,
+                           double* vals);
+int hg_matrix_destroy(hg_matrix* m);
+
+/* ---- device CT generators (synthetic inputs) -------- */
+/* geometry: 0 parallel, 1 fan.  Tables as produced by oracle/ct.py:ray_tables. */
+int hg_ct_projector(hg_ctx* ctx, int N, int n_views, int p, int geometry, double R,
+                    const double* cos_th, const double* sin_th, const double* ray_a,
+                    const double* ray_b, hg_matrix** out);
+int hg_ct_backprojector(hg_ctx* ctx, int N, int n_views, int p, int geometry, double R,
+                        const double* cos_th, const double* sin_th, hg_matrix** out);
+
+/* ---- building blocks on host vectors (tests, setup) ---------------------- */
+/* y = M x */
+int hg_spmv(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y);
+/* h = V^T w and out = z + s*V*c on a column-major host V (n x k, ld) — exercise
+ * the CGS2 kernels in isolation. */
+int hg_multidot(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, const double* w,
+                double* h);
+int hg_lincomb(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, const double* c,
+               double s, const double* z, double* out, double* out_norm2);
+
+/* ---- Arnoldi on device-resident data (a1-a4, a9 in SURVEY.md §8a) -------- */
+typedef enum hg_space {
+    HG_SPACE_N = 0, /* operator B*(A*q) + shift*q, start B*b  (hybrid_*_rtp.m:6-13,
+                       gcv_function.m:8,22)                                        */
+    HG_SPACE_M = 1  /* operator A*(B*q) + shift*q, start b    (gcv_function.m:5,20) */
+} hg_space;
+int hg_arnoldi_create(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, int space, int kmax,
+                      hg_arnoldi** out);
+int hg_arnoldi_destroy(hg_arnoldi* a);
+/* upload b (m doubles) and keep it device resident */
+int hg_arnoldi_set_rhs(hg_arnoldi* a, const double* b);
+/* r0, beta, Q(:,1); k <- 0.  Enqueued, no host sync. */
+int hg_arnoldi_reset(hg_arnoldi* a, double shift);
+/* enqueue `nsteps` CGS2 Arnoldi steps without any host synchronisation */
+int hg_arnoldi_steps(hg_arnoldi* a, int nsteps);
+/* wait; copy H ((kmax+1) x kmax, column-major, ldh >= kmax+1), beta, steps done */
+int hg_arnoldi_get(hg_arnoldi* a, double* H, int ldh, double* beta, int* ksteps);
+/* copy basis vector j (0-based) to the host: length rows(Q) */
+int hg_arnoldi_get_q(hg_arnoldi* a, int j, double* q);
+/* algorithmic bytes of Arnoldi step k (1-based), SURVEY.md §8d S(k) */
+int hg_arnoldi_step_bytes(hg_arnoldi* a, int k, double* bytes);
+
+/* ---- whole solvers: the reference signatures ----------------------------- */
+typedef struct hg_solver_opts {
+    int residual_mode; /* 0: r = b - W*y from the cached A*Q columns (default)
+                          1: literal r = b - A*x SpMV (hybrid_ab_gmres_rtp.m:35) */
+    int reserved[7];
+} hg_solver_opts;
+
+/* Optional extra outputs for parity tests (any pointer may be NULL). */
+typedef struct hg_extras {
+    double* H;      /* (maxit+1) x maxit column-major Hessenberg                */
+    double* beta;   /* norm of r0                                               */
+    double* X_hist; /* n x maxit column-major: iterate after every iteration    */
+    double* aux;    /* solver specific: GKB alphas/betas (2*(maxit+1))          */
+} hg_extras;
+
+/* [x,error_norm,residual_norm,niters] = hybrid_ab_gmres_rtp(A,B,b,x_true,tol,maxit,lambda)
+ * x: n, error_norm/residual_norm: maxit (first niters entries valid).
+ * x_valid (may be NULL) is 0 only when the reference would leave x unassigned
+ * (breakdown at k=1, hybrid_ab_gmres_rtp.m:25). */
+int hg_hybrid_ab_gmres_rtp(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, const double* b,
+                           const double* x_true, double tol, int maxit, double lambda, double* x,
+                           double* error_norm, double* residual_norm, int* niters, int* x_valid,
+                           const hg_solver_opts* opts, hg_extras* extras);
+int hg_hybrid_ba_gmres_rtp(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, const double* b,
+                           const double* x_true, double tol, int maxit, double lambda, double* x,
+                           double* error_norm, double* residual_norm, int* niters, int* x_valid,
+                           const hg_solver_opts* opts, hg_extras* extras);
+
+/* gcv_function(lambda,A,B,b,m,k_gcv,gcv_type): the lambda-independent Arnoldi
+ * (gcv_function.m:4-32) runs ONCE in hg_gcv_prepare; hg_gcv_eval is the
+ * projected part (:33-58) on the host.  gcv_type: 0 'ab', 1 'ba'. */
+int hg_gcv_prepare(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, const double* b,
+                   int64_t m, int k_gcv, int gcv_type, hg_gcv** out);
+int hg_gcv_eval(const hg_gcv* g, double lambda, double* gcv_val);
+/* copies H ((k_gcv+1) x k_gcv col-major) and beta */
+int hg_gcv_get(const hg_gcv* g, double* H, double* beta);
+/* MATLAB fminbnd(@(l) gcv_function(l,...), lo, hi, optimset('TolX',tolx)) */
+int hg_gcv_fminbnd(const hg_gcv* g, double lo, double hi, double tolx, double* lambda,
+                   double* fval, int* funccount, double* trace, int trace_cap);
+int hg_gcv_destroy(hg_gcv* g);
+/* Host-only constructor from an existing Arnoldi factorisation (no device work):
+ * H is (k+1) x k column-major with leading dimension ldh, trace_m is m ('ab') or
+ * n ('ba') (gcv_function.m:46-50).  This is plot_gcv_surface.m:58-122's "Arnoldi
+ * once, GCV for many lambda" form. */
+int hg_gcv_from_H(const double* H, int ldh, int k, double beta, double trace_m, hg_gcv** out);
+
+/* ---- host-side projected problems (north star: these stay on the CPU) ---- */
+/* y = argmin || beta*e1 - H(1:k+1,1:k) y ||  by Givens QR (hybrid_ba_gmres_rtp.m:28-29) */
+int hg_host_hessenberg_ls(const double* H, int ldh, int k, double beta, double* y);
+/* y = M \ rhs, square column-major M (not modified): Cholesky if symmetric with
+ * positive pivots, else LU with partial pivoting (hybrid_ab_gmres_rtp.m:32,
+ * gcv_function.m:38, hybrid_lsmr_solver.m:44).  Returns HG_OK also when singular. */
+int hg_host_solve_square(int n, const double* M, int ld, const double* rhs, double* y);
+/* singular values, descending (gcv_function.m:42) */
+int hg_host_singular_values(int n, const double* M, int ld, double* s);
+
+/* At may be NULL: the library then builds A^T on the device for the call. */
+int hg_hybrid_lsqr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At, const double* b,
+                          const double* x_true, double tol, int maxit, double lambda, double* x,
+                          double* error_norm, double* residual_norm, int* niters,
+                          hg_extras* extras);
+int hg_hybrid_lsmr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At, const double* b,
+                          const double* x_true, double tol, int maxit, double lambda, double* x,
+                          double* error_norm, double* residual_norm, int* niters,
+                          hg_extras* extras);
+int hg_lsqr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At, const double* b,
+                   const double* x_true, double tol, int maxit, double* x, double* error_norm,
+                   double* residual_norm, int* niters, hg_extras* extras);
+/* x_true may be NULL (err_hist is then NaN, lsmr_solver.m:28,72-74) */
+int hg_lsmr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At, const double* b,
+                   const double* x_true, double tol, int maxit, double* x, double* err_hist,
+                   double* res_hist, double* ar_hist, int* iters, hg_extras* extras);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGMRES_H */

@@ -1,0 +1,127 @@
+"""GPU parity of the individual kernels and data-format conversions, through the
+C ABI, against NumPy/SciPy on the same inputs."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-13  # FP64 mat-vec in a different summation order
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_extension_loaded(hg):
+    import ctypes
+    assert hg._lib.load().hg_version() >= 100
+    assert isinstance(hg._lib.load(), ctypes.CDLL)
+
+
+@pytest.mark.parametrize("which", ["A", "B"])
+def test_spmv_ct(hg, ctx, ct64, which):
+    A, B, b, x_true = ct64
+    M = A if which == "A" else B
+    d = hg.DeviceMatrix.from_any(M, ctx)
+    x = np.random.default_rng(1).standard_normal(M.shape[1])
+    assert _rel(d.matvec(x), M @ x) < RTOL
+
+
+@pytest.mark.parametrize("shape,density", [((1, 1), 1.0), ((7, 3), 0.5), ((300, 200), 0.02),
+                                           ((64, 5000), 0.3), ((5000, 64), 0.001), ((33, 33), 0.0)])
+def test_spmv_ragged_and_empty(hg, ctx, shape, density):
+    rng = np.random.default_rng(2)
+    M = sp.random(shape[0], shape[1], density=density, format="csr", random_state=rng, dtype=np.float64)
+    d = hg.DeviceMatrix.from_any(M, ctx)
+    assert d.shape == shape and d.nnz == M.nnz
+    x = rng.standard_normal(shape[1])
+    y = d.matvec(x)
+    ref = M @ x
+    assert np.allclose(y, ref, rtol=1e-12, atol=1e-14)
+
+
+def test_spmv_dense_input(hg, ctx):
+    from oracle import generate_test_problem
+    A, b, x = generate_test_problem("deriv2", 32)
+    d = hg.DeviceMatrix.from_any(A, ctx)
+    assert d.nnz == 32 * 32
+    assert _rel(d.matvec(x), A @ x) < RTOL
+    At = hg.DeviceMatrix.from_any(np.asfortranarray(A.T), ctx)
+    assert _rel(At.matvec(b), A.T @ b) < RTOL
+
+
+def test_transpose_bit_exact(hg, ctx, ct64):
+    A = ct64[0]
+    d = hg.DeviceMatrix.from_any(A, ctx)
+    t = d.transpose()
+    indptr, indices, data = t.download()
+    ref = A.T.tocsr()
+    ref.sort_indices()
+    assert np.array_equal(indptr, ref.indptr)
+    assert np.array_equal(indices, ref.indices)
+    assert np.array_equal(data, ref.data)  # values only move: bit exact
+    tt = t.transpose()
+    i2, j2, v2 = tt.download()
+    A2 = A.copy()
+    A2.sort_indices()
+    assert np.array_equal(i2, A2.indptr) and np.array_equal(j2, A2.indices) and np.array_equal(v2, A2.data)
+
+
+def test_transpose_long_rows_and_duplicates(hg, ctx):
+    rng = np.random.default_rng(3)
+    # one column hit by 20000 rows -> an output row longer than the shared-memory sort
+    rows = np.concatenate([np.arange(20000), rng.integers(0, 20000, 5000)])
+    cols = np.concatenate([np.zeros(20000, dtype=np.int64), rng.integers(1, 50, 5000)])
+    vals = rng.standard_normal(rows.shape[0])
+    M = sp.csr_matrix((vals, (rows, cols)), shape=(20000, 50))
+    d = hg.DeviceMatrix.from_any(M, ctx)
+    indptr, indices, data = d.transpose().download()
+    ref = M.T.tocsr()
+    ref.sort_indices()
+    assert np.array_equal(indptr, ref.indptr) and np.array_equal(indices, ref.indices)
+    assert np.array_equal(data, ref.data)
+
+
+@pytest.mark.parametrize("idx_dtype", [np.int32, np.uint64])
+def test_csc_upload_matches_csr(hg, ctx, ct48_unmatched, idx_dtype):
+    """MATLAB hands sparse matrices as CSC with 64-bit mwIndex."""
+    A = ct48_unmatched[0]
+    Ac = A.tocsc()
+    Ac.sort_indices()
+    d = hg.DeviceMatrix.from_csc(Ac.indptr.astype(idx_dtype), Ac.indices.astype(idx_dtype), Ac.data, A.shape, ctx)
+    indptr, indices, data = d.download()
+    ref = A.copy()
+    ref.sort_indices()
+    assert np.array_equal(indptr, ref.indptr) and np.array_equal(indices, ref.indices)
+    assert np.array_equal(data, ref.data)
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (37, 3), (4096, 8), (100003, 17), (70000, 60)])
+def test_multidot_and_lincomb(hg, ctx, n, k):
+    import ctypes as C
+    rng = np.random.default_rng(4)
+    V = np.asfortranarray(rng.standard_normal((n, k)))
+    w = rng.standard_normal(n)
+    c = rng.standard_normal(k)
+    lib = ctx._lib
+    h = np.zeros(k)
+    hg._lib.check(lib.hg_multidot(ctx._h, n, k, V.ctypes.data, n, w.ctypes.data, h.ctypes.data))
+    ref = V.T @ w
+    assert np.allclose(h, ref, rtol=1e-12, atol=1e-12 * np.linalg.norm(w))
+    out = np.zeros(n)
+    nrm2 = C.c_double()
+    hg._lib.check(lib.hg_lincomb(ctx._h, n, k, V.ctypes.data, n, c.ctypes.data, -1.0, w.ctypes.data,
+                                 out.ctypes.data, C.byref(nrm2)))
+    ref = w - V @ c
+    assert _rel(out, ref) < 1e-14
+    assert abs(nrm2.value - ref @ ref) <= 1e-13 * (ref @ ref)
+
+
+def test_reductions_are_deterministic(hg, ctx, ct64):
+    A = ct64[0]
+    d = hg.DeviceMatrix.from_any(A, ctx)
+    x = np.random.default_rng(5).standard_normal(A.shape[1])
+    y1 = d.matvec(x)
+    y2 = d.matvec(x)
+    assert np.array_equal(y1, y2)

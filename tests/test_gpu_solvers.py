@@ -1,0 +1,218 @@
+"""GPU parity of the whole solvers (called through the C ABI with the
+reference's own argument lists) against the literal oracle restatement.
+
+Tolerance: BASELINE.json's north star — per-iteration residual norms, Arnoldi
+coefficients and iterates within 1e-8 relative over the first 50 iterations;
+stopping iteration identical.  Arnoldi coefficients are compared norm-wise per
+column of H (element-wise is meaningless: with matched B the upper part of H is
+rounding noise, SURVEY.md §7 hard part 1).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-8   # north-star tolerance vs the literal (MGS) reference restatement
+TIGHT = 1e-10  # same algorithm (CGS2), different summation order
+
+
+def _colwise(Hd, Ho, kmax):
+    out = []
+    for k in range(kmax):
+        out.append(np.linalg.norm(Hd[: k + 2, k] - Ho[: k + 2, k]) / np.linalg.norm(Ho[: k + 2, k]))
+    return np.array(out)
+
+
+def _iter_rel(Xd, Xo):
+    k = min(Xd.shape[1], Xo.shape[1])
+    return np.array([np.linalg.norm(Xd[:, i] - Xo[:, i]) / np.linalg.norm(Xo[:, i]) for i in range(k)])
+
+
+@pytest.mark.parametrize("solver", ["ba", "ab"])
+@pytest.mark.parametrize("problem", ["ct64", "ct48_unmatched"])
+def test_rtp_vs_oracle(hg, ctx, request, solver, problem):
+    import oracle
+    A, B, b, x_true = request.getfixturevalue(problem)
+    maxit, lam, tol = 50, 1e-2, 1e-6
+    f_dev = hg.hybrid_ba_gmres_rtp if solver == "ba" else hg.hybrid_ab_gmres_rtp
+    f_orc = oracle.hybrid_ba_gmres_rtp if solver == "ba" else oracle.hybrid_ab_gmres_rtp
+    ex_d = {}
+    x, err, res, it = f_dev(A, B, b, x_true, tol, maxit, lam, ctx=ctx, extras=ex_d)
+    for orth, bound in (("mgs", TOL), ("cgs2", TIGHT)):
+        ex_o = {}
+        xo, erro, reso, ito = f_orc(A, B, b, x_true, tol, maxit, lam, orth=orth, extras=ex_o)
+        assert it == ito
+        assert np.max(np.abs(res - reso) / reso) < bound
+        assert np.max(np.abs(err - erro) / erro) < bound
+        assert np.max(_iter_rel(ex_d["X"], ex_o["X"])) < bound
+        assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < bound
+        assert abs(ex_d["beta"] - ex_o["beta"]) / ex_o["beta"] < 1e-13
+        assert np.max(_colwise(ex_d["H"], ex_o["H"], it)) < bound
+
+
+@pytest.mark.parametrize("solver", ["ba", "ab"])
+def test_rtp_literal_residual_mode(hg, ctx, ct64, solver):
+    """residual_mode=1 recomputes b - A*x with an SpMV exactly as the reference does."""
+    import oracle
+    A, B, b, x_true = ct64
+    f_dev = hg.hybrid_ba_gmres_rtp if solver == "ba" else hg.hybrid_ab_gmres_rtp
+    f_orc = oracle.hybrid_ba_gmres_rtp if solver == "ba" else oracle.hybrid_ab_gmres_rtp
+    x, err, res, it = f_dev(A, B, b, x_true, 1e-6, 20, 1e-2, ctx=ctx, residual_mode=1)
+    xo, erro, reso, ito = f_orc(A, B, b, x_true, 1e-6, 20, 1e-2)
+    assert it == ito
+    assert np.max(np.abs(res - reso) / reso) < TOL
+    assert np.max(np.abs(err - erro) / erro) < TOL
+
+
+def test_rtp_stops_on_tolerance(hg, ctx, ct64):
+    """Stopping iteration must match exactly (<= tol, hybrid_ba_gmres_rtp.m:35)."""
+    import oracle
+    A, B, b, x_true = ct64
+    for tol in (0.2, 0.05, 0.02):
+        for f_dev, f_orc in ((hg.hybrid_ba_gmres_rtp, oracle.hybrid_ba_gmres_rtp),
+                             (hg.hybrid_ab_gmres_rtp, oracle.hybrid_ab_gmres_rtp)):
+            x, err, res, it = f_dev(A, B, b, x_true, tol, 40, 1e-2, ctx=ctx)
+            xo, erro, reso, ito = f_orc(A, B, b, x_true, tol, 40, 1e-2)
+            assert it == ito and len(res) == it
+            assert res[-1] <= tol or it == 40
+
+
+def test_rtp_on_reference_dense_inputs(hg, ctx):
+    """run_ptr_rtp_comparison.m:4-19: deriv2 n=32, full A, B=A', lambda=1e-3, maxit=n.
+    Arnoldi breaks down numerically on this problem: only BA-RTP
+    iterates are reproducible beyond k~6, AB-RTP is checked on the first 5."""
+    import oracle
+    from oracle.generators import add_noise
+    A, b_exact, x_true = oracle.generate_test_problem("deriv2", 32)
+    B = A.T.copy()
+    b = add_noise(b_exact, 1e-2, 0)
+    ex_d, ex_o = {}, {}
+    x, err, res, it = hg.hybrid_ba_gmres_rtp(A, B, b, x_true, 1e-6, 32, 1e-3, ctx=ctx, extras=ex_d)
+    xo, erro, reso, ito = oracle.hybrid_ba_gmres_rtp(A, B, b, x_true, 1e-6, 32, 1e-3, extras=ex_o)
+    assert it == ito
+    assert np.max(_iter_rel(ex_d["X"], ex_o["X"])) < 1e-7
+    assert np.max(np.abs(err - erro) / erro) < 1e-7
+    ex_d, ex_o = {}, {}
+    x, err, res, it = hg.hybrid_ab_gmres_rtp(A, B, b, x_true, 1e-6, 5, 1e-3, ctx=ctx, extras=ex_d)
+    xo, erro, reso, ito = oracle.hybrid_ab_gmres_rtp(A, B, b, x_true, 1e-6, 5, 1e-3, extras=ex_o)
+    assert it == ito
+    assert np.max(_iter_rel(ex_d["X"], ex_o["X"])) < 1e-6
+
+
+def test_arnoldi_handle_matches_solver(hg, ctx, ct64):
+    """hg_arnoldi_* (the bench path, no host sync per step) gives the same H as the solver."""
+    A, B, b, x_true = ct64
+    dA, dB = hg.DeviceMatrix.from_any(A, ctx), hg.DeviceMatrix.from_any(B, ctx)
+    ar = hg.Arnoldi(dA, dB, "n", 30)
+    ar.set_rhs(b)
+    ar.reset(1e-2)
+    ar.steps(30)
+    H, beta, k = ar.get()
+    ex = {}
+    hg.hybrid_ba_gmres_rtp(dA, dB, b, x_true, 0.0, 30, 1e-2, ctx=ctx, extras=ex)
+    assert k == 30
+    assert np.array_equal(H, ex["H"]) and beta == ex["beta"]  # deterministic reductions
+    # orthonormal basis
+    Q = np.stack([ar.q(j) for j in range(31)], axis=1)
+    assert np.linalg.norm(Q.T @ Q - np.eye(31)) < 1e-13
+    # rerun is bit-identical
+    ar.reset(1e-2)
+    ar.steps(30)
+    H2, beta2, _ = ar.get()
+    assert np.array_equal(H, H2) and beta == beta2
+
+
+@pytest.mark.parametrize("gcv_type", ["ab", "ba"])
+def test_gcv_function_and_fminbnd(hg, ctx, ct64, gcv_type):
+    """analyze_regularization.m:35-46: fminbnd over gcv_function on [1e-9,1e-1], TolX 1e-8, k_gcv=20."""
+    import oracle
+    from oracle.solvers import gcv_arnoldi, gcv_from_H
+    A, B, b, x_true = ct64
+    m = A.shape[0]
+    prob = hg.gcv_prepare(A, B, b, m, 20, gcv_type, ctx=ctx)
+    Hd, betad = prob.get(20)
+    Ho, betao = gcv_arnoldi(A, B, b, m, 20, gcv_type)
+    assert abs(betad - betao) / betao < 1e-13
+    assert np.max(_colwise(Hd, Ho, 20)) < TIGHT
+    for lam in (1e-9, 1e-6, 1e-3, 1e-1):
+        v_dev = hg.gcv_function(lam, A, B, b, m, 20, gcv_type, ctx=ctx)
+        v_orc = oracle.gcv_function(lam, A, B, b, m, 20, gcv_type)
+        assert abs(v_dev - v_orc) / v_orc < 1e-8
+    tr_o = []
+    lam_o, f_o, flag, cnt_o = oracle.fminbnd(lambda l: oracle.gcv_function(l, A, B, b, m, 20, gcv_type),
+                                             1e-9, 1e-1, 1e-8, trace=tr_o)
+    lam_d, f_d, cnt_d, tr_d = prob.fminbnd(1e-9, 1e-1, 1e-8)
+    assert cnt_d == cnt_o  # identical evaluation sequence length
+    assert np.allclose(tr_d, np.array(tr_o), rtol=1e-6, atol=1e-8 * 1e-3)
+    assert abs(lam_d - lam_o) <= 1e-8 * 1e-3 + 1e-6 * lam_o  # far inside TolX
+    # the selected lambda drives the same stopping iteration in the solver
+    x, err, res, it = hg.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.05, 40, lam_d, ctx=ctx)
+    xo, erro, reso, ito = oracle.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.05, 40, lam_o)
+    assert it == ito
+
+
+def test_gcv_early_breakdown_keeps_zero_columns(hg, ctx):
+    """gcv_function.m:30,33: after `H(k+1,k) < 1e-12` the trailing zero columns stay."""
+    import oracle
+    from oracle.generators import add_noise
+    A, b_exact, x_true = oracle.generate_test_problem("shaw", 32)
+    B = A.T.copy()
+    b = add_noise(b_exact, 1e-2, 0)
+    for t in ("ab", "ba"):
+        for lam in (1e-6, 1e-3):
+            v_dev = hg.gcv_function(lam, A, B, b, 32, 20, t, ctx=ctx)
+            v_orc = oracle.gcv_function(lam, A, B, b, 32, 20, t)
+            assert np.isfinite(v_dev)
+            assert abs(v_dev - v_orc) / v_orc < 1e-5  # Arnoldi has broken down: loose
+
+
+@pytest.mark.parametrize("name", ["hybrid_lsqr_solver", "hybrid_lsmr_solver", "lsqr_solver", "lsmr_solver"])
+def test_gkb_solvers_vs_oracle(hg, ctx, ct48_unmatched, name):
+    import oracle
+    A, B, b, x_true = ct48_unmatched
+    maxit, lam, tol = 40, 1e-2, 1e-6
+    ex_d, ex_o = {}, {}
+    f_dev, f_orc = getattr(hg, name), getattr(oracle, name)
+    if name.startswith("hybrid"):
+        out_d = f_dev(A, b, x_true, tol, maxit, lam, ctx=ctx, extras=ex_d)
+        out_o = f_orc(A, b, x_true, tol, maxit, lam, extras=ex_o)
+    else:
+        out_d = f_dev(A, b, x_true, tol, maxit, ctx=ctx, extras=ex_d)
+        out_o = f_orc(A, b, x_true, tol, maxit, extras=ex_o)
+    assert out_d[-1] == out_o[-1]  # iterations
+    for hd, ho in zip(out_d[1:-1], out_o[1:-1]):  # histories
+        assert hd.shape == ho.shape
+        assert np.max(np.abs(hd - ho) / np.abs(ho)) < TOL
+    assert np.max(_iter_rel(ex_d["X"], ex_o["X"])) < TOL
+    assert np.linalg.norm(out_d[0] - out_o[0]) / np.linalg.norm(out_o[0]) < TOL
+
+
+def test_lsmr_defaults_and_missing_x_true(hg, ctx):
+    """lsmr_solver.m:3-5 defaults; err_hist is NaN without x_true (:28,72-74)."""
+    import oracle
+    A, b_exact, x_true = oracle.generate_test_problem("heat", 32)
+    x, err, res, ar, it = hg.lsmr_solver(A, b_exact, ctx=ctx)
+    xo, erro, reso, aro, ito = oracle.lsmr_solver(A, b_exact)
+    assert it == ito
+    assert np.all(np.isnan(err))
+    k = min(8, it)
+    assert np.max(np.abs(res[:k] - reso[:k]) / reso[:k]) < 1e-6
+
+
+def test_gkb_with_preuploaded_transpose(hg, ctx, ct48_unmatched):
+    A, B, b, x_true = ct48_unmatched
+    dA = hg.DeviceMatrix.from_any(A, ctx)
+    dAt = dA.transpose()
+    r1 = hg.lsqr_solver(dA, b, x_true, 1e-6, 10, ctx=ctx, At=dAt)
+    r2 = hg.lsqr_solver(A, b, x_true, 1e-6, 10, ctx=ctx)
+    assert np.array_equal(r1[0], r2[0])
+
+
+def test_cross_solver_identity(hg, ctx, ct64):
+    """AB-RTP with matched B equals hybrid LSQR (same Krylov space and Tikhonov
+    projection) on the first iterations."""
+    A, B, b, x_true = ct64
+    e1, e2 = {}, {}
+    hg.hybrid_ab_gmres_rtp(A, B, b, x_true, 0.0, 5, 1e-2, ctx=ctx, extras=e1)
+    hg.hybrid_lsqr_solver(A, b, x_true, 0.0, 5, 1e-2, ctx=ctx, extras=e2)
+    assert np.max(_iter_rel(e1["X"], e2["X"])) < 1e-8
