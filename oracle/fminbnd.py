@@ -16,7 +16,7 @@ _EPS = 2.220446049250313e-16
 
 
 def _sign(x: float) -> float:
-    return (x > 0) - (x < 0)
+    return float(x > 0) - float(x < 0)
 
 
 def fminbnd(fun, ax, bx, tolx=1e-4, max_fun_evals=500, max_iter=500, trace=None):

@@ -40,5 +40,5 @@ def test_backprojector(hg, ctx, geometry):
     assert np.array_equal(indices, ref.indices)
     if geometry == "parallel":
         assert np.array_equal(data, ref.data)
-    else:  # atan2 differs in the last bit between libm and CUDA
-        assert np.allclose(data, ref.data, rtol=1e-12, atol=1e-15)
+    else:  # atan2 differs in the last bit between libm and CUDA; f = (g+gmax)/dg amplifies it
+        assert np.allclose(data, ref.data, rtol=1e-12, atol=1e-12)
