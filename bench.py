@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py — Arnoldi iterations/s and HBM roofline on BASELINE.json's headline config.
+
+A "step" is one complete 200-iteration CGS2 Arnoldi cycle of the hybrid AB-/BA-GMRES
+hot path (operator B*(A*q)+lambda*q, two-pass CGS, normalise) on the 1024x1024
+fan-beam phantom problem with an unmatched pixel-driven back-projector (BASELINE.json
+configs[3]); `value` = 200*K / device time.  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, n_views, geometry, maxit)
+    "ct1024_fan_180v_pixelB_k200": dict(N=1024, n_views=180, geometry="fan", maxit=200),
+    "ct512_fan_180v_pixelB_k200": dict(N=512, n_views=180, geometry="fan", maxit=200),
+    "ct256_fan_180v_pixelB_k100": dict(N=256, n_views=180, geometry="fan", maxit=100),
+    "ct64_par_180v_pixelB_k80": dict(N=64, n_views=180, geometry="parallel", maxit=80),
+}
+LAMBDA = 1e-2  # run_2D_phantom.m:8
+NOISE = 0.01   # BASELINE config 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(hg, ctx, name):
+    w = WORKLOADS[name]
+    N, nv, geom = w["N"], w["n_views"], w["geometry"]
+    angles = np.arange(nv) * ((360.0 if geom == "fan" else 180.0) / nv)
+    p = int(round(math.sqrt(2.0) * N))
+    dA = hg.ct_projector(N, angles, p, geom, ctx=ctx)
+    dB = hg.ct_backprojector(N, angles, p, geom, ctx=ctx)
+    from hybrid_gmres_b200.ct import shepp_logan
+    x_true = shepp_logan(N)
+    b_exact = dA.matvec(x_true)
+    rng = np.random.default_rng(0)
+    e = rng.standard_normal(b_exact.shape)
+    b = b_exact + NOISE * np.linalg.norm(b_exact) * e / np.linalg.norm(e)  # run_2D_phantom.m:18-19
+    return dA, dB, b, x_true, w["maxit"]
+
+
+def host_csr(dM):
+    import scipy.sparse as sp
+    indptr, indices, data = dM.download()
+    return sp.csr_matrix((data, indices, indptr), shape=dM.shape)
+
+
+def cpu_reference_sample(A, B, b, x_true, iters):
+    """The reference's BA-RTP loop (literal oracle restatement) for `iters` iterations."""
+    import oracle
+    t0 = time.perf_counter()
+    x, err, res, it = oracle.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, iters, LAMBDA)
+    dt = time.perf_counter() - t0
+    return it / dt, dt, it
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ct1024_fan_180v_pixelB_k200", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-iters", type=int, default=8, help="iterations of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 0)
+
+    if args.impl == "reference" and rank != 0:
+        return 0
+
+    import torch
+    import hybrid_gmres_b200 as hg
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1 and args.impl != "reference":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = hg.Context(local_rank, stream=stream)
+    dA, dB, b, x_true, maxit = build_workload(hg, ctx, args.workload)
+    m, n = dA.shape
+    cores = len(os.sched_getaffinity(0))
+    config = {"workload": args.workload, "m": m, "n": n, "nnz_A": dA.nnz, "nnz_B": dB.nnz, "maxit": maxit,
+              "lambda": LAMBDA, "orth": "cgs2", "B": "pixel-driven (unmatched)",
+              "parallelism": f"replicas x{world}" if world > 1 else "single",
+              "l2": "inputs (A+B = %.1f GB) exceed the 126 MB L2; no flush needed" % ((dA.nnz + dB.nnz) * 12 / 1e9)}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        A, B = host_csr(dA), host_csr(dB)
+        del dA, dB
+        for _ in range(min(W, 1)):
+            cpu_reference_sample(A, B, b, x_true, 2)
+        t0 = time.perf_counter()
+        its = 0
+        for _ in range(K):
+            _, _, it = cpu_reference_sample(A, B, b, x_true, args.cpu_iters)
+            its += it
+        dt = time.perf_counter() - t0
+        val = its / dt
+        line = {"impl": "reference", "metric": "arnoldi_iters_per_s", "value": val, "unit": "iter/s",
+                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "iter/s", "cores": cores, "kind": "port",
+                                 "sample": f"{args.cpu_iters} full hybrid BA-RTP iterations per step (literal oracle "
+                                           "restatement of hybrid_ba_gmres_rtp.m: 3 SpMV + MGS + projected LS per "
+                                           "iteration; SciPy CSR mat-vec is single-threaded, BLAS uses all cores)"},
+                "e2e": {"value": val, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    ar = hg.Arnoldi(dA, dB, "n", maxit)
+    ar.set_rhs(b)
+    for _ in range(W):
+        ar.reset(LAMBDA)
+        ar.steps(maxit)
+    ctx.sync()
+    launches0 = ctx.launch_count
+    ctx.timing_enable(True)
+    ctx.timing_reset()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        ar.reset(LAMBDA)
+        ar.steps(maxit)
+    ev1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    timing = ctx.timing()
+    ctx.timing_enable(False)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    total_iters = maxit * K * world
+    value = total_iters / (ms * 1e-3)
+    step_bytes = sum(ar.step_bytes(k) for k in range(1, maxit + 1))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+    sp_ms, sp_cnt, sp_bytes = timing["spmv"]
+    achieved = (sp_bytes / sp_cnt) / (sp_ms / sp_cnt * 1e-3) / 1e9 if sp_cnt else 0.0
+    roofline = {"bound": "hbm", "kernel": "spmv_csr_kernel<32> (A and B launches)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "launches": sp_cnt, "avg_launch_ms": sp_ms / sp_cnt if sp_cnt else None,
+                "algorithmic_bytes_per_launch": sp_bytes / sp_cnt if sp_cnt else None,
+                "step_algorithmic_GBps": step_bytes * K / (ms * 1e-3) / 1e9,
+                "step_frac": step_bytes * K / (ms * 1e-3) / 1e9 / peak,
+                "per_class": {k: {"ms": v[0], "launches": v[1],
+                                  "GBps": (v[2] / (v[0] * 1e-3) / 1e9) if v[0] > 0 else None}
+                              for k, v in timing.items() if v[1]}}
+    line = {"metric": "arnoldi_iters_per_s", "value": value, "unit": "iter/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config, "roofline": roofline,
+            "gpu_launches": launches, "clocks": clocks}
+
+    # ------------------------------------------------------------------ e2e through the public API
+    if rank == 0 and not args.no_e2e:
+        A, B = host_csr(dA), host_csr(dB)
+        pinned = []
+        for arr in (A.indptr, A.indices, A.data, B.indptr, B.indices, B.data, b, x_true):
+            try:
+                hg._lib.check(ctx._lib.hg_host_register(arr.ctypes.data, arr.nbytes))
+                pinned.append(arr)
+            except Exception:
+                pass
+        ar.close()
+        del ar
+        Ke = max(1, min(K, 3))
+        hg.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, min(maxit, 3), LAMBDA, ctx=ctx)  # warm-up (allocators)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        its = 0
+        for _ in range(Ke):
+            x, err, res, it = hg.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, maxit, LAMBDA, ctx=ctx)
+            its += it
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        h2d = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes + B.indptr.nbytes + B.indices.nbytes + \
+            B.data.nbytes + b.nbytes + x_true.nbytes + maxit * (maxit + 1) // 2 * 8
+        d2h = x.nbytes + maxit * (maxit + 3) // 2 * 8 + maxit * 16
+        line["e2e"] = {"value": its / dt, "unit": "iter/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h), "steps": Ke, "final_residual": float(res[-1]),
+                       "api": "hybrid_ba_gmres_rtp(A,B,b,x_true,tol,maxit,lambda) with pinned host CSR A, B "
+                              "(upload + 200 full hybrid iterations + histories per step)"}
+        t0 = time.perf_counter()
+        x, err, res, it = hg.hybrid_ab_gmres_rtp(A, B, b, x_true, 0.0, maxit, LAMBDA, ctx=ctx)
+        torch.cuda.synchronize()
+        line["e2e"]["hybrid_ab_iters_per_s"] = it / (time.perf_counter() - t0)
+        if not args.no_cpu:
+            v, dt, it = cpu_reference_sample(A, B, b, x_true, args.cpu_iters)
+            line["cpu_baseline"] = {"value": v, "unit": "iter/s", "cores": cores, "kind": "port",
+                                    "sample": f"{it} full hybrid BA-RTP iterations of the same workload by the literal "
+                                              f"oracle restatement ({dt:.1f} s; SciPy CSR mat-vec single-threaded, BLAS "
+                                              f"on {cores} cores) — compare with e2e, not with value"}
+        for arr in pinned:
+            ctx._lib.hg_host_unregister(arr.ctypes.data)
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

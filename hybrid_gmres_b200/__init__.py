@@ -25,5 +25,6 @@ from .api import (  # noqa: E402,F401
     hybrid_lsqr_solver,
     lsmr_solver,
     lsqr_solver,
+    set_option,
 )
 from .ct import ct_backprojector, ct_projector, ray_tables  # noqa: E402,F401

@@ -38,6 +38,7 @@ _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 PROTOTYPES = {
     "hg_last_error": (C.c_char_p, []),
     "hg_version": (_i, []),
+    "hg_set_option": (_i, [C.c_char_p, _i]),
     "hg_ctx_create": (_i, [_i, _vp, c_void_pp]),
     "hg_ctx_destroy": (_i, [_vp]),
     "hg_ctx_sync": (_i, [_vp]),

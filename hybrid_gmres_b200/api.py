@@ -29,7 +29,7 @@ __all__ = [
     "Context", "DeviceMatrix", "Arnoldi", "GcvProblem", "default_context",
     "hybrid_ab_gmres_rtp", "hybrid_ba_gmres_rtp", "hybrid_lsqr_solver", "hybrid_lsmr_solver",
     "lsqr_solver", "lsmr_solver", "gcv_function", "gcv_prepare", "fminbnd_gcv",
-    "KERNEL_CLASSES",
+    "KERNEL_CLASSES", "set_option",
 ]
 
 KERNEL_CLASSES = {"spmv": 0, "multidot": 1, "lincomb": 2, "vector": 3, "reduce": 4, "setup": 5}
@@ -93,6 +93,11 @@ class Context:
             check(self._lib.hg_ctx_timing_get(self._h, k, C.byref(ms), C.byref(cnt), C.byref(by)))
             out[name] = (ms.value, int(cnt.value), by.value)
         return out
+
+
+def set_option(name: str, value: int) -> None:
+    """``hg_set_option``: e.g. ``set_option("spmv_mode", 2)`` forces the streaming SpMV."""
+    check(_lib.load().hg_set_option(name.encode(), int(value)))
 
 
 _default_ctx = None

@@ -77,7 +77,14 @@ struct hg_matrix {
     int32_t* colind = nullptr;  // device, nnz
     double* vals = nullptr;     // device, nnz
     int tpr = 32;               // threads per row chosen at upload
+    // streaming-SpMV work partition (lazily built cache, see spmv_stream.cu)
+    int64_t* unit_row = nullptr;  // device, n_units+1 row boundaries, nnz balanced
+    int n_units = 0;
 };
+
+// colind / vals are allocated with this many zero entries of tail padding so the
+// 16-byte granular bulk copies of the streaming SpMV may over-read safely
+constexpr int kNnzPad = 16;
 
 int hg_ensure_partials(hg_ctx* ctx, size_t ndoubles);
 int hg_matrix_alloc(hg_ctx* ctx, int64_t rows, int64_t cols, int64_t nnz, hg_matrix** out);
@@ -149,6 +156,11 @@ int hg_k_sumsq(hg_ctx* ctx, const double* x, int64_t n, double* stat, int* npart
 int hg_norm2_sync(hg_ctx* ctx, const double* x, int64_t n, double* out);
 // reduce `np` partials at ctx->d_partials into d_scalars[slot] (optionally sqrt)
 int hg_reduce_to_scalar(hg_ctx* ctx, int np, int slot, bool do_sqrt);
+
+// streaming SpMV (spmv_stream.cu)
+bool hg_spmv_stream_eligible(const hg_matrix* m);
+int hg_k_spmv_stream(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
+                     const hg_spmv_epilogue& ep, int* nparts);
 
 // transposition (matrix.cu)
 int hg_transpose_device(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out);

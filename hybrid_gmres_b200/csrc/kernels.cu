@@ -78,28 +78,51 @@ spmv_csr_kernel(int64_t rows, const int64_t* __restrict__ rowptr, const int* __r
     // invalid rows run zero trips but still take part in the shuffles below
     const int64_t s = valid ? rowptr[row] : 0;
     const int64_t e = valid ? rowptr[row + 1] : 0;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    // Software-pipelined batches of U*TPR entries: every (col,val) load of a batch — the
+    // ragged tail included, by predication — is issued together, and the next batch's
+    // stream loads are in flight while this batch's dependent x gathers resolve, so a row
+    // exposes one DRAM latency plus one L2 latency per batch instead of two serial
+    // latencies per trip and one per tail element (ncu: long_scoreboard dominated).
+    constexpr int U = 4;
+    double a[U];
+    int c[U];
+    double v[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = 0.0;
     int64_t i = s + lane;
-    for (; i + 3 * TPR < e; i += 4 * TPR) {
-        const int c0 = ld_stream(colind + i);
-        const int c1 = ld_stream(colind + i + TPR);
-        const int c2 = ld_stream(colind + i + 2 * TPR);
-        const int c3 = ld_stream(colind + i + 3 * TPR);
-        const double v0 = ld_stream(vals + i);
-        const double v1 = ld_stream(vals + i + TPR);
-        const double v2 = ld_stream(vals + i + 2 * TPR);
-        const double v3 = ld_stream(vals + i + 3 * TPR);
-        a0 = fma(v0, __ldg(x + c0), a0);
-        a1 = fma(v1, __ldg(x + c1), a1);
-        a2 = fma(v2, __ldg(x + c2), a2);
-        a3 = fma(v3, __ldg(x + c3), a3);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        ok[u] = i + u * TPR < e;
+        c[u] = ok[u] ? ld_stream(colind + i + u * TPR) : 0;
     }
-    for (; i < e; i += TPR) {
-        const int c0 = ld_stream(colind + i);
-        const double v0 = ld_stream(vals + i);
-        a0 = fma(v0, __ldg(x + c0), a0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = ok[u] ? ld_stream(vals + i + u * TPR) : 0.0;
+    while (i - lane < e) {  // warp-uniform per row group
+        double xg[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) xg[u] = ok[u] ? __ldg(x + c[u]) : 0.0;
+        const int64_t in = i + U * TPR;
+        int cn[U];
+        double vn[U];
+        bool okn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            okn[u] = in + u * TPR < e;
+            cn[u] = okn[u] ? ld_stream(colind + in + u * TPR) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) vn[u] = okn[u] ? ld_stream(vals + in + u * TPR) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            a[u] = fma(v[u], xg[u], a[u]);
+            c[u] = cn[u];
+            v[u] = vn[u];
+            ok[u] = okn[u];
+        }
+        i = in;
     }
-    double sum = (a0 + a1) + (a2 + a3);
+    double sum = (a[0] + a[1]) + (a[2] + a[3]);
 #pragma unroll
     for (int o = TPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, TPR);
     if (valid && lane == 0) {
@@ -359,6 +382,7 @@ int hg_k_spmv(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
               const hg_spmv_epilogue& ep, int* nparts) {
     if (nparts) *nparts = 0;
     if (m->rows == 0) return HG_OK;
+    if (hg_spmv_stream_eligible(m)) return hg_k_spmv_stream(ctx, m, x, y, ep, nparts);
     const int tpr = m->tpr;
     const int rpb = kBlock / tpr;
     const int64_t grid = cdiv(m->rows, rpb);

@@ -165,8 +165,10 @@ int hg_matrix_alloc(hg_ctx* ctx, int64_t rows, int64_t cols, int64_t nnz, hg_mat
     m->cols = cols;
     m->nnz = nnz;
     cudaError_t e = cudaMalloc(&m->rowptr, (size_t)(rows + 1) * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&m->colind, (size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&m->vals, (size_t)std::max<int64_t>(nnz, 1) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&m->colind, (size_t)(nnz + kNnzPad) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&m->vals, (size_t)(nnz + kNnzPad) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->colind + nnz, 0, kNnzPad * sizeof(int32_t), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->vals + nnz, 0, kNnzPad * sizeof(double), ctx->stream);
     if (e != cudaSuccess) {
         hg_set_error("matrix: device allocation of %lld nnz failed: %s", (long long)nnz,
                      cudaGetErrorString(e));
@@ -193,6 +195,7 @@ extern "C" int hg_matrix_destroy(hg_matrix* m) {
     if (m->rowptr) cudaFree(m->rowptr);
     if (m->colind) cudaFree(m->colind);
     if (m->vals) cudaFree(m->vals);
+    if (m->unit_row) cudaFree(m->unit_row);
     delete m;
     return HG_OK;
 }

@@ -61,3 +61,22 @@ def ct_backprojector(N, angles_deg, p=None, geometry="parallel", R=None, ctx: Co
     check(ctx._lib.hg_ct_backprojector(ctx._h, int(N), int(c.shape[0]), int(p), _geom(geometry), float(R),
                                        _ptr(c), _ptr(s), C.byref(h)))
     return DeviceMatrix(h, ctx)
+
+
+def shepp_logan(N: int) -> np.ndarray:
+    """Modified Shepp-Logan phantom, N x N, column-major vectorised (``x_true(:)``,
+    ``reshape(x, N, N)`` at ``run_2D_phantom.m:57``) — the synthetic ``x_true`` of the bench."""
+    ell = [(1.0, .69, .92, 0.0, 0.0, 0.0), (-.8, .6624, .8740, 0.0, -.0184, 0.0),
+           (-.2, .1100, .3100, .22, 0.0, -18.0), (-.2, .1600, .4100, -.22, 0.0, 18.0),
+           (.1, .2100, .2500, 0.0, .35, 0.0), (.1, .0460, .0460, 0.0, .1, 0.0),
+           (.1, .0460, .0460, 0.0, -.1, 0.0), (.1, .0460, .0230, -.08, -.605, 0.0),
+           (.1, .0230, .0230, 0.0, -.606, 0.0), (.1, .0230, .0460, .06, -.605, 0.0)]
+    xs = ((np.arange(N) + 0.5) - N / 2.0) / (N / 2.0)
+    X, Y = np.meshgrid(xs, -xs)
+    img = np.zeros((N, N))
+    for amp, a, b, x0, y0, phi in ell:
+        ph = math.radians(phi)
+        xr = (X - x0) * math.cos(ph) + (Y - y0) * math.sin(ph)
+        yr = -(X - x0) * math.sin(ph) + (Y - y0) * math.cos(ph)
+        img[(xr / a) ** 2 + (yr / b) ** 2 <= 1.0] += amp
+    return img.ravel(order="F")

@@ -61,6 +61,10 @@ typedef struct hg_gcv hg_gcv;         /* memoised gcv_function Arnoldi       */
 const char* hg_last_error(void);
 int hg_version(void);
 
+/* Tuning knobs.  "spmv_mode": 0 auto (default; also env HG_SPMV=v1|v2), 1 force the
+ * row-per-warp SpMV, 2 force the TMA-staged streaming SpMV. */
+int hg_set_option(const char* name, int value);
+
 /* ---- context ------------------------------------------------------------ */
 /* `stream` is a cudaStream_t to launch on (e.g. torch's current stream), or
  * NULL to let the library create its own non-blocking stream. */
