@@ -226,8 +226,16 @@ def main():
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     sp_ms, sp_cnt, sp_bytes = timing["spmv"]
     achieved = (sp_bytes / sp_cnt) / (sp_ms / sp_cnt * 1e-3) / 1e9 if sp_cnt else 0.0
+    traffic, traffic_src = None, None
+    if args.workload == "ct1024_fan_180v_pixelB_k200":
+        try:  # dram__bytes_read+write per launch from the committed `ncu --set full` capture of this kernel
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_spmv_traffic.json")))
+            traffic, traffic_src = float(tj["mean"]), tj["source"]
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": "spmv_csr_kernel<32> (A and B launches)", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "peak_source": peak_src,
                 "launches": sp_cnt, "avg_launch_ms": sp_ms / sp_cnt if sp_cnt else None,
                 "algorithmic_bytes_per_launch": sp_bytes / sp_cnt if sp_cnt else None,
                 "step_algorithmic_GBps": step_bytes * K / (ms * 1e-3) / 1e9,

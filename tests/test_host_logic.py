@@ -156,3 +156,23 @@ def test_argument_validation(lib):
     assert lib.hg_gcv_from_H(H.ctypes.data, 2, 2, 1.0, 2.0, C.byref(out)) == 1  # ldh too small
     with pytest.raises(ValueError):
         hg.GcvProblem.from_H(np.zeros((2, 2)), 1.0, 2.0)
+
+
+def test_mex_gateway_parses_and_binds_the_abi():
+    """The MEX gateway cannot be built without MATLAB; it must at least
+    parse against the real C ABI header and the stub mex.h."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    src = os.path.join(ROOT, "hybrid_gmres_b200", "mex", "hgmres_mex.cpp")
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(ROOT, "hybrid_gmres_b200", "mex", "stub"), src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    txt = open(src).read()
+    for fn in ("hg_hybrid_ab_gmres_rtp", "hg_hybrid_ba_gmres_rtp", "hg_gcv_prepare", "hg_gcv_eval",
+               "hg_hybrid_lsqr_solver", "hg_hybrid_lsmr_solver", "hg_lsqr_solver", "hg_lsmr_solver",
+               "hg_matrix_from_csc", "hg_matrix_from_dense"):
+        assert fn in txt
