@@ -86,19 +86,31 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_workload(hg, ctx, name):
+def build_workload(hg, ctx, name, rank=0, world=1, dist=None):
+    """Matrices are generated on the device.  world > 1: this rank's detector-row block A_p and
+    the matching column block B^p; b is the matching slice."""
     w = WORKLOADS[name]
     N, nv, geom = w["N"], w["n_views"], w["geometry"]
     angles = np.arange(nv) * ((360.0 if geom == "fan" else 180.0) / nv)
     p = int(round(math.sqrt(2.0) * N))
-    dA = hg.ct_projector(N, angles, p, geom, ctx=ctx)
-    dB = hg.ct_backprojector(N, angles, p, geom, ctx=ctx)
-    from hybrid_gmres_b200.ct import shepp_logan
+    from hybrid_gmres_b200.ct import ct_backprojector_cols, ct_projector_rows, shepp_logan
+    from hybrid_gmres_b200.sharding import uniform_row_blocks
+    m = nv * p
+    bounds = uniform_row_blocks(m, world)  # every view carries ~the same nnz: equal ray counts balance nnz
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    dA = ct_projector_rows(N, angles, p, geom, lo, hi, ctx=ctx)
+    dB = ct_backprojector_cols(N, angles, p, geom, lo, hi, ctx=ctx)
     x_true = shepp_logan(N)
     b_exact = dA.matvec(x_true)
     rng = np.random.default_rng(0)
-    e = rng.standard_normal(b_exact.shape)
-    b = b_exact + NOISE * np.linalg.norm(b_exact) * e / np.linalg.norm(e)  # run_2D_phantom.m:18-19
+    e = rng.standard_normal(m)
+    nb2 = float(b_exact @ b_exact)
+    if world > 1:
+        import torch
+        t = torch.tensor([nb2], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        nb2 = float(t.item())
+    b = b_exact + NOISE * math.sqrt(nb2) * e[lo:hi] / np.linalg.norm(e)  # run_2D_phantom.m:18-19
     return dA, dB, b, x_true, w["maxit"]
 
 
@@ -148,13 +160,22 @@ def main():
 
     stream = torch.cuda.current_stream().cuda_stream
     ctx = hg.Context(local_rank, stream=stream)
-    dA, dB, b, x_true, maxit = build_workload(hg, ctx, args.workload)
+    if args.impl == "reference":
+        dA, dB, b, x_true, maxit = build_workload(hg, ctx, args.workload)
+    else:
+        dA, dB, b, x_true, maxit = build_workload(hg, ctx, args.workload, rank, world, dist)
     m, n = dA.shape
+    nnzA, nnzB = dA.nnz, dB.nnz
+    if dist is not None:
+        t = torch.tensor([float(m), float(nnzA), float(nnzB)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        m, nnzA, nnzB = (int(v) for v in t.tolist())
     cores = len(os.sched_getaffinity(0))
-    config = {"workload": args.workload, "m": m, "n": n, "nnz_A": dA.nnz, "nnz_B": dB.nnz, "maxit": maxit,
+    config = {"workload": args.workload, "m": m, "n": n, "nnz_A": nnzA, "nnz_B": nnzB, "maxit": maxit,
               "lambda": LAMBDA, "orth": "cgs2", "B": "pixel-driven (unmatched)",
-              "parallelism": f"replicas x{world}" if world > 1 else "single",
-              "l2": "inputs (A+B = %.1f GB) exceed the 126 MB L2; no flush needed" % ((dA.nnz + dB.nnz) * 12 / 1e9)}
+              "parallelism": (f"A row-sharded / B column-sharded x{world}, NCCL reduce-scatter + all-gather + "
+                              "3 all-reduce per step") if world > 1 else "single",
+              "l2": "inputs (A+B = %.1f GB) exceed the 126 MB L2; no flush needed" % ((nnzA + nnzB) * 12 / 1e9)}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -182,8 +203,15 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ B200 arm
-    ar = hg.Arnoldi(dA, dB, "n", maxit)
-    ar.set_rhs(b)
+    sharded = world > 1
+    if sharded:
+        from hybrid_gmres_b200.distributed import Communicator, ShardedArnoldi
+        comm = Communicator(ctx)
+        ar = ShardedArnoldi(comm, dA, dB, maxit)
+        ar.set_rhs(b)
+    else:
+        ar = hg.Arnoldi(dA, dB, "n", maxit)
+        ar.set_rhs(b)
     for _ in range(W):
         ar.reset(LAMBDA)
         ar.steps(maxit)
@@ -214,9 +242,16 @@ def main():
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    total_iters = maxit * K * world
+    total_iters = maxit * K  # one sharded job: the same 200-iteration cycle on N GPUs (strong scaling)
     value = total_iters / (ms * 1e-3)
     step_bytes = sum(ar.step_bytes(k) for k in range(1, maxit + 1))
+    if sharded:  # whole-job algorithmic bytes = sum over ranks
+        t = torch.tensor([step_bytes], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        step_bytes = float(t.item())
+        peak_scale = world
+    else:
+        peak_scale = 1
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -239,17 +274,60 @@ def main():
                 "launches": sp_cnt, "avg_launch_ms": sp_ms / sp_cnt if sp_cnt else None,
                 "algorithmic_bytes_per_launch": sp_bytes / sp_cnt if sp_cnt else None,
                 "step_algorithmic_GBps": step_bytes * K / (ms * 1e-3) / 1e9,
-                "step_frac": step_bytes * K / (ms * 1e-3) / 1e9 / peak,
+                "step_frac": step_bytes * K / (ms * 1e-3) / 1e9 / (peak * peak_scale),
                 "per_class": {k: {"ms": v[0], "launches": v[1],
                                   "GBps": (v[2] / (v[0] * 1e-3) / 1e9) if v[0] > 0 else None}
                               for k, v in timing.items() if v[1]}}
     line = {"metric": "arnoldi_iters_per_s", "value": value, "unit": "iter/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "roofline": roofline,
             "gpu_launches": launches, "clocks": clocks}
 
     # ------------------------------------------------------------------ e2e through the public API
-    if rank == 0 and not args.no_e2e:
+    if sharded and not args.no_e2e:
+        # end to end of the sharded API: every rank uploads its shards from pinned host memory,
+        # builds the sharded Arnoldi, runs the 200-step cycle and reads H back
+        A, B = host_csr(dA), host_csr(dB)
+        pinned = []
+        for arr in (A.indptr, A.indices, A.data, B.indptr, B.indices, B.data, b):
+            try:
+                hg._lib.check(ctx._lib.hg_host_register(arr.ctypes.data, arr.nbytes))
+                pinned.append(arr)
+            except Exception:
+                pass
+        ar.close()
+        del ar, dA, dB
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        Ke = max(1, min(K, 2))
+        for _ in range(Ke):
+            uA, uB = hg.DeviceMatrix.from_any(A, ctx), hg.DeviceMatrix.from_any(B, ctx)
+            ar2 = ShardedArnoldi(comm, uA, uB, maxit)
+            ar2.set_rhs(b)
+            ar2.reset(LAMBDA)
+            ar2.steps(maxit)
+            H, beta, kk = ar2.get()
+            ar2.close()
+            uA.close()
+            uB.close()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes + B.indptr.nbytes + B.indices.nbytes + \
+            B.data.nbytes + b.nbytes
+        tb = torch.tensor([float(h2d)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tb)
+        line["e2e"] = {"value": maxit * Ke / float(t.item()), "unit": "iter/s", "h2d_bytes_per_step": int(tb.item()),
+                       "d2h_bytes_per_step": int(world * maxit * (maxit + 3) // 2 * 8), "steps": Ke,
+                       "api": "ShardedArnoldi: per-rank upload of A_p, B^p from pinned host CSR + 200 sharded "
+                              "Arnoldi steps + H read back (whole-solver sharded entry points are next)"}
+        for arr in pinned:
+            ctx._lib.hg_host_unregister(arr.ctypes.data)
+    elif rank == 0 and not args.no_e2e:
         A, B = host_csr(dA), host_csr(dB)
         pinned = []
         for arr in (A.indptr, A.indices, A.data, B.indptr, B.indices, B.data, b, x_true):

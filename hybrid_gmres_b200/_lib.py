@@ -57,6 +57,19 @@ PROTOTYPES = {
     "hg_matrix_destroy": (_i, [_vp]),
     "hg_ct_projector": (_i, [_vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, c_void_pp]),
     "hg_ct_backprojector": (_i, [_vp, _i, _i, _i, _i, _d, _vp, _vp, c_void_pp]),
+    "hg_ct_projector_rows": (_i, [_vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _i64, _i64, c_void_pp]),
+    "hg_ct_backprojector_cols": (_i, [_vp, _i, _i, _i, _i, _d, _vp, _vp, _i64, _i64, c_void_pp]),
+    "hg_comm_unique_id": (_i, [_vp]),
+    "hg_comm_init": (_i, [_vp, _i, _i, _vp, c_void_pp]),
+    "hg_comm_destroy": (_i, [_vp]),
+    "hg_darnoldi_create": (_i, [_vp, _vp, _vp, _vp, _i, c_void_pp]),
+    "hg_darnoldi_destroy": (_i, [_vp]),
+    "hg_darnoldi_set_rhs": (_i, [_vp, _vp]),
+    "hg_darnoldi_reset": (_i, [_vp, _d]),
+    "hg_darnoldi_steps": (_i, [_vp, _i]),
+    "hg_darnoldi_get": (_i, [_vp, _vp, _i, c_double_p, c_int_p]),
+    "hg_darnoldi_get_q": (_i, [_vp, _i, _vp, c_int64_p, c_int64_p]),
+    "hg_darnoldi_step_bytes": (_i, [_vp, _i, c_double_p]),
     "hg_spmv": (_i, [_vp, _vp, _vp, _vp]),
     "hg_multidot": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp]),
     "hg_lincomb": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _d, _vp, _vp, c_double_p]),

@@ -102,11 +102,12 @@ template <bool EMIT>
 __global__ void __launch_bounds__(kBlock)
 projector_kernel(int N, int n_views, int p, int geometry, double R, const double* __restrict__ cos_th,
                  const double* __restrict__ sin_th, const double* __restrict__ ray_a,
-                 const double* __restrict__ ray_b, int64_t* __restrict__ rowptr,
-                 int32_t* __restrict__ colind, double* __restrict__ vals) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= (int64_t)n_views * p) return;
-    const int v = (int)(row / p), i = (int)(row % p);
+                 const double* __restrict__ ray_b, int64_t row_lo, int64_t row_hi,
+                 int64_t* __restrict__ rowptr, int32_t* __restrict__ colind, double* __restrict__ vals) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // local row of the block
+    if (row >= row_hi - row_lo) return;
+    const int64_t grow = row_lo + row;  // global ray index = view*p + i
+    const int v = (int)(grow / p), i = (int)(grow % p);
     const Ray r = make_ray(geometry, R, cos_th[v], sin_th[v], ray_a[i], ray_b[i]);
     if (EMIT) {
         const int64_t s = rowptr[row];
@@ -121,8 +122,8 @@ template <bool EMIT>
 __global__ void __launch_bounds__(kBlock)
 backprojector_kernel(int N, int n_views, int p, int geometry, double R, double gmax, double dg,
                      const double* __restrict__ cos_th, const double* __restrict__ sin_th,
-                     int64_t* __restrict__ rowptr, int32_t* __restrict__ colind,
-                     double* __restrict__ vals) {
+                     int64_t col_lo, int64_t col_hi, int64_t* __restrict__ rowptr,
+                     int32_t* __restrict__ colind, double* __restrict__ vals) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (int64_t)N * N) return;
     // row = (N-1-iy) + N*ix
@@ -152,16 +153,17 @@ backprojector_kernel(int N, int n_views, int p, int geometry, double R, double g
         const double i0 = floor(f);
         const double w1 = sub(f, i0);
         const double w0 = sub(1.0, w1);
-        if (i0 >= 0 && i0 < p) {
+        const int64_t c0 = (int64_t)v * p + (int64_t)i0;  // global sinogram index of bin i0
+        if (i0 >= 0 && i0 < p && c0 >= col_lo && c0 < col_hi) {
             if (EMIT) {
-                colind[pos + count] = (int32_t)((double)v * p + i0);
+                colind[pos + count] = (int32_t)(c0 - col_lo);
                 vals[pos + count] = mul(w0, scale);
             }
             ++count;
         }
-        if (i0 + 1 >= 0 && i0 + 1 < p) {
+        if (i0 + 1 >= 0 && i0 + 1 < p && c0 + 1 >= col_lo && c0 + 1 < col_hi) {
             if (EMIT) {
-                colind[pos + count] = (int32_t)((double)v * p + i0 + 1);
+                colind[pos + count] = (int32_t)(c0 + 1 - col_lo);
                 vals[pos + count] = mul(w1, scale);
             }
             ++count;
@@ -207,16 +209,17 @@ int upload(hg_ctx* ctx, double** d, const double* h, int n) {
 
 }  // namespace
 
-extern "C" int hg_ct_projector(hg_ctx* ctx, int N, int n_views, int p, int geometry, double R,
-                               const double* cos_th, const double* sin_th, const double* ray_a,
-                               const double* ray_b, hg_matrix** out) {
+extern "C" int hg_ct_projector_rows(hg_ctx* ctx, int N, int n_views, int p, int geometry, double R,
+                                    const double* cos_th, const double* sin_th, const double* ray_a,
+                                    const double* ray_b, int64_t row_lo, int64_t row_hi, hg_matrix** out) {
     HG_REQUIRE(ctx && cos_th && sin_th && ray_a && out, "hg_ct_projector: NULL argument");
+    HG_REQUIRE(row_lo >= 0 && row_lo <= row_hi && row_hi <= (int64_t)n_views * p, "hg_ct_projector: bad row range");
     HG_REQUIRE(N >= 1 && n_views >= 1 && p >= 1, "hg_ct_projector: bad sizes");
     HG_REQUIRE(geometry == 0 || (geometry == 1 && ray_b), "hg_ct_projector: bad geometry");
     HG_REQUIRE((int64_t)N * N <= 2147483647LL, "hg_ct_projector: image too large for int32 columns");
     HG_CUDA(cudaSetDevice(ctx->device));
     *out = nullptr;
-    const int64_t rows = (int64_t)n_views * p;
+    const int64_t rows = row_hi - row_lo;
     Tables t;
     HG_TRY(upload(ctx, &t.c, cos_th, n_views));
     HG_TRY(upload(ctx, &t.s, sin_th, n_views));
@@ -224,11 +227,11 @@ extern "C" int hg_ct_projector(hg_ctx* ctx, int N, int n_views, int p, int geome
     HG_TRY(upload(ctx, &t.b, geometry == 1 ? ray_b : nullptr, p));
     int64_t* d_ptr = nullptr;
     HG_CUDA(cudaMalloc(&d_ptr, (size_t)(rows + 1) * 8));
-    const unsigned grid = (unsigned)cdiv(rows, kBlock);
+    const unsigned grid = (unsigned)std::max<int64_t>(cdiv(rows, kBlock), 1);
     {
         hg_launch_scope scope(ctx, HG_K_SETUP, 8.0 * (double)rows);
         projector_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(N, n_views, p, geometry, R, t.c, t.s,
-                                                                   t.a, t.b, d_ptr, nullptr, nullptr);
+                                                                   t.a, t.b, row_lo, row_hi, d_ptr, nullptr, nullptr);
     }
     int64_t nnz = 0;
     int st = cudaGetLastError() == cudaSuccess ? scan_counts(ctx, rows, d_ptr, &nnz) : HG_ERR_CUDA;
@@ -238,7 +241,7 @@ extern "C" int hg_ct_projector(hg_ctx* ctx, int N, int n_views, int p, int geome
         cudaMemcpyAsync(m->rowptr, d_ptr, (size_t)(rows + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
         hg_launch_scope scope(ctx, HG_K_SETUP, 12.0 * (double)nnz);
         projector_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(N, n_views, p, geometry, R, t.c, t.s,
-                                                                  t.a, t.b, m->rowptr, m->colind, m->vals);
+                                                                  t.a, t.b, row_lo, row_hi, m->rowptr, m->colind, m->vals);
     }
     if (st == HG_OK && (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
         hg_set_error("hg_ct_projector: kernel failed");
@@ -254,9 +257,18 @@ extern "C" int hg_ct_projector(hg_ctx* ctx, int N, int n_views, int p, int geome
     return HG_OK;
 }
 
-extern "C" int hg_ct_backprojector(hg_ctx* ctx, int N, int n_views, int p, int geometry, double R,
-                                   const double* cos_th, const double* sin_th, hg_matrix** out) {
+extern "C" int hg_ct_projector(hg_ctx* ctx, int N, int n_views, int p, int geometry, double R,
+                               const double* cos_th, const double* sin_th, const double* ray_a,
+                               const double* ray_b, hg_matrix** out) {
+    return hg_ct_projector_rows(ctx, N, n_views, p, geometry, R, cos_th, sin_th, ray_a, ray_b, 0,
+                                (int64_t)n_views * p, out);
+}
+
+extern "C" int hg_ct_backprojector_cols(hg_ctx* ctx, int N, int n_views, int p, int geometry, double R,
+                                        const double* cos_th, const double* sin_th, int64_t col_lo,
+                                        int64_t col_hi, hg_matrix** out) {
     HG_REQUIRE(ctx && cos_th && sin_th && out, "hg_ct_backprojector: NULL argument");
+    HG_REQUIRE(col_lo >= 0 && col_lo <= col_hi && col_hi <= (int64_t)n_views * p, "hg_ct_backprojector: bad column range");
     HG_REQUIRE(N >= 1 && n_views >= 1 && p >= 2, "hg_ct_backprojector: bad sizes");
     HG_REQUIRE(geometry == 0 || geometry == 1, "hg_ct_backprojector: bad geometry");
     HG_REQUIRE((int64_t)n_views * p <= 2147483647LL, "hg_ct_backprojector: sinogram too large for int32 columns");
@@ -277,17 +289,17 @@ extern "C" int hg_ct_backprojector(hg_ctx* ctx, int N, int n_views, int p, int g
     {
         hg_launch_scope scope(ctx, HG_K_SETUP, 8.0 * (double)rows);
         backprojector_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(N, n_views, p, geometry, R, gmax, dg,
-                                                                       t.c, t.s, d_ptr, nullptr, nullptr);
+                                                                       t.c, t.s, col_lo, col_hi, d_ptr, nullptr, nullptr);
     }
     int64_t nnz = 0;
     int st = cudaGetLastError() == cudaSuccess ? scan_counts(ctx, rows, d_ptr, &nnz) : HG_ERR_CUDA;
     hg_matrix* m = nullptr;
-    if (st == HG_OK) st = hg_matrix_alloc(ctx, rows, (int64_t)n_views * p, nnz, &m);
+    if (st == HG_OK) st = hg_matrix_alloc(ctx, rows, col_hi - col_lo, nnz, &m);
     if (st == HG_OK) {
         cudaMemcpyAsync(m->rowptr, d_ptr, (size_t)(rows + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
         hg_launch_scope scope(ctx, HG_K_SETUP, 12.0 * (double)nnz);
         backprojector_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(N, n_views, p, geometry, R, gmax, dg,
-                                                                      t.c, t.s, m->rowptr, m->colind, m->vals);
+                                                                      t.c, t.s, col_lo, col_hi, m->rowptr, m->colind, m->vals);
     }
     if (st == HG_OK && (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
         hg_set_error("hg_ct_backprojector: kernel failed");
@@ -301,4 +313,9 @@ extern "C" int hg_ct_backprojector(hg_ctx* ctx, int N, int n_views, int p, int g
     hg_matrix_pick_tpr(m);
     *out = m;
     return HG_OK;
+}
+
+extern "C" int hg_ct_backprojector(hg_ctx* ctx, int N, int n_views, int p, int geometry, double R,
+                                   const double* cos_th, const double* sin_th, hg_matrix** out) {
+    return hg_ct_backprojector_cols(ctx, N, n_views, p, geometry, R, cos_th, sin_th, 0, (int64_t)n_views * p, out);
 }

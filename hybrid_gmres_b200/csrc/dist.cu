@@ -1,0 +1,346 @@
+// Multi-GPU (one process per GPU) sharded Arnoldi — SURVEY.md §8(e).
+//
+// Rank p owns a contiguous, nnz-balanced detector-row block A_p (m_p x n) of A, the
+// matching column block B^p (n x m_p) of B, the row slice [p*n_p, (p+1)*n_p) of every
+// Krylov vector and the m_p-slice of T = [b, A q_1, ...].  Per step:
+//     u_p = A_p q            local SpMV (q replicated)
+//     w   = sum_p B^p u_p    local SpMV -> ncclReduceScatter of the n-vector
+//     w  += shift * q        on the slice
+//     CGS2 on slices         two ncclAllReduce of k coefficients, one of the norm
+//     q_{k+1}                ncclAllGather of the normalised slice
+// NCCL is resolved at run time with dlopen (the single-GPU library has no NCCL
+// dependency); the communicator is built from a unique id that the Python side
+// broadcasts with torch.distributed (plumbing only).
+#include <dlfcn.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclDouble = 8 };  // ncclFloat64
+enum { ncclSum = 0 };
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+} g_nccl;
+
+int load_nccl() {
+    if (g_nccl.lib) return HG_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) {
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) {
+        hg_set_error("NCCL: cannot dlopen libnccl.so.2 (%s)", dlerror());
+        return HG_ERR_NCCL;
+    }
+#define HG_SYM(field, name)                                                    \
+    do {                                                                       \
+        *(void**)(&g_nccl.field) = dlsym(lib, name);                           \
+        if (!g_nccl.field) {                                                   \
+            hg_set_error("NCCL: symbol %s not found", name);                   \
+            return HG_ERR_NCCL;                                                \
+        }                                                                      \
+    } while (0)
+    HG_SYM(GetUniqueId, "ncclGetUniqueId");
+    HG_SYM(CommInitRank, "ncclCommInitRank");
+    HG_SYM(CommDestroy, "ncclCommDestroy");
+    HG_SYM(AllReduce, "ncclAllReduce");
+    HG_SYM(ReduceScatter, "ncclReduceScatter");
+    HG_SYM(AllGather, "ncclAllGather");
+    HG_SYM(GetErrorString, "ncclGetErrorString");
+#undef HG_SYM
+    g_nccl.lib = lib;
+    return HG_OK;
+}
+
+#define HG_NCCL(call)                                                                          \
+    do {                                                                                       \
+        int _r = (call);                                                                       \
+        if (_r != ncclSuccess) {                                                               \
+            hg_set_error("NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(_r)); \
+            return HG_ERR_NCCL;                                                                \
+        }                                                                                      \
+    } while (0)
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+}  // namespace
+
+struct hg_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+extern "C" int hg_comm_unique_id(void* out128) {
+    HG_REQUIRE(out128, "hg_comm_unique_id: NULL");
+    HG_TRY(load_nccl());
+    ncclUniqueId id;
+    HG_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return HG_OK;
+}
+
+extern "C" int hg_comm_init(hg_ctx* ctx, int nranks, int rank, const void* id128, hg_comm** out) {
+    HG_REQUIRE(ctx && id128 && out, "hg_comm_init: NULL argument");
+    HG_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "hg_comm_init: bad rank %d of %d", rank, nranks);
+    HG_TRY(load_nccl());
+    HG_CUDA(cudaSetDevice(ctx->device));
+    hg_comm* c = new (std::nothrow) hg_comm();
+    if (!c) {
+        hg_set_error("hg_comm_init: out of host memory");
+        return HG_ERR_NOMEM;
+    }
+    c->rank = rank;
+    c->nranks = nranks;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        hg_set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+        delete c;
+        return HG_ERR_NCCL;
+    }
+    *out = c;
+    return HG_OK;
+}
+
+extern "C" int hg_comm_destroy(hg_comm* c) {
+    if (!c) return HG_OK;
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    delete c;
+    return HG_OK;
+}
+
+// ===========================================================================
+struct hg_darnoldi {
+    hg_ctx* ctx = nullptr;
+    hg_comm* comm = nullptr;
+    const hg_matrix* A = nullptr;  // m_p x n
+    const hg_matrix* B = nullptr;  // n x m_p
+    int kmax = 0, k = 0;
+    int64_t n = 0, n_p = 0, n_pad = 0, m_p = 0, ldq = 0, ldt = 0;
+    double* Q = nullptr;       // n_p x (kmax+1) row slice of the basis (zero padded)
+    double* T = nullptr;       // m_p x (kmax+1): column 0 = b_p, column k = A_p q_k
+    double* q_full = nullptr;  // n_pad, replicated current basis vector
+    double* w_part = nullptr;  // n_pad, partial B^p u_p
+    double *w0 = nullptr, *w1 = nullptr;  // n_p
+    double *d_H = nullptr, *d_hcur = nullptr, *d_s = nullptr;
+    double *h_H = nullptr, *h_beta = nullptr;
+    double *partials = nullptr, *stat = nullptr;
+    double shift = 0.0;
+    bool have_rhs = false, started = false;
+    int ldh() const { return kmax + 1; }
+};
+
+int hg_multidot_nslabs(const hg_ctx* ctx, int64_t n);
+
+extern "C" int hg_darnoldi_destroy(hg_darnoldi* a) {
+    if (!a) return HG_OK;
+    cudaStreamSynchronize(a->ctx->stream);
+    cudaFree(a->Q); cudaFree(a->T); cudaFree(a->q_full); cudaFree(a->w_part);
+    cudaFree(a->w0); cudaFree(a->w1); cudaFree(a->d_H); cudaFree(a->d_hcur); cudaFree(a->d_s);
+    cudaFree(a->partials); cudaFree(a->stat);
+    if (a->h_H) cudaFreeHost(a->h_H);
+    if (a->h_beta) cudaFreeHost(a->h_beta);
+    delete a;
+    return HG_OK;
+}
+
+extern "C" int hg_darnoldi_create(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_p, const hg_matrix* B_p,
+                                  int kmax, hg_darnoldi** out) {
+    HG_REQUIRE(ctx && comm && A_p && B_p && out, "hg_darnoldi_create: NULL argument");
+    HG_REQUIRE(kmax >= 1, "hg_darnoldi_create: kmax must be >= 1");
+    HG_REQUIRE(A_p->cols == B_p->rows && A_p->rows == B_p->cols,
+               "hg_darnoldi_create: shard shapes do not match (A_p %lld x %lld, B^p %lld x %lld)",
+               (long long)A_p->rows, (long long)A_p->cols, (long long)B_p->rows, (long long)B_p->cols);
+    HG_CUDA(cudaSetDevice(ctx->device));
+    *out = nullptr;
+    hg_darnoldi* a = new (std::nothrow) hg_darnoldi();
+    if (!a) {
+        hg_set_error("hg_darnoldi_create: out of host memory");
+        return HG_ERR_NOMEM;
+    }
+    a->ctx = ctx;
+    a->comm = comm;
+    a->A = A_p;
+    a->B = B_p;
+    a->kmax = kmax;
+    a->n = A_p->cols;
+    a->m_p = A_p->rows;
+    const int P = comm->nranks;
+    a->n_p = round_up((a->n + P - 1) / P, 32);  // equal, 256-byte aligned slices (NCCL needs equal counts)
+    a->n_pad = a->n_p * P;
+    a->ldq = a->n_p;
+    a->ldt = round_up(std::max<int64_t>(a->m_p, 1), 32);
+    const int nslabs = hg_multidot_nslabs(ctx, std::max(a->n_p, a->m_p));
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](double** p, size_t cnt) {
+        if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(cnt, 1) * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, std::max<size_t>(cnt, 1) * sizeof(double), ctx->stream);
+    };
+    alloc(&a->Q, (size_t)a->ldq * (kmax + 1));
+    alloc(&a->T, (size_t)a->ldt * (kmax + 1));
+    alloc(&a->q_full, (size_t)a->n_pad);
+    alloc(&a->w_part, (size_t)a->n_pad);
+    alloc(&a->w0, (size_t)a->n_p);
+    alloc(&a->w1, (size_t)a->n_p);
+    alloc(&a->d_H, (size_t)a->ldh() * kmax);
+    alloc(&a->d_hcur, (size_t)kmax + 1);
+    alloc(&a->d_s, 8);
+    alloc(&a->partials, (size_t)(kmax + 2) * (size_t)(nslabs + 1));
+    alloc(&a->stat, (size_t)std::max(a->n_pad, a->m_p) / 8 + 2048);
+    if (e == cudaSuccess) e = cudaMallocHost(&a->h_H, (size_t)a->ldh() * kmax * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost(&a->h_beta, 8 * sizeof(double));
+    if (e != cudaSuccess) {
+        hg_set_error("hg_darnoldi_create: allocation failed: %s", cudaGetErrorString(e));
+        hg_darnoldi_destroy(a);
+        return HG_ERR_NOMEM;
+    }
+    *out = a;
+    return HG_OK;
+}
+
+extern "C" int hg_darnoldi_set_rhs(hg_darnoldi* a, const double* b_p) {
+    HG_REQUIRE(a && (b_p || a->m_p == 0), "hg_darnoldi_set_rhs: NULL argument");
+    HG_CUDA(cudaSetDevice(a->ctx->device));
+    if (a->m_p)
+        HG_CUDA(cudaMemcpyAsync(a->T, b_p, (size_t)a->m_p * 8, cudaMemcpyHostToDevice, a->ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(a->ctx->stream));
+    a->have_rhs = true;
+    return HG_OK;
+}
+
+// global norm of a slice vector: d_s[0] <- sqrt(allreduce(sum v^2)); then v /= d_s[0] and all-gather
+static int normalise_and_gather(hg_darnoldi* a, double* v_slice, double* norm_out_dev) {
+    hg_ctx* ctx = a->ctx;
+    cudaStream_t st = ctx->stream;
+    HG_NCCL(g_nccl.AllReduce(a->d_s, a->d_s, 1, ncclDouble, ncclSum, a->comm->comm, st));
+    HG_TRY(hg_k_reduce(ctx, a->d_s, 1, 1, norm_out_dev, false, nullptr, true));  // sqrt of the global sum
+    HG_TRY(hg_k_scale_div(ctx, v_slice, a->n_p, norm_out_dev));
+    HG_NCCL(g_nccl.AllGather(v_slice, a->q_full, (size_t)a->n_p, ncclDouble, a->comm->comm, st));
+    return HG_OK;
+}
+
+extern "C" int hg_darnoldi_reset(hg_darnoldi* a, double shift) {
+    HG_REQUIRE(a, "hg_darnoldi_reset: NULL");
+    if (!a->have_rhs) {
+        hg_set_error("hg_darnoldi_reset: right-hand side not set");
+        return HG_ERR_STATE;
+    }
+    hg_ctx* ctx = a->ctx;
+    cudaStream_t st = ctx->stream;
+    HG_CUDA(cudaSetDevice(ctx->device));
+    a->shift = shift;
+    a->k = 0;
+    HG_CUDA(cudaStreamSynchronize(st));
+    memset(a->h_H, 0, (size_t)a->ldh() * a->kmax * sizeof(double));
+    HG_CUDA(cudaMemsetAsync(a->d_H, 0, (size_t)a->ldh() * a->kmax * sizeof(double), st));
+    // r0 = B*b = sum_p B^p b_p  (hybrid_ba_gmres_rtp.m:7-9)
+    hg_spmv_epilogue ep;
+    HG_TRY(hg_k_spmv(ctx, a->B, a->T, a->w_part, ep, nullptr));
+    HG_NCCL(g_nccl.ReduceScatter(a->w_part, a->Q, (size_t)a->n_p, ncclDouble, ncclSum, a->comm->comm, st));
+    int np = 0;
+    HG_TRY(hg_k_sumsq(ctx, a->Q, a->n_p, a->stat, &np));
+    HG_TRY(hg_k_reduce(ctx, a->stat, np, 1, a->d_s, false, nullptr, false));
+    HG_TRY(normalise_and_gather(a, a->Q, a->d_s + 1));  // beta in d_s[1]
+    HG_CUDA(cudaMemcpyAsync(a->h_beta, a->d_s + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+    a->started = true;
+    return HG_OK;
+}
+
+static int darnoldi_step(hg_darnoldi* a, int kk) {
+    hg_ctx* ctx = a->ctx;
+    cudaStream_t st = ctx->stream;
+    const double* q_slice = a->Q + (size_t)(kk - 1) * a->ldq;
+    double* tcol = a->T + (size_t)kk * a->ldt;
+    double* qnext = a->Q + (size_t)kk * a->ldq;
+    double* Hcol = a->d_H + (size_t)(kk - 1) * a->ldh();
+    hg_spmv_epilogue ep;
+    HG_TRY(hg_k_spmv(ctx, a->A, a->q_full, tcol, ep, nullptr));       // u_p = A_p q
+    HG_TRY(hg_k_spmv(ctx, a->B, tcol, a->w_part, ep, nullptr));       // partial B^p u_p
+    HG_NCCL(g_nccl.ReduceScatter(a->w_part, a->w1, (size_t)a->n_p, ncclDouble, ncclSum, a->comm->comm, st));
+    // w0 = w + shift*q on the slice
+    HG_TRY(hg_k_axpby(ctx, a->n_p, 1.0, a->w1, a->shift, q_slice, a->w0, nullptr, nullptr, nullptr));
+    int ns = 0, np = 0;
+    // CGS2 pass 1
+    HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->n_p, kk, a->w0, a->partials, &ns));
+    HG_TRY(hg_k_reduce(ctx, a->partials, ns, kk, a->d_hcur, false, nullptr, false));
+    HG_NCCL(g_nccl.AllReduce(a->d_hcur, a->d_hcur, (size_t)kk, ncclDouble, ncclSum, a->comm->comm, st));
+    HG_CUDA(cudaMemcpyAsync(Hcol, a->d_hcur, (size_t)kk * 8, cudaMemcpyDeviceToDevice, st));
+    HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr, nullptr, nullptr));
+    // pass 2
+    HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->n_p, kk, a->w1, a->partials, &ns));
+    HG_TRY(hg_k_reduce(ctx, a->partials, ns, kk, a->d_hcur, false, nullptr, false));
+    HG_NCCL(g_nccl.AllReduce(a->d_hcur, a->d_hcur, (size_t)kk, ncclDouble, ncclSum, a->comm->comm, st));
+    HG_TRY(hg_k_axpby(ctx, kk, 1.0, Hcol, 1.0, a->d_hcur, Hcol, nullptr, nullptr, nullptr));  // H(1:k,k) = h1 + h2
+    HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w1, qnext, nullptr, a->stat, &np));
+    HG_TRY(hg_k_reduce(ctx, a->stat, np, 1, a->d_s, false, nullptr, false));
+    HG_TRY(normalise_and_gather(a, qnext, Hcol + kk));
+    HG_CUDA(cudaMemcpyAsync(a->h_H + (size_t)(kk - 1) * a->ldh(), Hcol, (size_t)(kk + 1) * 8,
+                            cudaMemcpyDeviceToHost, st));
+    return HG_OK;
+}
+
+extern "C" int hg_darnoldi_steps(hg_darnoldi* a, int nsteps) {
+    HG_REQUIRE(a, "hg_darnoldi_steps: NULL");
+    if (!a->started) {
+        hg_set_error("hg_darnoldi_steps: call hg_darnoldi_reset first");
+        return HG_ERR_STATE;
+    }
+    HG_REQUIRE(nsteps >= 0 && a->k + nsteps <= a->kmax, "hg_darnoldi_steps: exceeds kmax");
+    HG_CUDA(cudaSetDevice(a->ctx->device));
+    for (int i = 0; i < nsteps; ++i) {
+        HG_TRY(darnoldi_step(a, a->k + 1));
+        a->k += 1;
+    }
+    return HG_OK;
+}
+
+extern "C" int hg_darnoldi_get(hg_darnoldi* a, double* H, int ldh, double* beta, int* ksteps) {
+    HG_REQUIRE(a, "hg_darnoldi_get: NULL");
+    HG_CUDA(cudaStreamSynchronize(a->ctx->stream));
+    if (H) {
+        HG_REQUIRE(ldh >= a->ldh(), "hg_darnoldi_get: ldh too small");
+        for (int j = 0; j < a->kmax; ++j)
+            memcpy(H + (size_t)j * ldh, a->h_H + (size_t)j * a->ldh(), (size_t)a->ldh() * 8);
+    }
+    if (beta) *beta = a->h_beta[0];
+    if (ksteps) *ksteps = a->k;
+    return HG_OK;
+}
+
+// local slice (n_p entries, zero padded) of basis vector j; *row0 receives its first global row
+extern "C" int hg_darnoldi_get_q(hg_darnoldi* a, int j, double* q_slice, int64_t* row0, int64_t* nrows) {
+    HG_REQUIRE(a && q_slice, "hg_darnoldi_get_q: NULL");
+    HG_REQUIRE(j >= 0 && j <= a->kmax, "hg_darnoldi_get_q: column out of range");
+    HG_CUDA(cudaMemcpyAsync(q_slice, a->Q + (size_t)j * a->ldq, (size_t)a->n_p * 8, cudaMemcpyDeviceToHost,
+                            a->ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(a->ctx->stream));
+    if (row0) *row0 = (int64_t)a->comm->rank * a->n_p;
+    if (nrows) *nrows = a->n_p;
+    return HG_OK;
+}
+
+extern "C" int hg_darnoldi_step_bytes(hg_darnoldi* a, int k, double* bytes) {
+    HG_REQUIRE(a && bytes, "hg_darnoldi_step_bytes: NULL");
+    // this rank's share of S(k) plus the replicated q / partial w vectors
+    const double np = (double)a->n_p, mp = (double)a->m_p, n = (double)a->n_pad;
+    *bytes = 12.0 * ((double)a->A->nnz + (double)a->B->nnz) + 8.0 * (mp + n + 2.0) + 16.0 * mp + 16.0 * n +
+             72.0 * np + 32.0 * (double)k * np;
+    return HG_OK;
+}

@@ -80,3 +80,29 @@ def shepp_logan(N: int) -> np.ndarray:
         yr = -(X - x0) * math.sin(ph) + (Y - y0) * math.cos(ph)
         img[(xr / a) ** 2 + (yr / b) ** 2 <= 1.0] += amp
     return img.ravel(order="F")
+
+
+def ct_projector_rows(N, angles_deg, p, geometry, row_lo, row_hi, R=None, ctx: Context | None = None) -> DeviceMatrix:
+    """Rows ``[row_lo,row_hi)`` (rays, view-major) of the projector — one rank's ``A_p``."""
+    ctx = ctx or default_context()
+    if R is None:
+        R = 2.0 * N
+    c, s, a, b = (np.ascontiguousarray(t) for t in ray_tables(N, angles_deg, p, geometry, R))
+    h = C.c_void_p()
+    check(ctx._lib.hg_ct_projector_rows(ctx._h, int(N), int(c.shape[0]), int(p), _geom(geometry), float(R),
+                                        _ptr(c), _ptr(s), _ptr(a), _ptr(b), int(row_lo), int(row_hi), C.byref(h)))
+    return DeviceMatrix(h, ctx)
+
+
+def ct_backprojector_cols(N, angles_deg, p, geometry, col_lo, col_hi, R=None, ctx: Context | None = None) -> DeviceMatrix:
+    """Sinogram columns ``[col_lo,col_hi)`` of the back-projector (local column indices) —
+    one rank's ``B^p``."""
+    ctx = ctx or default_context()
+    if R is None:
+        R = 2.0 * N
+    th = np.deg2rad(np.asarray(angles_deg, dtype=float))
+    c, s = np.ascontiguousarray(np.cos(th)), np.ascontiguousarray(np.sin(th))
+    h = C.c_void_p()
+    check(ctx._lib.hg_ct_backprojector_cols(ctx._h, int(N), int(c.shape[0]), int(p), _geom(geometry), float(R),
+                                            _ptr(c), _ptr(s), int(col_lo), int(col_hi), C.byref(h)))
+    return DeviceMatrix(h, ctx)

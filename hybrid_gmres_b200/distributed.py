@@ -1,0 +1,89 @@
+"""One-process-per-GPU sharded Arnoldi (``hg_darnoldi_*``).  ``torch.distributed`` is used
+only to broadcast the NCCL unique id; the collectives between the kernels (reduce-scatter,
+all-reduce, all-gather) are issued by ``libhgmres.so`` on its own stream."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check
+from .api import Context, DeviceMatrix, _ptr, _vec
+from .sharding import slice_len
+
+
+class Communicator:
+    """``hg_comm``: an NCCL communicator over all ranks of the default process group."""
+
+    def __init__(self, ctx: Context, rank: int | None = None, world: int | None = None):
+        import torch
+        import torch.distributed as dist
+        if rank is None:
+            rank = dist.get_rank()
+        if world is None:
+            world = dist.get_world_size()
+        self.ctx, self.rank, self.world = ctx, rank, world
+        uid = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            check(ctx._lib.hg_comm_unique_id(_ptr(uid)))
+        if world > 1:
+            t = torch.from_numpy(uid)
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+                dist.broadcast(t, src=0)
+                uid = t.cpu().numpy()
+            else:
+                dist.broadcast(t, src=0)
+        h = C.c_void_p()
+        check(ctx._lib.hg_comm_init(ctx._h, world, rank, _ptr(np.ascontiguousarray(uid)), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.hg_comm_destroy(self._h)
+            self._h = None
+
+
+class ShardedArnoldi:
+    """CGS2 Arnoldi on ``B*A + shift*I`` with ``A`` row-sharded and ``B`` column-sharded."""
+
+    def __init__(self, comm: Communicator, A_p: DeviceMatrix, B_p: DeviceMatrix, kmax: int):
+        self.comm, self.ctx = comm, comm.ctx
+        self.A_p, self.B_p, self.kmax = A_p, B_p, int(kmax)
+        self.n = A_p.shape[1]
+        self.n_p = slice_len(self.n, comm.world)
+        h = C.c_void_p()
+        check(self.ctx._lib.hg_darnoldi_create(self.ctx._h, comm._h, A_p._h, B_p._h, self.kmax, C.byref(h)))
+        self._h = h
+
+    def set_rhs(self, b_p):
+        b_p = _vec(b_p, self.A_p.shape[0], "b_p")
+        check(self.ctx._lib.hg_darnoldi_set_rhs(self._h, _ptr(b_p)))
+
+    def reset(self, shift: float):
+        check(self.ctx._lib.hg_darnoldi_reset(self._h, float(shift)))
+
+    def steps(self, n: int):
+        check(self.ctx._lib.hg_darnoldi_steps(self._h, int(n)))
+
+    def get(self):
+        H = np.zeros((self.kmax + 1, self.kmax), order="F")
+        beta, k = C.c_double(), C.c_int()
+        check(self.ctx._lib.hg_darnoldi_get(self._h, _ptr(H), self.kmax + 1, C.byref(beta), C.byref(k)))
+        return H, beta.value, k.value
+
+    def q_slice(self, j: int):
+        q = np.empty(self.n_p)
+        r0, nr = C.c_int64(), C.c_int64()
+        check(self.ctx._lib.hg_darnoldi_get_q(self._h, int(j), _ptr(q), C.byref(r0), C.byref(nr)))
+        return q, int(r0.value)
+
+    def step_bytes(self, k: int) -> float:
+        out = C.c_double()
+        check(self.ctx._lib.hg_darnoldi_step_bytes(self._h, int(k), C.byref(out)))
+        return out.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.hg_darnoldi_destroy(self._h)
+            self._h = None

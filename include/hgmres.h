@@ -122,6 +122,15 @@ int hg_ct_projector(hg_ctx* ctx, int N, int n_views, int p, int geometry, double
 int hg_ct_backprojector(hg_ctx* ctx, int N, int n_views, int p, int geometry, double R,
                         const double* cos_th, const double* sin_th, hg_matrix** out);
 
+/* Shards for the multi-GPU path: rays [row_lo,row_hi) of the projector (rows of A), and the
+ * sinogram columns [col_lo,col_hi) of the back-projector (column block of B, local indices). */
+int hg_ct_projector_rows(hg_ctx* ctx, int N, int n_views, int p, int geometry, double R,
+                         const double* cos_th, const double* sin_th, const double* ray_a,
+                         const double* ray_b, int64_t row_lo, int64_t row_hi, hg_matrix** out);
+int hg_ct_backprojector_cols(hg_ctx* ctx, int N, int n_views, int p, int geometry, double R,
+                             const double* cos_th, const double* sin_th, int64_t col_lo, int64_t col_hi,
+                             hg_matrix** out);
+
 /* ---- building blocks on host vectors (tests, setup) ---------------------- */
 /* y = M x */
 int hg_spmv(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y);
@@ -153,6 +162,26 @@ int hg_arnoldi_get(hg_arnoldi* a, double* H, int ldh, double* beta, int* ksteps)
 int hg_arnoldi_get_q(hg_arnoldi* a, int j, double* q);
 /* algorithmic bytes of Arnoldi step k (1-based), SURVEY.md §8d S(k) */
 int hg_arnoldi_step_bytes(hg_arnoldi* a, int k, double* bytes);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ---------------- */
+typedef struct hg_comm hg_comm;
+typedef struct hg_darnoldi hg_darnoldi;
+/* rank 0 creates a 128-byte NCCL unique id; the caller broadcasts it (torch.distributed) */
+int hg_comm_unique_id(void* out128);
+int hg_comm_init(hg_ctx* ctx, int nranks, int rank, const void* id128, hg_comm** out);
+int hg_comm_destroy(hg_comm* c);
+/* Sharded n-space Arnoldi.  A_p: this rank's detector-row block of A (m_p x n); B_p: the
+ * matching column block of B (n x m_p, local column indices).  Krylov vectors are sharded in
+ * equal row slices of n_p = roundup32(ceil(n/P)) entries (zero padded). */
+int hg_darnoldi_create(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_p, const hg_matrix* B_p, int kmax,
+                       hg_darnoldi** out);
+int hg_darnoldi_destroy(hg_darnoldi* a);
+int hg_darnoldi_set_rhs(hg_darnoldi* a, const double* b_p); /* this rank's m_p entries of b */
+int hg_darnoldi_reset(hg_darnoldi* a, double shift);
+int hg_darnoldi_steps(hg_darnoldi* a, int nsteps);
+int hg_darnoldi_get(hg_darnoldi* a, double* H, int ldh, double* beta, int* ksteps);
+int hg_darnoldi_get_q(hg_darnoldi* a, int j, double* q_slice, int64_t* row0, int64_t* nrows);
+int hg_darnoldi_step_bytes(hg_darnoldi* a, int k, double* bytes);
 
 /* ---- whole solvers: the reference signatures ----------------------------- */
 typedef struct hg_solver_opts {

@@ -1,0 +1,66 @@
+"""Multi-GPU worker (torchrun, one process per GPU): sharded device Arnoldi vs the oracle.
+Also exercises the sharded device CT generators against the host shards."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import hybrid_gmres_b200 as hg  # noqa: E402
+import oracle  # noqa: E402
+from hybrid_gmres_b200 import sharding  # noqa: E402
+from hybrid_gmres_b200.distributed import Communicator, ShardedArnoldi  # noqa: E402
+from oracle import ct  # noqa: E402
+
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local_rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+rank, P = dist.get_rank(), dist.get_world_size()
+ctx = hg.Context(local_rank)
+comm = Communicator(ctx)
+
+N, nv, K, lam = 40, 60, 30, 1e-2
+A, B, b, x_true = ct.make_ct_problem(N, nv, "fan", "pixel")
+n = A.shape[1]
+A_p, B_p, (lo, hi) = sharding.shard_host_matrices(A, B, P, rank)
+dA, dB = hg.DeviceMatrix.from_any(A_p, ctx), hg.DeviceMatrix.from_any(B_p, ctx)
+ar = ShardedArnoldi(comm, dA, dB, K)
+ar.set_rhs(b[lo:hi])
+ar.reset(lam)
+ar.steps(K)
+H, beta, k = ar.get()
+op = lambda v: np.asarray(B @ (A @ v)).ravel() + lam * v
+Qo, Ho, betao, _ = oracle.arnoldi(op, np.asarray(B @ b).ravel(), K, orth="cgs2")
+assert k == K
+assert abs(beta - betao) / betao < 1e-13, (beta, betao)
+worst = max(np.linalg.norm(H[:j + 2, j] - Ho[:j + 2, j]) / np.linalg.norm(Ho[:j + 2, j]) for j in range(K))
+assert worst < 1e-10, worst
+q, r0 = ar.q_slice(K)
+seg = Qo[r0:min(r0 + ar.n_p, n), K]
+assert np.linalg.norm(q[:seg.shape[0]] - seg) < 1e-9 and np.all(q[seg.shape[0]:] == 0)
+# all ranks hold bit-identical H (replicated host projected problem relies on it)
+t = torch.from_numpy(H.copy()).cuda()
+t0 = t.clone()
+dist.broadcast(t0, src=0)
+assert torch.equal(t, t0)
+
+# sharded device generators == host shards
+angles = np.arange(nv) * (360.0 / nv)
+p = int(round(np.sqrt(2.0) * N))
+import ctypes as C  # noqa: E402
+from hybrid_gmres_b200.ct import ct_backprojector_cols, ct_projector_rows  # noqa: E402
+gA = ct_projector_rows(N, angles, p, "fan", lo, hi, ctx=ctx)
+ip, ix, dv = gA.download()
+assert np.array_equal(ip, A_p.indptr) and np.array_equal(ix, A_p.indices) and np.array_equal(dv, A_p.data)
+gB = ct_backprojector_cols(N, angles, p, "fan", lo, hi, ctx=ctx)
+ip, ix, dv = gB.download()
+Bs = B_p.copy()
+Bs.sort_indices()
+assert np.array_equal(ip, Bs.indptr) and np.array_equal(ix, Bs.indices) and np.allclose(dv, Bs.data, rtol=1e-12, atol=1e-12)
+print("NCCL_OK", rank, worst, flush=True)
+ar.close()
+comm.close()
+dist.destroy_process_group()

@@ -23,4 +23,4 @@ def load(name):
 def strict_iters(name):
     """Iterations over which 1e-8 parity is meaningful: on deriv2 n=32 the Arnoldi / GKB
     processes break down numerically after ~5 steps."""
-    return 5 if name == "deriv2_n32" else 8
+    return 4 if name == "deriv2_n32" else 8
