@@ -1,6 +1,7 @@
 // Device Arnoldi (CGS2) and the solvers built on it:
 //   hybrid_ab_gmres_rtp.m, hybrid_ba_gmres_rtp.m, gcv_function.m
 #include <algorithm>
+#include <chrono>
 #include <memory>
 
 #include "common.cuh"
@@ -311,6 +312,10 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     HG_CUDA(cudaSetDevice(ctx->device));
     const int residual_mode = opts ? opts->residual_mode : 0;
     const int64_t n = A->cols, m = A->rows;
+    const bool trace = getenv("HG_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_host = 0.0, t_wait = 0.0;
     ArnoldiHolder holder;
     HG_TRY(hg_arnoldi_create(ctx, A, B, HG_SPACE_N, maxit, &holder.a));
     hg_arnoldi* a = holder.a;
@@ -336,6 +341,7 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     HG_CUDA(cudaStreamSynchronize(ctx->stream));
     const double beta = a->h_beta[0];
 
+    const double t_setup = now();
     for (int i = 0; i < maxit; ++i) error_norm[i] = residual_norm[i] = 0.0;
     hgd::HessenbergLS ls;
     hgd::BorderedCholesky chol;
@@ -360,7 +366,10 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
             HG_TRY(hg_k_reduce(ctx, a->partials, ns, k + 1, d_g.p, false, nullptr, false));
             HG_CUDA(cudaMemcpyAsync(h_g.p, d_g.p, (size_t)(k + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         }
+        double tw = now();
         HG_CUDA(cudaStreamSynchronize(ctx->stream));
+        t_wait += now() - tw;
+        const double th = now();
         const double* hcol = a->h_H + (size_t)(k - 1) * ldh;
         if (hcol[k] == 0.0) break;  // :25 — leaves before x / histories are touched
         if (kind == RTP_BA) {
@@ -383,6 +392,7 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
                 hgd::solve_square(k, M.data(), k, rhs.data(), h_y.p);
             }
         }
+        t_host += now() - th;
         HG_CUDA(cudaMemcpyAsync(d_y.p, h_y.p, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
         // x = Q(:,1:k)*yk fused with ||x - x_true||^2          (:33,36 / :30,33)
         int np_e = 0, np_r = 0;
@@ -405,7 +415,9 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
         if (extras && extras->X_hist)
             HG_CUDA(cudaMemcpyAsync(extras->X_hist + (size_t)(k - 1) * n, d_x.p, (size_t)n * 8,
                                     cudaMemcpyDeviceToHost, ctx->stream));
+        tw = now();
         HG_CUDA(cudaStreamSynchronize(ctx->stream));
+        t_wait += now() - tw;
         have_x = true;
         residual_norm[k - 1] = h_s.p[1] / norm_b;
         error_norm[k - 1] = h_s.p[0] / norm_xt;
@@ -415,6 +427,9 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     *niters = k;
     HG_CUDA(cudaMemcpyAsync(x, d_x.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (trace)
+        fprintf(stderr, "[hg trace] rtp %s: setup %.1f ms, loop %.1f ms (host solve %.1f, gpu wait %.1f), k=%d\n",
+                kind == RTP_AB ? "AB" : "BA", t_setup - t_begin, now() - t_setup, t_host, t_wait, k);
     if (x_valid) *x_valid = have_x ? 1 : 0;
     if (extras) {
         if (extras->beta) *extras->beta = beta;
