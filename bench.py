@@ -345,8 +345,8 @@ def main():
             try:
                 hg._lib.check(ctx._lib.hg_host_register(arr.ctypes.data, arr.nbytes))
                 pinned.append(arr)
-            except Exception:
-                pass
+            except Exception as exc:  # pageable upload still works, only slower
+                print(f"[bench] hg_host_register failed for a {arr.nbytes}-byte array: {exc}", file=sys.stderr)
         ar.close()
         del ar
         Ke = max(1, min(K, 3))

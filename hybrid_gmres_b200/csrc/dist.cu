@@ -344,3 +344,152 @@ extern "C" int hg_darnoldi_step_bytes(hg_darnoldi* a, int k, double* bytes) {
              72.0 * np + 32.0 * (double)k * np;
     return HG_OK;
 }
+
+// ===========================================================================
+// Sharded RTP solvers: hybrid_ab_gmres_rtp.m / hybrid_ba_gmres_rtp.m on row-sharded A,
+// column-sharded B.  The projected problem is solved redundantly on every rank from the
+// all-reduced (bit-identical) H / Gram data, so all ranks take the same decisions.
+// ===========================================================================
+#include "dense_host.h"
+
+namespace {
+struct DBufD {
+    double* p = nullptr;
+    ~DBufD() { if (p) cudaFree(p); }
+    int alloc(size_t n) {
+        if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double)) != cudaSuccess) {
+            hg_set_error("device allocation of %zu doubles failed", n);
+            return HG_ERR_NOMEM;
+        }
+        return HG_OK;
+    }
+};
+struct PinD {
+    double* p = nullptr;
+    ~PinD() { if (p) cudaFreeHost(p); }
+    int alloc(size_t n) {
+        if (cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(double)) != cudaSuccess) {
+            hg_set_error("pinned allocation of %zu doubles failed", n);
+            return HG_ERR_NOMEM;
+        }
+        return HG_OK;
+    }
+};
+struct DHolder {
+    hg_darnoldi* a = nullptr;
+    ~DHolder() { hg_darnoldi_destroy(a); }
+};
+}  // namespace
+
+// kind 0: AB-RTP, 1: BA-RTP.  b_p: this rank's m_p entries of b; x_true, x: full n-vectors
+// (replicated on the host of every rank).
+extern "C" int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_p,
+                                  const hg_matrix* B_p, const double* b_p, const double* x_true, double tol,
+                                  int maxit, double lambda, double* x, double* error_norm,
+                                  double* residual_norm, int* niters, int* x_valid, hg_extras* extras) {
+    HG_REQUIRE(ctx && comm && A_p && B_p && x_true && x && error_norm && residual_norm && niters,
+               "hg_dist_hybrid_rtp: NULL argument");
+    HG_REQUIRE(kind == 0 || kind == 1, "hg_dist_hybrid_rtp: kind must be 0 (AB) or 1 (BA)");
+    HG_REQUIRE(maxit >= 1, "hg_dist_hybrid_rtp: maxit must be >= 1");
+    HG_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DHolder holder;
+    HG_TRY(hg_darnoldi_create(ctx, comm, A_p, B_p, maxit, &holder.a));
+    hg_darnoldi* a = holder.a;
+    const int64_t n = a->n, n_p = a->n_p, m_p = a->m_p;
+    const int64_t row0 = (int64_t)comm->rank * n_p;
+    const int64_t nloc = std::max<int64_t>(0, std::min(n, row0 + n_p) - row0);
+    DBufD d_x, d_xt, d_y, d_g, stat_e, stat_r, d_xfull;
+    PinD h_y, h_g, h_s;
+    HG_TRY(d_x.alloc((size_t)n_p)); HG_TRY(d_xt.alloc((size_t)n_p)); HG_TRY(d_y.alloc((size_t)maxit + 1));
+    HG_TRY(d_g.alloc((size_t)maxit + 2)); HG_TRY(stat_e.alloc((size_t)std::max(n_p, m_p) / 8 + 2048));
+    HG_TRY(stat_r.alloc((size_t)std::max(n_p, m_p) / 8 + 2048)); HG_TRY(d_xfull.alloc((size_t)a->n_pad));
+    HG_TRY(h_y.alloc((size_t)maxit + 1)); HG_TRY(h_g.alloc((size_t)maxit + 2)); HG_TRY(h_s.alloc(8));
+    HG_CUDA(cudaMemsetAsync(d_x.p, 0, (size_t)n_p * 8, st));
+    HG_CUDA(cudaMemsetAsync(d_xt.p, 0, (size_t)n_p * 8, st));
+    if (nloc > 0)
+        HG_CUDA(cudaMemcpyAsync(d_xt.p, x_true + row0, (size_t)nloc * 8, cudaMemcpyHostToDevice, st));
+    HG_TRY(hg_darnoldi_set_rhs(a, b_p));
+    // global ||b||, ||x_true||
+    int np = 0;
+    HG_TRY(hg_k_sumsq(ctx, a->T, m_p, stat_e.p, &np));
+    HG_TRY(hg_k_reduce(ctx, stat_e.p, np, 1, ctx->d_scalars + 3, false, nullptr, false));
+    HG_TRY(hg_k_sumsq(ctx, d_xt.p, n_p, stat_r.p, &np));
+    HG_TRY(hg_k_reduce(ctx, stat_r.p, np, 1, ctx->d_scalars + 4, false, nullptr, false));
+    HG_NCCL(g_nccl.AllReduce(ctx->d_scalars + 3, ctx->d_scalars + 3, 2, ncclDouble, ncclSum, comm->comm, st));
+    HG_CUDA(cudaMemcpyAsync(h_s.p + 2, ctx->d_scalars + 3, 16, cudaMemcpyDeviceToHost, st));
+    HG_TRY(hg_darnoldi_reset(a, lambda));
+    HG_CUDA(cudaStreamSynchronize(st));
+    const double norm_b = std::sqrt(h_s.p[2]), norm_xt = std::sqrt(h_s.p[3]);
+    const double beta = a->h_beta[0];
+    for (int i = 0; i < maxit; ++i) error_norm[i] = residual_norm[i] = 0.0;
+    hgd::HessenbergLS ls;
+    hgd::BorderedCholesky chol;
+    std::vector<double> Gfull, rhs;
+    bool chol_ok = true;
+    if (kind == 1) ls.reset(maxit, beta);
+    else {
+        chol.reset(maxit, lambda);
+        Gfull.assign((size_t)maxit * maxit, 0.0);
+        rhs.assign(maxit, 0.0);
+    }
+    bool have_x = (kind == 1);
+    const int ldh = a->ldh();
+    int k;
+    for (k = 1; k <= maxit; ++k) {
+        HG_TRY(hg_darnoldi_steps(a, 1));
+        if (kind == 0) {
+            int ns = 0;
+            HG_TRY(hg_k_multidot(ctx, a->T, a->ldt, m_p, k + 1, a->T + (size_t)k * a->ldt, a->partials, &ns));
+            HG_TRY(hg_k_reduce(ctx, a->partials, ns, k + 1, d_g.p, false, nullptr, false));
+            HG_NCCL(g_nccl.AllReduce(d_g.p, d_g.p, (size_t)(k + 1), ncclDouble, ncclSum, comm->comm, st));
+            HG_CUDA(cudaMemcpyAsync(h_g.p, d_g.p, (size_t)(k + 1) * 8, cudaMemcpyDeviceToHost, st));
+        }
+        HG_CUDA(cudaStreamSynchronize(st));
+        const double* hcol = a->h_H + (size_t)(k - 1) * ldh;
+        if (hcol[k] == 0.0) break;
+        if (kind == 1) {
+            ls.add_column(hcol);
+            ls.solve(h_y.p);
+        } else {
+            rhs[k - 1] = h_g.p[0];
+            for (int j = 0; j < k; ++j) {
+                Gfull[(size_t)(k - 1) * maxit + j] = h_g.p[1 + j];
+                Gfull[(size_t)j * maxit + (k - 1)] = h_g.p[1 + j];
+            }
+            if (chol_ok) chol_ok = chol.add_row(h_g.p + 1);
+            if (chol_ok) chol.solve(rhs.data(), h_y.p);
+            else {
+                std::vector<double> M((size_t)k * k);
+                for (int j = 0; j < k; ++j)
+                    for (int i2 = 0; i2 < k; ++i2)
+                        M[(size_t)j * k + i2] = Gfull[(size_t)j * maxit + i2] + (i2 == j ? lambda : 0.0);
+                hgd::solve_square(k, M.data(), k, rhs.data(), h_y.p);
+            }
+        }
+        HG_CUDA(cudaMemcpyAsync(d_y.p, h_y.p, (size_t)k * 8, cudaMemcpyHostToDevice, st));
+        int np_e = 0, np_r = 0;
+        HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n_p, k, d_y.p, 1.0, nullptr, d_x.p, d_xt.p, stat_e.p, &np_e));
+        HG_TRY(hg_k_lincomb(ctx, a->T + a->ldt, a->ldt, m_p, k, d_y.p, -1.0, a->T, nullptr, nullptr, stat_r.p, &np_r));
+        HG_TRY(hg_k_reduce(ctx, stat_e.p, np_e, 1, ctx->d_scalars + 1, false, nullptr, false));
+        HG_TRY(hg_k_reduce(ctx, stat_r.p, np_r, 1, ctx->d_scalars + 2, false, nullptr, false));
+        HG_NCCL(g_nccl.AllReduce(ctx->d_scalars + 1, ctx->d_scalars + 1, 2, ncclDouble, ncclSum, comm->comm, st));
+        HG_CUDA(cudaMemcpyAsync(h_s.p, ctx->d_scalars + 1, 16, cudaMemcpyDeviceToHost, st));
+        HG_CUDA(cudaStreamSynchronize(st));
+        have_x = true;
+        error_norm[k - 1] = std::sqrt(h_s.p[0]) / norm_xt;
+        residual_norm[k - 1] = std::sqrt(h_s.p[1]) / norm_b;
+        if (residual_norm[k - 1] <= tol) break;
+    }
+    if (k > maxit) k = maxit;
+    *niters = k;
+    HG_NCCL(g_nccl.AllGather(d_x.p, d_xfull.p, (size_t)n_p, ncclDouble, comm->comm, st));
+    HG_CUDA(cudaMemcpyAsync(x, d_xfull.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    HG_CUDA(cudaStreamSynchronize(st));
+    if (x_valid) *x_valid = have_x ? 1 : 0;
+    if (extras) {
+        if (extras->beta) *extras->beta = beta;
+        if (extras->H) memcpy(extras->H, a->h_H, (size_t)ldh * maxit * 8);
+    }
+    return HG_OK;
+}

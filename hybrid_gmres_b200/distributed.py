@@ -87,3 +87,38 @@ class ShardedArnoldi:
         if getattr(self, "_h", None):
             self.ctx._lib.hg_darnoldi_destroy(self._h)
             self._h = None
+
+
+def _dist_rtp(kind, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras):
+    from ._lib import HgExtras, c_double_p
+    ctx = comm.ctx
+    maxit = int(maxit)
+    n = A_p.shape[1]
+    b_p = _vec(b_p, A_p.shape[0], "b_p")
+    x_true = _vec(x_true, n, "x_true")
+    x, err, res = np.zeros(n), np.zeros(maxit), np.zeros(maxit)
+    niters, x_valid = C.c_int(), C.c_int()
+    ex, bufs = None, None
+    if extras is not None:
+        bufs = {"H": np.zeros((maxit + 1, maxit), order="F"), "beta": np.zeros(1)}
+        ex = HgExtras()
+        ex.H = bufs["H"].ctypes.data_as(c_double_p)
+        ex.beta = bufs["beta"].ctypes.data_as(c_double_p)
+    check(ctx._lib.hg_dist_hybrid_rtp(kind, ctx._h, comm._h, A_p._h, B_p._h, _ptr(b_p), _ptr(x_true), float(tol),
+                                      maxit, float(lam), _ptr(x), _ptr(err), _ptr(res), C.byref(niters),
+                                      C.byref(x_valid), C.byref(ex) if ex else None))
+    k = niters.value
+    if extras is not None:
+        extras.update(H=bufs["H"], beta=float(bufs["beta"][0]))
+    return (x if x_valid.value else None), err[:k], res[:k], k
+
+
+def hybrid_ab_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lam, *, extras=None):
+    """Sharded ``hybrid_ab_gmres_rtp.m``: ``A_p``/``B_p`` are this rank's shards (device
+    matrices), ``b_p`` its slice of ``b``; returns the reference's four outputs on every rank."""
+    return _dist_rtp(0, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras)
+
+
+def hybrid_ba_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lam, *, extras=None):
+    """Sharded ``hybrid_ba_gmres_rtp.m``."""
+    return _dist_rtp(1, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras)

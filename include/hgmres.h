@@ -256,6 +256,16 @@ int hg_lsmr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At, const d
                    const double* x_true, double tol, int maxit, double* x, double* err_hist,
                    double* res_hist, double* ar_hist, int* iters, hg_extras* extras);
 
+
+/* ---- multi-GPU whole solvers ---------------------------------------------- */
+/* Sharded hybrid_ab_gmres_rtp (kind 0) / hybrid_ba_gmres_rtp (kind 1): same arguments and
+ * outputs as the single-GPU entry points, with A, B given as this rank's shards and b as this
+ * rank's m_p entries; x_true and x are full n-vectors, histories are identical on all ranks. */
+int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_p, const hg_matrix* B_p,
+                       const double* b_p, const double* x_true, double tol, int maxit, double lambda,
+                       double* x, double* error_norm, double* residual_norm, int* niters, int* x_valid,
+                       hg_extras* extras);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,17 @@ ip, ix, dv = gB.download()
 Bs = B_p.copy()
 Bs.sort_indices()
 assert np.array_equal(ip, Bs.indptr) and np.array_equal(ix, Bs.indices) and np.allclose(dv, Bs.data, rtol=1e-12, atol=1e-12)
+# sharded whole solvers vs the oracle
+from hybrid_gmres_b200 import distributed as hgd  # noqa: E402
+for f_dev, f_orc in ((hgd.hybrid_ba_gmres_rtp, oracle.hybrid_ba_gmres_rtp),
+                     (hgd.hybrid_ab_gmres_rtp, oracle.hybrid_ab_gmres_rtp)):
+    for tol in (1e-6, 0.05):
+        xs, errs, ress, its = f_dev(comm, dA, dB, b[lo:hi], x_true, tol, K, lam)
+        xo, erro, reso, ito = f_orc(A, B, b, x_true, tol, K, lam)
+        assert its == ito, (its, ito)
+        assert np.max(np.abs(ress - reso) / reso) < 1e-8
+        assert np.max(np.abs(errs - erro) / erro) < 1e-8
+        assert np.linalg.norm(xs - xo) / np.linalg.norm(xo) < 1e-8
 print("NCCL_OK", rank, worst, flush=True)
 ar.close()
 comm.close()
