@@ -94,7 +94,8 @@ extern "C" int hg_arnoldi_create(hg_ctx* ctx, const hg_matrix* A, const hg_matri
     a->ldq = round_up(std::max<int64_t>(a->nq, 1), 32);
     a->ldt = round_up(std::max<int64_t>(a->nt, 1), 32);
     const int nslabs = hg_multidot_nslabs(ctx, std::max(a->nq, a->nt));
-    const size_t npart = (size_t)(kmax + 2) * (size_t)(nslabs + 1);
+    const size_t npart = (size_t)(kmax + 2) *
+                         (size_t)(std::max(nslabs, hg_update_dot_ntiles(std::max(a->nq, a->nt))) + 1);
     const size_t nstat = (size_t)std::max(a->nq, a->nt) / 8 + 1024;
     cudaError_t e = cudaSuccess;
     auto alloc = [&](double** p, size_t n) {
@@ -198,9 +199,14 @@ static int arnoldi_step(hg_arnoldi* a, int kk) {
     int ns = 0, np = 0;
     HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->nq, kk, a->w0, a->partials, &ns));
     HG_TRY(hg_k_reduce(ctx, a->partials, ns, kk, Hcol, false, a->d_hcur, false));
-    HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr,
-                        nullptr, nullptr));
-    HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->nq, kk, a->w1, a->partials, &ns));
+    if (hg_cgs_fused()) {
+        // v -= Q h1 and h2 = Q' v in one kernel: the second read of the Q tile is an L2 hit
+        HG_TRY(hg_k_update_dot(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, a->w0, a->w1, a->partials, &ns));
+    } else {
+        HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr,
+                            nullptr, nullptr));
+        HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->nq, kk, a->w1, a->partials, &ns));
+    }
     HG_TRY(hg_k_reduce(ctx, a->partials, ns, kk, Hcol, true, a->d_hcur, false));
     HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, -1.0, a->w1, qnext, nullptr,
                         a->stat, &np));

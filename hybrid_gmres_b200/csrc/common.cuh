@@ -136,6 +136,11 @@ int hg_k_lincomb(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, con
                  double s, const double* z, double* out, const double* ref, double* stat,
                  int* nparts);
 
+// fused CGS2 middle stage: w1 = w0 - V h ; partials[j*ntiles + tile] = sum_tile V[:,j].*w1
+int hg_update_dot_ntiles(int64_t n);
+int hg_k_update_dot(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* h,
+                    const double* w0, double* w1, double* partials, int* ntiles);
+
 // v[i] = v[i] / *d_div   (division, as `v / H(k+1,k)` in the reference)
 int hg_k_scale_div(hg_ctx* ctx, double* v, int64_t n, const double* d_div);
 // out = a*x + b*y (y may be null); optional stat of (out-ref)^2
@@ -156,6 +161,9 @@ int hg_k_sumsq(hg_ctx* ctx, const double* x, int64_t n, double* stat, int* npart
 int hg_norm2_sync(hg_ctx* ctx, const double* x, int64_t n, double* out);
 // reduce `np` partials at ctx->d_partials into d_scalars[slot] (optionally sqrt)
 int hg_reduce_to_scalar(hg_ctx* ctx, int np, int slot, bool do_sqrt);
+
+// options (spmv_stream.cu)
+bool hg_cgs_fused();
 
 // streaming SpMV (spmv_stream.cu)
 bool hg_spmv_stream_eligible(const hg_matrix* m);

@@ -251,8 +251,21 @@ static int spmv_mode() {
     return g_spmv_mode;
 }
 
+static int g_cgs_fused = -1;
+bool hg_cgs_fused() {
+    if (g_cgs_fused < 0) {
+        const char* e = getenv("HG_CGS_FUSED");
+        g_cgs_fused = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured slower, profiles/r01_cgs_fusion.md
+    }
+    return g_cgs_fused != 0;
+}
+
 extern "C" int hg_set_option(const char* name, int value) {
     HG_REQUIRE(name, "hg_set_option: NULL name");
+    if (strcmp(name, "cgs_fused") == 0) {
+        g_cgs_fused = value ? 1 : 0;
+        return HG_OK;
+    }
     if (strcmp(name, "spmv_mode") == 0) {
         HG_REQUIRE(value >= 0 && value <= 2, "hg_set_option: spmv_mode must be 0, 1 or 2");
         g_spmv_mode = value;

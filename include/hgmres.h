@@ -62,7 +62,10 @@ const char* hg_last_error(void);
 int hg_version(void);
 
 /* Tuning knobs.  "spmv_mode": 0 auto (default; also env HG_SPMV=v1|v2), 1 force the
- * row-per-warp SpMV, 2 force the TMA-staged streaming SpMV. */
+ * row-per-warp SpMV, 2 force the TMA-staged streaming SpMV.
+ * "cgs_fused": 0 (default; env HG_CGS_FUSED=1 enables) fuses the first CGS2 update with the
+ * second-pass dot products (basis crosses HBM three times per step instead of four; measured
+ * slower than the two separate streaming kernels on B200, see profiles/r01_cgs_fusion.md). */
 int hg_set_option(const char* name, int value);
 
 /* ---- context ------------------------------------------------------------ */

@@ -253,3 +253,23 @@ def test_cross_solver_identity(hg, ctx, ct64):
     hg.hybrid_ab_gmres_rtp(A, B, b, x_true, 0.0, 5, 1e-2, ctx=ctx, extras=e1)
     hg.hybrid_lsqr_solver(A, b, x_true, 0.0, 5, 1e-2, ctx=ctx, extras=e2)
     assert np.max(_iter_rel(e1["X"], e2["X"])) < 1e-8
+
+
+def test_cgs_fused_option_matches_default(hg, ctx, ct64):
+    """The opt-in fused CGS2 middle stage (update + second-pass dot products in one kernel,
+    butterfly transpose-reduce) gives the same Arnoldi factorisation as the separate kernels."""
+    A, B, b, x_true = ct64
+    out = {}
+    try:
+        for fused in (0, 1):
+            hg.set_option("cgs_fused", fused)
+            ex = {}
+            r = hg.hybrid_ba_gmres_rtp(A, B, b, x_true, 1e-6, 45, 1e-2, ctx=ctx, extras=ex)
+            out[fused] = (r, ex)
+    finally:
+        hg.set_option("cgs_fused", 0)
+    (r0, e0), (r1, e1) = out[0], out[1]
+    assert r0[3] == r1[3]
+    assert np.max(_colwise(e1["H"], e0["H"], r0[3])) < 1e-11
+    assert np.max(np.abs(r0[2] - r1[2]) / r0[2]) < 1e-11
+    assert np.linalg.norm(r0[0] - r1[0]) / np.linalg.norm(r0[0]) < 1e-11
