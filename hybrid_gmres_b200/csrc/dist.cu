@@ -493,3 +493,100 @@ extern "C" int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg
     }
     return HG_OK;
 }
+
+// ===========================================================================
+// Sharded gcv_function (gcv_function.m:4-32 on the device, :33-58 on the host).
+//   'ba' (n-space): the sharded Arnoldi above with shift 0 and the <1e-12 breakdown test.
+//   'ab' (m-space): Q is sharded by the detector-row blocks m_p;
+//        z = B q = sum_p B^p q_p  -> ncclAllReduce of the n-vector -> w_p = A_p z (local);
+//        CGS2 on the m_p slices with all-reduced coefficients.  No all-gather is needed.
+// ===========================================================================
+extern "C" int hg_gcv_from_H(const double* H, int ldh, int k, double beta, double trace_m, hg_gcv** out);
+
+static int dist_gcv_ab(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_p, const hg_matrix* B_p,
+                       const double* b_p, int k_gcv, std::vector<double>& H, double* beta_out) {
+    cudaStream_t st = ctx->stream;
+    const int64_t m_p = A_p->rows, n = A_p->cols;
+    const int64_t ldq = round_up(std::max<int64_t>(m_p, 1), 32);
+    const int ldh = k_gcv + 1;
+    const int nslabs = hg_multidot_nslabs(ctx, std::max<int64_t>(m_p, 1));
+    DBufD Q, z, w0, w1, dH, hcur, ds, partials, stat;
+    PinD hH;
+    HG_TRY(Q.alloc((size_t)ldq * (k_gcv + 1))); HG_TRY(z.alloc((size_t)n)); HG_TRY(w0.alloc((size_t)ldq));
+    HG_TRY(w1.alloc((size_t)ldq)); HG_TRY(dH.alloc((size_t)ldh * k_gcv)); HG_TRY(hcur.alloc((size_t)k_gcv + 1));
+    HG_TRY(ds.alloc(8)); HG_TRY(partials.alloc((size_t)(k_gcv + 2) * (nslabs + 1)));
+    HG_TRY(stat.alloc((size_t)std::max(m_p, n) / 8 + 2048)); HG_TRY(hH.alloc((size_t)ldh * k_gcv + 8));
+    HG_CUDA(cudaMemsetAsync(Q.p, 0, (size_t)ldq * (k_gcv + 1) * 8, st));
+    HG_CUDA(cudaMemsetAsync(dH.p, 0, (size_t)ldh * k_gcv * 8, st));
+    memset(hH.p, 0, ((size_t)ldh * k_gcv + 8) * 8);
+    // r0 = b; beta = norm(r0); Q(:,1) = r0/beta            (gcv_function.m:5,12,15)
+    if (m_p) HG_CUDA(cudaMemcpyAsync(Q.p, b_p, (size_t)m_p * 8, cudaMemcpyHostToDevice, st));
+    int np = 0;
+    HG_TRY(hg_k_sumsq(ctx, Q.p, m_p, stat.p, &np));
+    HG_TRY(hg_k_reduce(ctx, stat.p, np, 1, ds.p, false, nullptr, false));
+    HG_NCCL(g_nccl.AllReduce(ds.p, ds.p, 1, ncclDouble, ncclSum, comm->comm, st));
+    HG_TRY(hg_k_reduce(ctx, ds.p, 1, 1, ds.p + 1, false, nullptr, true));
+    HG_TRY(hg_k_scale_div(ctx, Q.p, m_p, ds.p + 1));
+    HG_CUDA(cudaMemcpyAsync(hH.p + (size_t)ldh * k_gcv, ds.p + 1, 8, cudaMemcpyDeviceToHost, st));
+    for (int kk = 1; kk <= k_gcv; ++kk) {
+        const double* q = Q.p + (size_t)(kk - 1) * ldq;
+        double* qn = Q.p + (size_t)kk * ldq;
+        double* Hcol = dH.p + (size_t)(kk - 1) * ldh;
+        hg_spmv_epilogue ep;
+        HG_TRY(hg_k_spmv(ctx, B_p, q, z.p, ep, nullptr));                     // partial B^p q_p
+        HG_NCCL(g_nccl.AllReduce(z.p, z.p, (size_t)n, ncclDouble, ncclSum, comm->comm, st));
+        HG_TRY(hg_k_spmv(ctx, A_p, z.p, w0.p, ep, nullptr));                  // v = A*(B*q)     (:20)
+        int ns = 0;
+        HG_TRY(hg_k_multidot(ctx, Q.p, ldq, m_p, kk, w0.p, partials.p, &ns));
+        HG_TRY(hg_k_reduce(ctx, partials.p, ns, kk, hcur.p, false, nullptr, false));
+        HG_NCCL(g_nccl.AllReduce(hcur.p, hcur.p, (size_t)kk, ncclDouble, ncclSum, comm->comm, st));
+        HG_CUDA(cudaMemcpyAsync(Hcol, hcur.p, (size_t)kk * 8, cudaMemcpyDeviceToDevice, st));
+        HG_TRY(hg_k_lincomb(ctx, Q.p, ldq, m_p, kk, hcur.p, -1.0, w0.p, w1.p, nullptr, nullptr, nullptr));
+        HG_TRY(hg_k_multidot(ctx, Q.p, ldq, m_p, kk, w1.p, partials.p, &ns));
+        HG_TRY(hg_k_reduce(ctx, partials.p, ns, kk, hcur.p, false, nullptr, false));
+        HG_NCCL(g_nccl.AllReduce(hcur.p, hcur.p, (size_t)kk, ncclDouble, ncclSum, comm->comm, st));
+        HG_TRY(hg_k_axpby(ctx, kk, 1.0, Hcol, 1.0, hcur.p, Hcol, nullptr, nullptr, nullptr));
+        HG_TRY(hg_k_lincomb(ctx, Q.p, ldq, m_p, kk, hcur.p, -1.0, w1.p, qn, nullptr, stat.p, &np));
+        HG_TRY(hg_k_reduce(ctx, stat.p, np, 1, ds.p, false, nullptr, false));
+        HG_NCCL(g_nccl.AllReduce(ds.p, ds.p, 1, ncclDouble, ncclSum, comm->comm, st));
+        HG_TRY(hg_k_reduce(ctx, ds.p, 1, 1, Hcol + kk, false, nullptr, true));     // H(k+1,k)    (:29)
+        HG_TRY(hg_k_scale_div(ctx, qn, m_p, Hcol + kk));
+        HG_CUDA(cudaMemcpyAsync(hH.p + (size_t)(kk - 1) * ldh, Hcol, (size_t)(kk + 1) * 8,
+                                cudaMemcpyDeviceToHost, st));
+        HG_CUDA(cudaStreamSynchronize(st));
+        if (hH.p[(size_t)(kk - 1) * ldh + kk] < 1e-12) break;                 // :30 (same on all ranks)
+    }
+    HG_CUDA(cudaStreamSynchronize(st));
+    H.assign(hH.p, hH.p + (size_t)ldh * k_gcv);
+    *beta_out = hH.p[(size_t)ldh * k_gcv];
+    return HG_OK;
+}
+
+extern "C" int hg_dist_gcv_prepare(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_p, const hg_matrix* B_p,
+                                   const double* b_p, int64_t m, int k_gcv, int gcv_type, hg_gcv** out) {
+    HG_REQUIRE(ctx && comm && A_p && B_p && out, "hg_dist_gcv_prepare: NULL argument");
+    HG_REQUIRE(gcv_type == 0 || gcv_type == 1, "hg_dist_gcv_prepare: gcv_type must be 0 ('ab') or 1 ('ba')");
+    HG_REQUIRE(k_gcv >= 1, "hg_dist_gcv_prepare: k_gcv must be >= 1");
+    HG_CUDA(cudaSetDevice(ctx->device));
+    *out = nullptr;
+    std::vector<double> H;
+    double beta = 0.0;
+    if (gcv_type == 0) {
+        HG_TRY(dist_gcv_ab(ctx, comm, A_p, B_p, b_p, k_gcv, H, &beta));
+    } else {
+        DHolder holder;
+        HG_TRY(hg_darnoldi_create(ctx, comm, A_p, B_p, k_gcv, &holder.a));
+        hg_darnoldi* a = holder.a;
+        HG_TRY(hg_darnoldi_set_rhs(a, b_p));
+        HG_TRY(hg_darnoldi_reset(a, 0.0));
+        for (int k = 1; k <= k_gcv; ++k) {
+            HG_TRY(hg_darnoldi_steps(a, 1));
+            HG_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (a->h_H[(size_t)(k - 1) * a->ldh() + k] < 1e-12) break;
+        }
+        H.assign(a->h_H, a->h_H + (size_t)(k_gcv + 1) * k_gcv);
+        beta = a->h_beta[0];
+    }
+    const double trace_m = gcv_type == 0 ? (double)m : (double)A_p->cols;  // gcv_function.m:46-50
+    return hg_gcv_from_H(H.data(), k_gcv + 1, k_gcv, beta, trace_m, out);
+}

@@ -122,3 +122,16 @@ def hybrid_ab_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lam, *, extras=
 def hybrid_ba_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lam, *, extras=None):
     """Sharded ``hybrid_ba_gmres_rtp.m``."""
     return _dist_rtp(1, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras)
+
+
+def gcv_prepare(comm, A_p, B_p, b_p, m, k_gcv, gcv_type):
+    """Sharded ``gcv_function`` Arnoldi (``hg_dist_gcv_prepare``): returns a
+    :class:`hybrid_gmres_b200.GcvProblem` whose ``eval`` / ``fminbnd`` run on the host of
+    every rank with identical results."""
+    from .api import GcvProblem
+    ctx = comm.ctx
+    b_p = _vec(b_p, A_p.shape[0], "b_p")
+    h = C.c_void_p()
+    check(ctx._lib.hg_dist_gcv_prepare(ctx._h, comm._h, A_p._h, B_p._h, _ptr(b_p), int(m), int(k_gcv),
+                                       {"ab": 0, "ba": 1}[gcv_type], C.byref(h)))
+    return GcvProblem(h, ctx._lib)

@@ -268,6 +268,11 @@ int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_
                        const double* b_p, const double* x_true, double tol, int maxit, double lambda,
                        double* x, double* error_norm, double* residual_norm, int* niters, int* x_valid,
                        hg_extras* extras);
+/* Sharded gcv_function Arnoldi: 'ab' runs in m-space on the detector-row blocks (all-reduce of
+ * the n-vector B*q), 'ba' in n-space; the returned handle is evaluated with hg_gcv_eval /
+ * hg_gcv_fminbnd on every rank (identical H on all ranks). b_p: this rank's m_p entries. */
+int hg_dist_gcv_prepare(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_p, const hg_matrix* B_p,
+                        const double* b_p, int64_t m, int k_gcv, int gcv_type, hg_gcv** out);
 
 #ifdef __cplusplus
 }

@@ -60,6 +60,20 @@ ip, ix, dv = gB.download()
 Bs = B_p.copy()
 Bs.sort_indices()
 assert np.array_equal(ip, Bs.indptr) and np.array_equal(ix, Bs.indices) and np.allclose(dv, Bs.data, rtol=1e-12, atol=1e-12)
+# sharded gcv_function (m-space 'ab' and n-space 'ba') vs the oracle
+from oracle.solvers import gcv_arnoldi  # noqa: E402
+from hybrid_gmres_b200 import distributed as hgd0  # noqa: E402
+for t in ("ab", "ba"):
+    prob = hgd0.gcv_prepare(comm, dA, dB, b[lo:hi], A.shape[0], 20, t)
+    Hg, bg = prob.get(20)
+    Hgo, bgo = gcv_arnoldi(A, B, b, A.shape[0], 20, t, orth="cgs2")
+    assert abs(bg - bgo) / bgo < 1e-13
+    wg = max(np.linalg.norm(Hg[:j + 2, j] - Hgo[:j + 2, j]) / np.linalg.norm(Hgo[:j + 2, j]) for j in range(20))
+    assert wg < 1e-9, (t, wg)
+    for l in (1e-6, 1e-3):
+        v, vo = prob.eval(l), oracle.gcv_function(l, A, B, b, A.shape[0], 20, t)
+        assert abs(v - vo) / vo < 1e-8, (t, l, v, vo)
+
 # sharded whole solvers vs the oracle
 from hybrid_gmres_b200 import distributed as hgd  # noqa: E402
 for f_dev, f_orc in ((hgd.hybrid_ba_gmres_rtp, oracle.hybrid_ba_gmres_rtp),
