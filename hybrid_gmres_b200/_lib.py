@@ -70,6 +70,8 @@ PROTOTYPES = {
     "hg_darnoldi_get": (_i, [_vp, _vp, _i, c_double_p, c_int_p]),
     "hg_darnoldi_get_q": (_i, [_vp, _i, _vp, c_int64_p, c_int64_p]),
     "hg_darnoldi_step_bytes": (_i, [_vp, _i, c_double_p]),
+    "hg_dist_gkb_solver": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _d, _vp, _vp, _vp, _vp, c_int_p,
+                                C.POINTER(HgExtras)]),
     "hg_dist_gcv_prepare": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, c_void_pp]),
     "hg_dist_hybrid_rtp": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _d, _vp, _vp, _vp, c_int_p, c_int_p,
                                 C.POINTER(HgExtras)]),

@@ -172,3 +172,10 @@ int hg_k_spmv_stream(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y
 
 // transposition (matrix.cu)
 int hg_transpose_device(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out);
+
+// collectives of the multi-GPU path (dist.cu); comm == nullptr means single GPU
+int hg_comm_rank(const hg_comm* c);
+int hg_comm_size(const hg_comm* c);
+int hg_comm_allreduce(hg_comm* c, double* buf, size_t count, cudaStream_t st);
+int hg_comm_reduce_scatter(hg_comm* c, const double* send, double* recv, size_t recvcount, cudaStream_t st);
+int hg_comm_allgather(hg_comm* c, const double* send, double* recv, size_t sendcount, cudaStream_t st);

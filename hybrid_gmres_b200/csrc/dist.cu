@@ -590,3 +590,19 @@ extern "C" int hg_dist_gcv_prepare(hg_ctx* ctx, hg_comm* comm, const hg_matrix* 
     const double trace_m = gcv_type == 0 ? (double)m : (double)A_p->cols;  // gcv_function.m:46-50
     return hg_gcv_from_H(H.data(), k_gcv + 1, k_gcv, beta, trace_m, out);
 }
+
+// ---- thin collective wrappers for the other translation units (gkb.cu) -------------------
+int hg_comm_rank(const hg_comm* c) { return c->rank; }
+int hg_comm_size(const hg_comm* c) { return c->nranks; }
+int hg_comm_allreduce(hg_comm* c, double* buf, size_t count, cudaStream_t st) {
+    HG_NCCL(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, st));
+    return HG_OK;
+}
+int hg_comm_reduce_scatter(hg_comm* c, const double* send, double* recv, size_t recvcount, cudaStream_t st) {
+    HG_NCCL(g_nccl.ReduceScatter(send, recv, recvcount, ncclDouble, ncclSum, c->comm, st));
+    return HG_OK;
+}
+int hg_comm_allgather(hg_comm* c, const double* send, double* recv, size_t sendcount, cudaStream_t st) {
+    HG_NCCL(g_nccl.AllGather(send, recv, sendcount, ncclDouble, c->comm, st));
+    return HG_OK;
+}

@@ -3,6 +3,13 @@
 // A' is an explicit CSR matrix (MATLAB's CSC of A already is CSR of A'), so the
 // transposed product is the same row-per-warp SpMV as the forward one — no
 // atomics.  Scalars (Givens / LSMR recurrences) stay on the host.
+//
+// One implementation serves one GPU and P GPUs (GKB row): with a
+// communicator, A is this rank's detector-row block A_p (m_p x n), A' its transpose
+// (n x m_p); m-vectors (u, b, r) are local blocks, n-vectors (v, w, x, h) are equal row
+// slices.  A_p*v needs the all-gathered v; A_p'*u_p is a partial n-vector that is
+// reduce-scattered; norms are all-reduced.  Without a communicator every collective
+// disappears and the epilogues stay fused in the SpMV exactly as before.
 #include <algorithm>
 
 #include "common.cuh"
@@ -15,12 +22,13 @@ struct DBuf {
     ~DBuf() {
         if (p) cudaFree(p);
     }
-    int alloc(size_t n) {
+    int alloc(size_t n, cudaStream_t st = nullptr, bool zero = false) {
         cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double));
         if (e != cudaSuccess) {
             hg_set_error("device allocation of %zu doubles failed: %s", n, cudaGetErrorString(e));
             return HG_ERR_NOMEM;
         }
+        if (zero) cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(double), st);
         return HG_OK;
     }
 };
@@ -30,21 +38,33 @@ struct MatHolder {
     ~MatHolder() { hg_matrix_destroy(m); }
 };
 
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
 // Shared plumbing for the four solvers.
 struct Gkb {
-    hg_ctx* ctx;
-    const hg_matrix* A;
-    const hg_matrix* At;
+    hg_ctx* ctx = nullptr;
+    hg_comm* comm = nullptr;  // nullptr: single GPU
+    const hg_matrix* A = nullptr;
+    const hg_matrix* At = nullptr;
     MatHolder own_at;
-    int64_t m, n;
-    DBuf b, xt, stat;
+    int64_t m = 0;      // local rows of A (m_p)
+    int64_t n = 0;      // global n
+    int64_t nl = 0;     // length of the n-vector slices held here (n, or n_p zero padded)
+    int64_t n_pad = 0;  // nl * P
+    int64_t row0 = 0;   // first global row of this rank's slice
+    int64_t nvalid = 0; // rows of the slice that exist (rest is padding)
+    DBuf b, xt, stat, vfull, part, tmp;
     double norm_b = 0, norm_xt = 0;
     bool have_xt = false;
-    double* hs;  // pinned scalars
-    double* ds;  // device scalars
+    double* hs = nullptr;  // pinned scalars
+    double* ds = nullptr;  // device scalars
+    cudaStream_t st = nullptr;
 
-    int init(hg_ctx* c, const hg_matrix* A_, const hg_matrix* At_, const double* hb, const double* hxt) {
+    int init(hg_ctx* c, hg_comm* cm, const hg_matrix* A_, const hg_matrix* At_, const double* hb,
+             const double* hxt) {
         ctx = c;
+        comm = cm;
+        st = ctx->stream;
         A = A_;
         m = A->rows;
         n = A->cols;
@@ -57,39 +77,105 @@ struct Gkb {
             HG_TRY(hg_transpose_device(ctx, A, &own_at.m));
             At = own_at.m;
         }
+        if (comm) {
+            const int P = hg_comm_size(comm);
+            nl = round_up((n + P - 1) / P, 32);
+            n_pad = nl * P;
+            row0 = (int64_t)hg_comm_rank(comm) * nl;
+            nvalid = std::max<int64_t>(0, std::min(n, row0 + nl) - row0);
+            HG_TRY(vfull.alloc((size_t)n_pad, st, true));
+            HG_TRY(part.alloc((size_t)n_pad, st, true));
+            HG_TRY(tmp.alloc((size_t)nl, st, true));
+        } else {
+            nl = n_pad = nvalid = n;
+            row0 = 0;
+        }
         HG_TRY(b.alloc((size_t)m));
-        HG_TRY(xt.alloc((size_t)n));
-        HG_TRY(stat.alloc((size_t)(m + n) / 4 + 4096));
-        HG_CUDA(cudaMemcpyAsync(b.p, hb, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
-        double t = 0;
-        HG_TRY(hg_norm2_sync(ctx, b.p, m, &t));
-        norm_b = std::sqrt(t);
+        HG_TRY(xt.alloc((size_t)nl, st, true));
+        HG_TRY(stat.alloc((size_t)(m + n_pad) / 4 + 4096));
+        if (m) HG_CUDA(cudaMemcpyAsync(b.p, hb, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+        int np = 0;
+        HG_TRY(hg_k_sumsq(ctx, b.p, m, stat.p, &np));
+        HG_TRY(norm_from_stat(np, 11, &norm_b));
         if (hxt) {
             have_xt = true;
-            HG_CUDA(cudaMemcpyAsync(xt.p, hxt, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-            HG_TRY(hg_norm2_sync(ctx, xt.p, n, &t));
-            norm_xt = std::sqrt(t);
+            if (nvalid) HG_CUDA(cudaMemcpyAsync(xt.p, hxt + row0, (size_t)nvalid * 8, cudaMemcpyHostToDevice, st));
+            HG_TRY(hg_k_sumsq(ctx, xt.p, nl, stat.p, &np));
+            HG_TRY(norm_from_stat(np, 12, &norm_xt));
         }
         return HG_OK;
     }
-    // sqrt(sum of np partials at stat.p) -> device slot + host value (synchronises)
+    // global sqrt(sum of np local partials at stat.p) -> device slot + host value (synchronises)
     int norm_from_stat(int np, int slot, double* host) {
-        HG_TRY(hg_k_reduce(ctx, stat.p, np, 1, ds + slot, false, nullptr, true));
-        HG_CUDA(cudaMemcpyAsync(hs + slot, ds + slot, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        HG_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (comm) {
+            HG_TRY(hg_k_reduce(ctx, stat.p, np, 1, ds + 32, false, nullptr, false));
+            HG_TRY(hg_comm_allreduce(comm, ds + 32, 1, st));
+            HG_TRY(hg_k_reduce(ctx, ds + 32, 1, 1, ds + slot, false, nullptr, true));
+        } else {
+            HG_TRY(hg_k_reduce(ctx, stat.p, np, 1, ds + slot, false, nullptr, true));
+        }
+        HG_CUDA(cudaMemcpyAsync(hs + slot, ds + slot, 8, cudaMemcpyDeviceToHost, st));
+        HG_CUDA(cudaStreamSynchronize(st));
         *host = hs[slot];
         return HG_OK;
     }
-    // ||b - A x|| / ||b||  (true residual, e.g. hybrid_lsqr_solver.m:43); optional r store
-    int residual(const double* x, double* r_out, double* rn) {
+    // out(m) = alpha*A*v + g1*z1, v an n-slice; optional stat partials at stat.p (+offset)
+    int apply_A(const double* v, double* out, double alpha, const double* z1, double g1, const double* ref,
+                bool want_stat, int stat_off, int* np) {
+        const double* vin = v;
+        if (comm) {
+            HG_TRY(hg_comm_allgather(comm, v, vfull.p, (size_t)nl, st));
+            vin = vfull.p;
+        }
         hg_spmv_epilogue ep;
-        ep.alpha = -1.0;
-        ep.z1 = b.p;
-        ep.g1 = 1.0;
-        ep.stat = stat.p;
+        ep.alpha = alpha;
+        ep.z1 = z1;
+        ep.g1 = g1;
+        ep.ref = ref;
+        ep.stat = want_stat ? stat.p + stat_off : nullptr;
+        return hg_k_spmv(ctx, A, vin, out, ep, np);
+    }
+    // out(n-slice) = A'*u + g1*z1 + g2*z2 (z1, z2 n-slices); stat partials of out^2 at stat.p
+    int apply_At(const double* u, double* out, const double* z1, double g1, const double* z2, double g2,
+                 bool want_stat, int* np) {
+        if (!comm) {
+            hg_spmv_epilogue ep;
+            ep.z1 = z1;
+            ep.g1 = g1;
+            ep.z2 = z2;
+            ep.g2 = g2;
+            ep.stat = want_stat ? stat.p : nullptr;
+            return hg_k_spmv(ctx, At, u, out, ep, np);
+        }
+        hg_spmv_epilogue ep;
+        HG_TRY(hg_k_spmv(ctx, At, u, part.p, ep, nullptr));  // rows >= n of `part` stay zero
+        double* rs = (z1 || z2 || out == nullptr) ? tmp.p : out;
+        HG_TRY(hg_comm_reduce_scatter(comm, part.p, rs, (size_t)nl, st));
+        if (z1 && z2) {
+            HG_TRY(hg_k_axpby(ctx, nl, 1.0, rs, g1, z1, rs, nullptr, nullptr, nullptr));
+            return hg_k_axpby(ctx, nl, 1.0, rs, g2, z2, out, nullptr, want_stat ? stat.p : nullptr, np);
+        }
+        if (z1) return hg_k_axpby(ctx, nl, 1.0, rs, g1, z1, out, nullptr, want_stat ? stat.p : nullptr, np);
+        if (want_stat) return hg_k_sumsq(ctx, rs, nl, stat.p, np);
+        if (np) *np = 0;
+        return HG_OK;
+    }
+    // ||b - A x|| (global); optional local residual block r_out
+    int residual(const double* x, double* r_out, double* rn) {
         int np = 0;
-        HG_TRY(hg_k_spmv(ctx, A, x, r_out, ep, &np));
+        HG_TRY(apply_A(x, r_out, -1.0, b.p, 1.0, nullptr, true, 0, &np));
         return norm_from_stat(np, 10, rn);
+    }
+    // full n-vector to the host (all ranks)
+    int fetch_x(const double* xs, double* host) {
+        if (comm) {
+            HG_TRY(hg_comm_allgather(comm, xs, vfull.p, (size_t)nl, st));
+            HG_CUDA(cudaMemcpyAsync(host, vfull.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        } else {
+            HG_CUDA(cudaMemcpyAsync(host, xs, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        }
+        HG_CUDA(cudaStreamSynchronize(st));
+        return HG_OK;
     }
 };
 
@@ -99,48 +185,37 @@ inline void swap_ptr(double*& a, double*& b) {
     b = t;
 }
 
-}  // namespace
-
 // ---------------------------------------------------------------------------
 // hybrid_lsqr_solver.m:1-52 — stacked operator [A; sqrt(lambda) I] never formed
 // ---------------------------------------------------------------------------
-extern "C" int hg_hybrid_lsqr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At,
-                                     const double* b, const double* x_true, double tol, int maxit,
-                                     double lambda, double* x, double* error_norm,
-                                     double* residual_norm, int* niters, hg_extras* extras) {
-    HG_REQUIRE(ctx && A && b && x_true && x && error_norm && residual_norm && niters,
+int hybrid_lsqr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* At, const double* b,
+                     const double* x_true, double tol, int maxit, double lambda, double* x,
+                     double* error_norm, double* residual_norm, int* niters, hg_extras* extras) {
+    HG_REQUIRE(ctx && A && x_true && x && error_norm && residual_norm && niters,
                "hg_hybrid_lsqr_solver: NULL argument");
     HG_REQUIRE(maxit >= 1, "hg_hybrid_lsqr_solver: maxit must be >= 1");
     HG_CUDA(cudaSetDevice(ctx->device));
     Gkb g;
-    HG_TRY(g.init(ctx, A, At, b, x_true));
-    const int64_t m = g.m, n = g.n;
+    HG_TRY(g.init(ctx, comm, A, At, b, x_true));
+    const int64_t m = g.m, nl = g.nl, n = g.n;
+    cudaStream_t st = ctx->stream;
     const double sl = std::sqrt(lambda);  // :5
     DBuf bu1, bu2, bt1, bt2, bv, bt3, bw, bx;
-    HG_TRY(bu1.alloc(m)); HG_TRY(bu2.alloc(n)); HG_TRY(bt1.alloc(m)); HG_TRY(bt2.alloc(n));
-    HG_TRY(bv.alloc(n)); HG_TRY(bt3.alloc(n)); HG_TRY(bw.alloc(n)); HG_TRY(bx.alloc(n));
+    HG_TRY(bu1.alloc(m)); HG_TRY(bu2.alloc(nl, st, true)); HG_TRY(bt1.alloc(m)); HG_TRY(bt2.alloc(nl, st, true));
+    HG_TRY(bv.alloc(nl, st, true)); HG_TRY(bt3.alloc(nl, st, true)); HG_TRY(bw.alloc(nl)); HG_TRY(bx.alloc(nl, st, true));
     double *u1 = bu1.p, *u2 = bu2.p, *t1 = bt1.p, *t2 = bt2.p, *v = bv.p, *t3 = bt3.p, *w = bw.p, *dx = bx.p;
-    cudaStream_t st = ctx->stream;
-    HG_CUDA(cudaMemsetAsync(dx, 0, (size_t)n * 8, st));
-    HG_CUDA(cudaMemsetAsync(u2, 0, (size_t)n * 8, st));
     // beta = norm(b_aug) ; u = b_aug/beta                       (:9-10)
     double beta_aug = 0, alpha_aug = 0;
     int np = 0;
     HG_TRY(hg_k_sumsq(ctx, g.b.p, m, g.stat.p, &np));
     HG_TRY(g.norm_from_stat(np, 5, &beta_aug));
-    HG_CUDA(cudaMemcpyAsync(u1, g.b.p, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));
+    if (m) HG_CUDA(cudaMemcpyAsync(u1, g.b.p, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));
     HG_TRY(hg_k_scale_div(ctx, u1, m, g.ds + 5));
     // v_hat = A_aug'*u ; alpha ; v                                (:11-13)
-    {
-        hg_spmv_epilogue ep;
-        ep.z1 = u2;
-        ep.g1 = sl;
-        ep.stat = g.stat.p;
-        HG_TRY(hg_k_spmv(ctx, g.At, u1, v, ep, &np));
-        HG_TRY(g.norm_from_stat(np, 6, &alpha_aug));
-        HG_TRY(hg_k_scale_div(ctx, v, n, g.ds + 6));
-    }
-    HG_CUDA(cudaMemcpyAsync(w, v, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));  // :14
+    HG_TRY(g.apply_At(u1, v, u2, sl, nullptr, 0.0, true, &np));
+    HG_TRY(g.norm_from_stat(np, 6, &alpha_aug));
+    HG_TRY(hg_k_scale_div(ctx, v, nl, g.ds + 6));
+    HG_CUDA(cudaMemcpyAsync(w, v, (size_t)nl * 8, cudaMemcpyDeviceToDevice, st));  // :14
     double phi_bar = beta_aug, rho_bar = alpha_aug;
     for (int i = 0; i < maxit; ++i) error_norm[i] = residual_norm[i] = 0.0;
     if (extras && extras->aux) {
@@ -151,31 +226,17 @@ extern "C" int hg_hybrid_lsqr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_m
     for (k = 1; k <= maxit; ++k) {
         // u_hat = A_aug*v - alpha*u                               (:22)
         int np1 = 0, np2 = 0;
-        {
-            hg_spmv_epilogue ep;
-            ep.z1 = u1;
-            ep.g1 = -alpha_aug;
-            ep.stat = g.stat.p;
-            HG_TRY(hg_k_spmv(ctx, A, v, t1, ep, &np1));
-        }
-        HG_TRY(hg_k_axpby(ctx, n, sl, v, -alpha_aug, u2, t2, nullptr, g.stat.p + np1, &np2));
+        HG_TRY(g.apply_A(v, t1, 1.0, u1, -alpha_aug, nullptr, true, 0, &np1));
+        HG_TRY(hg_k_axpby(ctx, nl, sl, v, -alpha_aug, u2, t2, nullptr, g.stat.p + np1, &np2));
         HG_TRY(g.norm_from_stat(np1 + np2, 5, &beta_aug));  // :23
         HG_TRY(hg_k_scale_div(ctx, t1, m, g.ds + 5));       // :24
-        HG_TRY(hg_k_scale_div(ctx, t2, n, g.ds + 5));
+        HG_TRY(hg_k_scale_div(ctx, t2, nl, g.ds + 5));
         swap_ptr(u1, t1);
         swap_ptr(u2, t2);
         // v_hat = A_aug'*u - beta*v                               (:26)
-        {
-            hg_spmv_epilogue ep;
-            ep.z1 = u2;
-            ep.g1 = sl;
-            ep.z2 = v;
-            ep.g2 = -beta_aug;
-            ep.stat = g.stat.p;
-            HG_TRY(hg_k_spmv(ctx, g.At, u1, t3, ep, &np));
-        }
-        HG_TRY(g.norm_from_stat(np, 6, &alpha_aug));  // :27
-        HG_TRY(hg_k_scale_div(ctx, t3, n, g.ds + 6));  // :28
+        HG_TRY(g.apply_At(u1, t3, u2, sl, v, -beta_aug, true, &np));
+        HG_TRY(g.norm_from_stat(np, 6, &alpha_aug));   // :27
+        HG_TRY(hg_k_scale_div(ctx, t3, nl, g.ds + 6));  // :28
         swap_ptr(v, t3);
         // Givens                                                 (:30-37)
         const double rho = std::sqrt(rho_bar * rho_bar + beta_aug * beta_aug);
@@ -186,7 +247,7 @@ extern "C" int hg_hybrid_lsqr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_m
         const double phi = c * phi_bar;
         phi_bar = s * phi_bar;
         // x, w updates + error                                   (:39-42)
-        HG_TRY(hg_k_lsqr_update(ctx, n, dx, w, v, phi / rho, theta / rho, g.xt.p, g.stat.p, &np));
+        HG_TRY(hg_k_lsqr_update(ctx, nl, dx, w, v, phi / rho, theta / rho, g.xt.p, g.stat.p, &np));
         double en = 0, rn = 0;
         HG_TRY(g.norm_from_stat(np, 7, &en));
         HG_TRY(g.residual(dx, nullptr, &rn));  // :43
@@ -196,53 +257,44 @@ extern "C" int hg_hybrid_lsqr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_m
             extras->aux[k] = alpha_aug;
             extras->aux[maxit + 1 + k] = beta_aug;
         }
-        if (extras && extras->X_hist)
-            HG_CUDA(cudaMemcpy(extras->X_hist + (size_t)(k - 1) * n, dx, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        if (extras && extras->X_hist) HG_TRY(g.fetch_x(dx, extras->X_hist + (size_t)(k - 1) * n));
         if (residual_norm[k - 1] < tol) break;  // :45 strict
     }
     if (k > maxit) k = maxit;
     *niters = k;
-    HG_CUDA(cudaMemcpyAsync(x, dx, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    HG_CUDA(cudaStreamSynchronize(st));
-    return HG_OK;
+    return g.fetch_x(dx, x);
 }
 
 // ---------------------------------------------------------------------------
 // hybrid_lsmr_solver.m:1-57
 // ---------------------------------------------------------------------------
-extern "C" int hg_hybrid_lsmr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At,
-                                     const double* b, const double* x_true, double tol, int maxit,
-                                     double lambda, double* x, double* error_norm,
-                                     double* residual_norm, int* niters, hg_extras* extras) {
-    HG_REQUIRE(ctx && A && b && x_true && x && error_norm && residual_norm && niters,
+int hybrid_lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* At, const double* b,
+                     const double* x_true, double tol, int maxit, double lambda, double* x,
+                     double* error_norm, double* residual_norm, int* niters, hg_extras* extras) {
+    HG_REQUIRE(ctx && A && x_true && x && error_norm && residual_norm && niters,
                "hg_hybrid_lsmr_solver: NULL argument");
     HG_REQUIRE(maxit >= 1, "hg_hybrid_lsmr_solver: maxit must be >= 1");
     HG_CUDA(cudaSetDevice(ctx->device));
     Gkb g;
-    HG_TRY(g.init(ctx, A, At, b, x_true));
-    const int64_t m = g.m, n = g.n;
-    const int64_t ldv = (n + 31) / 32 * 32;
-    DBuf bu, bt, bV, bx, by;
-    HG_TRY(bu.alloc(m)); HG_TRY(bt.alloc(m)); HG_TRY(bV.alloc((size_t)ldv * maxit));
-    HG_TRY(bx.alloc(n)); HG_TRY(by.alloc(maxit));
-    double *u = bu.p, *t = bt.p, *V = bV.p, *dx = bx.p;
+    HG_TRY(g.init(ctx, comm, A, At, b, x_true));
+    const int64_t m = g.m, nl = g.nl, n = g.n;
     cudaStream_t st = ctx->stream;
-    HG_CUDA(cudaMemsetAsync(dx, 0, (size_t)n * 8, st));
+    const int64_t ldv = round_up(std::max<int64_t>(nl, 1), 32);
+    DBuf bu, bt, bV, bx, by;
+    HG_TRY(bu.alloc(m)); HG_TRY(bt.alloc(m)); HG_TRY(bV.alloc((size_t)ldv * maxit, st, true));
+    HG_TRY(bx.alloc(nl, st, true)); HG_TRY(by.alloc(maxit));
+    double *u = bu.p, *t = bt.p, *V = bV.p, *dx = bx.p;
     std::vector<double> Bk((size_t)(maxit + 1) * maxit, 0.0);  // (maxit+1) x maxit col-major
     const int ldb = maxit + 1;
     double beta1 = 0, alpha1 = 0;
     int np = 0;
     HG_TRY(hg_k_sumsq(ctx, g.b.p, m, g.stat.p, &np));
     HG_TRY(g.norm_from_stat(np, 5, &beta1));  // :7
-    HG_CUDA(cudaMemcpyAsync(u, g.b.p, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));
+    if (m) HG_CUDA(cudaMemcpyAsync(u, g.b.p, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));
     HG_TRY(hg_k_scale_div(ctx, u, m, g.ds + 5));  // :8
-    {
-        hg_spmv_epilogue ep;
-        ep.stat = g.stat.p;
-        HG_TRY(hg_k_spmv(ctx, g.At, u, V, ep, &np));  // :13
-        HG_TRY(g.norm_from_stat(np, 6, &alpha1));
-        HG_TRY(hg_k_scale_div(ctx, V, n, g.ds + 6));  // :15-16
-    }
+    HG_TRY(g.apply_At(u, V, nullptr, 0.0, nullptr, 0.0, true, &np));  // :13
+    HG_TRY(g.norm_from_stat(np, 6, &alpha1));
+    HG_TRY(hg_k_scale_div(ctx, V, nl, g.ds + 6));  // :15-16
     for (int i = 0; i < maxit; ++i) error_norm[i] = residual_norm[i] = 0.0;
     std::vector<double> T, LHS, RHS, y;
     int k;
@@ -250,27 +302,17 @@ extern "C" int hg_hybrid_lsmr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_m
         double* v = V + (size_t)(k - 1) * ldv;
         Bk[(size_t)(k - 1) * ldb + (k - 1)] = alpha1;  // :23
         double beta_k = 0;
-        {
-            hg_spmv_epilogue ep;
-            ep.z1 = u;
-            ep.g1 = -alpha1;
-            ep.stat = g.stat.p;
-            HG_TRY(hg_k_spmv(ctx, A, v, t, ep, &np));  // :24
-            HG_TRY(g.norm_from_stat(np, 5, &beta_k));
-            HG_TRY(hg_k_scale_div(ctx, t, m, g.ds + 5));  // :26
-            swap_ptr(u, t);
-        }
+        HG_TRY(g.apply_A(v, t, 1.0, u, -alpha1, nullptr, true, 0, &np));  // :24
+        HG_TRY(g.norm_from_stat(np, 5, &beta_k));
+        HG_TRY(hg_k_scale_div(ctx, t, m, g.ds + 5));  // :26
+        swap_ptr(u, t);
         Bk[(size_t)(k - 1) * ldb + k] = beta_k;  // :27
         if (k < maxit) {                          // :29-35
             double* vn = V + (size_t)k * ldv;
-            hg_spmv_epilogue ep;
-            ep.z1 = v;
-            ep.g1 = -beta_k;
-            ep.stat = g.stat.p;
-            HG_TRY(hg_k_spmv(ctx, g.At, u, vn, ep, &np));
+            HG_TRY(g.apply_At(u, vn, v, -beta_k, nullptr, 0.0, true, &np));
             double a_next = 0;
             HG_TRY(g.norm_from_stat(np, 6, &a_next));
-            HG_TRY(hg_k_scale_div(ctx, vn, n, g.ds + 6));
+            HG_TRY(hg_k_scale_div(ctx, vn, nl, g.ds + 6));
             alpha1 = a_next;
         }
         // projected problem on the host                           (:37-44)
@@ -298,14 +340,13 @@ extern "C" int hg_hybrid_lsmr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_m
         HG_CUDA(cudaMemcpyAsync(by.p, y.data(), (size_t)k * 8, cudaMemcpyHostToDevice, st));
         HG_CUDA(cudaStreamSynchronize(st));  // y is pageable host memory
         // x = V(:,1:k)*yk + error                                 (:45,47)
-        HG_TRY(hg_k_lincomb(ctx, V, ldv, n, k, by.p, 1.0, nullptr, dx, g.xt.p, g.stat.p, &np));
+        HG_TRY(hg_k_lincomb(ctx, V, ldv, nl, k, by.p, 1.0, nullptr, dx, g.xt.p, g.stat.p, &np));
         double en = 0, rn = 0;
         HG_TRY(g.norm_from_stat(np, 7, &en));
         HG_TRY(g.residual(dx, nullptr, &rn));  // :48
         error_norm[k - 1] = en / g.norm_xt;
         residual_norm[k - 1] = rn / g.norm_b;
-        if (extras && extras->X_hist)
-            HG_CUDA(cudaMemcpy(extras->X_hist + (size_t)(k - 1) * n, dx, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        if (extras && extras->X_hist) HG_TRY(g.fetch_x(dx, extras->X_hist + (size_t)(k - 1) * n));
         if (residual_norm[k - 1] <= tol) break;  // :50
     }
     if (k > maxit) k = maxit;
@@ -315,69 +356,48 @@ extern "C" int hg_hybrid_lsmr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_m
             extras->aux[j] = Bk[(size_t)j * ldb + j];
             extras->aux[maxit + 1 + j] = Bk[(size_t)j * ldb + j + 1];
         }
-    HG_CUDA(cudaMemcpyAsync(x, dx, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    HG_CUDA(cudaStreamSynchronize(st));
-    return HG_OK;
+    return g.fetch_x(dx, x);
 }
 
 // ---------------------------------------------------------------------------
 // lsqr_solver.m:1-54
 // ---------------------------------------------------------------------------
-extern "C" int hg_lsqr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At, const double* b,
-                              const double* x_true, double tol, int maxit, double* x,
-                              double* error_norm, double* residual_norm, int* niters,
-                              hg_extras* extras) {
-    HG_REQUIRE(ctx && A && b && x_true && x && error_norm && residual_norm && niters,
-               "hg_lsqr_solver: NULL argument");
+int lsqr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* At, const double* b,
+              const double* x_true, double tol, int maxit, double* x, double* error_norm,
+              double* residual_norm, int* niters, hg_extras* extras) {
+    HG_REQUIRE(ctx && A && x_true && x && error_norm && residual_norm && niters, "hg_lsqr_solver: NULL argument");
     HG_REQUIRE(maxit >= 1, "hg_lsqr_solver: maxit must be >= 1");
     HG_CUDA(cudaSetDevice(ctx->device));
     Gkb g;
-    HG_TRY(g.init(ctx, A, At, b, x_true));
-    const int64_t m = g.m, n = g.n;
-    DBuf bu, bt, bv, bt3, bw, bx;
-    HG_TRY(bu.alloc(m)); HG_TRY(bt.alloc(m)); HG_TRY(bv.alloc(n)); HG_TRY(bt3.alloc(n));
-    HG_TRY(bw.alloc(n)); HG_TRY(bx.alloc(n));
-    double *u = bu.p, *t = bt.p, *v = bv.p, *t3 = bt3.p, *w = bw.p, *dx = bx.p;
+    HG_TRY(g.init(ctx, comm, A, At, b, x_true));
+    const int64_t m = g.m, nl = g.nl, n = g.n;
     cudaStream_t st = ctx->stream;
-    HG_CUDA(cudaMemsetAsync(dx, 0, (size_t)n * 8, st));
+    DBuf bu, bt, bv, bt3, bw, bx;
+    HG_TRY(bu.alloc(m)); HG_TRY(bt.alloc(m)); HG_TRY(bv.alloc(nl, st, true)); HG_TRY(bt3.alloc(nl, st, true));
+    HG_TRY(bw.alloc(nl)); HG_TRY(bx.alloc(nl, st, true));
+    double *u = bu.p, *t = bt.p, *v = bv.p, *t3 = bt3.p, *w = bw.p, *dx = bx.p;
     double beta = 0, alpha = 0;
     int np = 0;
     HG_TRY(hg_k_sumsq(ctx, g.b.p, m, g.stat.p, &np));
     HG_TRY(g.norm_from_stat(np, 5, &beta));  // :7
-    HG_CUDA(cudaMemcpyAsync(u, g.b.p, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));
+    if (m) HG_CUDA(cudaMemcpyAsync(u, g.b.p, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));
     HG_TRY(hg_k_scale_div(ctx, u, m, g.ds + 5));  // :8
-    {
-        hg_spmv_epilogue ep;
-        ep.stat = g.stat.p;
-        HG_TRY(hg_k_spmv(ctx, g.At, u, v, ep, &np));  // :10
-        HG_TRY(g.norm_from_stat(np, 6, &alpha));
-        HG_TRY(hg_k_scale_div(ctx, v, n, g.ds + 6));  // :12
-    }
-    HG_CUDA(cudaMemcpyAsync(w, v, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    HG_TRY(g.apply_At(u, v, nullptr, 0.0, nullptr, 0.0, true, &np));  // :10
+    HG_TRY(g.norm_from_stat(np, 6, &alpha));
+    HG_TRY(hg_k_scale_div(ctx, v, nl, g.ds + 6));  // :12
+    HG_CUDA(cudaMemcpyAsync(w, v, (size_t)nl * 8, cudaMemcpyDeviceToDevice, st));
     double phi_bar = beta, rho_bar = alpha;
     for (int i = 0; i < maxit; ++i) error_norm[i] = residual_norm[i] = 0.0;
     int k;
     for (k = 1; k <= maxit; ++k) {
-        {
-            hg_spmv_epilogue ep;
-            ep.z1 = u;
-            ep.g1 = -alpha;
-            ep.stat = g.stat.p;
-            HG_TRY(hg_k_spmv(ctx, A, v, t, ep, &np));  // :22
-            HG_TRY(g.norm_from_stat(np, 5, &beta));
-            HG_TRY(hg_k_scale_div(ctx, t, m, g.ds + 5));
-            swap_ptr(u, t);
-        }
-        {
-            hg_spmv_epilogue ep;
-            ep.z1 = v;
-            ep.g1 = -beta;
-            ep.stat = g.stat.p;
-            HG_TRY(hg_k_spmv(ctx, g.At, u, t3, ep, &np));  // :26
-            HG_TRY(g.norm_from_stat(np, 6, &alpha));
-            HG_TRY(hg_k_scale_div(ctx, t3, n, g.ds + 6));
-            swap_ptr(v, t3);
-        }
+        HG_TRY(g.apply_A(v, t, 1.0, u, -alpha, nullptr, true, 0, &np));  // :22
+        HG_TRY(g.norm_from_stat(np, 5, &beta));
+        HG_TRY(hg_k_scale_div(ctx, t, m, g.ds + 5));
+        swap_ptr(u, t);
+        HG_TRY(g.apply_At(u, t3, v, -beta, nullptr, 0.0, true, &np));  // :26
+        HG_TRY(g.norm_from_stat(np, 6, &alpha));
+        HG_TRY(hg_k_scale_div(ctx, t3, nl, g.ds + 6));
+        swap_ptr(v, t3);
         const double rho = std::sqrt(rho_bar * rho_bar + beta * beta);  // :31
         const double c = rho_bar / rho;
         const double s = beta / rho;
@@ -385,13 +405,12 @@ extern "C" int hg_lsqr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* 
         rho_bar = -c * alpha;
         const double phi = c * phi_bar;
         phi_bar = s * phi_bar;
-        HG_TRY(hg_k_lsqr_update(ctx, n, dx, w, v, phi / rho, theta / rho, g.xt.p, g.stat.p, &np));  // :40-41
+        HG_TRY(hg_k_lsqr_update(ctx, nl, dx, w, v, phi / rho, theta / rho, g.xt.p, g.stat.p, &np));  // :40-41
         double en = 0;
         HG_TRY(g.norm_from_stat(np, 7, &en));
-        error_norm[k - 1] = en / g.norm_xt;                  // :43
+        error_norm[k - 1] = en / g.norm_xt;                    // :43
         residual_norm[k - 1] = std::fabs(phi_bar) / g.norm_b;  // :44
-        if (extras && extras->X_hist)
-            HG_CUDA(cudaMemcpy(extras->X_hist + (size_t)(k - 1) * n, dx, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        if (extras && extras->X_hist) HG_TRY(g.fetch_x(dx, extras->X_hist + (size_t)(k - 1) * n));
         if (residual_norm[k - 1] <= tol) break;  // :46
     }
     if (k > maxit) k = maxit;
@@ -399,52 +418,42 @@ extern "C" int hg_lsqr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* 
     double rn = 0;
     HG_TRY(g.residual(dx, nullptr, &rn));
     residual_norm[k - 1] = rn / g.norm_b;  // :52
-    HG_CUDA(cudaMemcpyAsync(x, dx, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    HG_CUDA(cudaStreamSynchronize(st));
-    return HG_OK;
+    return g.fetch_x(dx, x);
 }
 
 // ---------------------------------------------------------------------------
 // lsmr_solver.m:1-83
 // ---------------------------------------------------------------------------
-extern "C" int hg_lsmr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At, const double* b,
-                              const double* x_true, double tol, int maxit, double* x,
-                              double* err_hist, double* res_hist, double* ar_hist, int* iters,
-                              hg_extras* extras) {
-    HG_REQUIRE(ctx && A && b && x && err_hist && res_hist && ar_hist && iters,
-               "hg_lsmr_solver: NULL argument");
+int lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* At, const double* b,
+              const double* x_true, double tol, int maxit, double* x, double* err_hist, double* res_hist,
+              double* ar_hist, int* iters, hg_extras* extras) {
+    HG_REQUIRE(ctx && A && x && err_hist && res_hist && ar_hist && iters, "hg_lsmr_solver: NULL argument");
     HG_REQUIRE(maxit >= 1, "hg_lsmr_solver: maxit must be >= 1");
     HG_CUDA(cudaSetDevice(ctx->device));
     const double eps = 2.220446049250313e-16;
     Gkb g;
-    HG_TRY(g.init(ctx, A, At, b, x_true));
-    const int64_t m = g.m, n = g.n;
-    DBuf bu, bt, bv, bt3, bh, bhb, bx, br, bar;
-    HG_TRY(bu.alloc(m)); HG_TRY(bt.alloc(m)); HG_TRY(bv.alloc(n)); HG_TRY(bt3.alloc(n));
-    HG_TRY(bh.alloc(n)); HG_TRY(bhb.alloc(n)); HG_TRY(bx.alloc(n)); HG_TRY(br.alloc(m));
-    double *u = bu.p, *t = bt.p, *v = bv.p, *t3 = bt3.p, *h = bh.p, *hbar = bhb.p, *dx = bx.p, *r = br.p;
+    HG_TRY(g.init(ctx, comm, A, At, b, x_true));
+    const int64_t m = g.m, nl = g.nl, n = g.n;
     cudaStream_t st = ctx->stream;
-    HG_CUDA(cudaMemsetAsync(dx, 0, (size_t)n * 8, st));
-    HG_CUDA(cudaMemsetAsync(hbar, 0, (size_t)n * 8, st));
+    DBuf bu, bt, bv, bt3, bh, bhb, bx, br;
+    HG_TRY(bu.alloc(m)); HG_TRY(bt.alloc(m)); HG_TRY(bv.alloc(nl, st, true)); HG_TRY(bt3.alloc(nl, st, true));
+    HG_TRY(bh.alloc(nl)); HG_TRY(bhb.alloc(nl, st, true)); HG_TRY(bx.alloc(nl, st, true)); HG_TRY(br.alloc(m));
+    double *u = bu.p, *t = bt.p, *v = bv.p, *t3 = bt3.p, *h = bh.p, *hbar = bhb.p, *dx = bx.p, *r = br.p;
     // norm(A,'fro'): recomputed every iteration by the reference (:71), constant here
-    double fro2 = 0;
-    HG_TRY(hg_norm2_sync(ctx, A->vals, A->nnz, &fro2));
-    const double normA = std::sqrt(fro2);
-    double beta = 0, alpha = 0;
     int np = 0;
-    HG_CUDA(cudaMemcpyAsync(u, g.b.p, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));
+    double normA = 0;
+    HG_TRY(hg_k_sumsq(ctx, A->vals, A->nnz, g.stat.p, &np));
+    HG_TRY(g.norm_from_stat(np, 9, &normA));
+    double beta = 0, alpha = 0;
+    if (m) HG_CUDA(cudaMemcpyAsync(u, g.b.p, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));
     HG_TRY(hg_k_sumsq(ctx, u, m, g.stat.p, &np));
-    HG_TRY(g.norm_from_stat(np, 5, &beta));                          // :11
-    if (beta > 0) HG_TRY(hg_k_scale_div(ctx, u, m, g.ds + 5));       // :12
-    {
-        hg_spmv_epilogue ep;
-        ep.stat = g.stat.p;
-        HG_TRY(hg_k_spmv(ctx, g.At, u, v, ep, &np));                 // :14
-        HG_TRY(g.norm_from_stat(np, 6, &alpha));
-        if (alpha > 0) HG_TRY(hg_k_scale_div(ctx, v, n, g.ds + 6));  // :16
-    }
+    HG_TRY(g.norm_from_stat(np, 5, &beta));                         // :11
+    if (beta > 0) HG_TRY(hg_k_scale_div(ctx, u, m, g.ds + 5));      // :12
+    HG_TRY(g.apply_At(u, v, nullptr, 0.0, nullptr, 0.0, true, &np));  // :14
+    HG_TRY(g.norm_from_stat(np, 6, &alpha));
+    if (alpha > 0) HG_TRY(hg_k_scale_div(ctx, v, nl, g.ds + 6));    // :16
     double zetabar = alpha * beta, alphabar = alpha, rho = 1, rhobar = 1, cbar = 1, sbar = 0;  // :19-23
-    HG_CUDA(cudaMemcpyAsync(h, v, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));              // :25
+    HG_CUDA(cudaMemcpyAsync(h, v, (size_t)nl * 8, cudaMemcpyDeviceToDevice, st));              // :25
     const double nan = std::nan("");
     for (int i = 0; i < maxit; ++i) {
         err_hist[i] = nan;
@@ -453,26 +462,14 @@ extern "C" int hg_lsmr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* 
     }
     int k;
     for (k = 1; k <= maxit; ++k) {
-        {
-            hg_spmv_epilogue ep;
-            ep.z1 = u;
-            ep.g1 = -alpha;
-            ep.stat = g.stat.p;
-            HG_TRY(hg_k_spmv(ctx, A, v, t, ep, &np));  // :34
-            HG_TRY(g.norm_from_stat(np, 5, &beta));
-            if (beta > 0) HG_TRY(hg_k_scale_div(ctx, t, m, g.ds + 5));  // :36
-            swap_ptr(u, t);
-        }
-        {
-            hg_spmv_epilogue ep;
-            ep.z1 = v;
-            ep.g1 = -beta;
-            ep.stat = g.stat.p;
-            HG_TRY(hg_k_spmv(ctx, g.At, u, t3, ep, &np));  // :38
-            HG_TRY(g.norm_from_stat(np, 6, &alpha));
-            if (alpha > 0) HG_TRY(hg_k_scale_div(ctx, t3, n, g.ds + 6));  // :40
-            swap_ptr(v, t3);
-        }
+        HG_TRY(g.apply_A(v, t, 1.0, u, -alpha, nullptr, true, 0, &np));  // :34
+        HG_TRY(g.norm_from_stat(np, 5, &beta));
+        if (beta > 0) HG_TRY(hg_k_scale_div(ctx, t, m, g.ds + 5));  // :36
+        swap_ptr(u, t);
+        HG_TRY(g.apply_At(u, t3, v, -beta, nullptr, 0.0, true, &np));  // :38
+        HG_TRY(g.norm_from_stat(np, 6, &alpha));
+        if (alpha > 0) HG_TRY(hg_k_scale_div(ctx, t3, nl, g.ds + 6));  // :40
+        swap_ptr(v, t3);
         const double alphahat = alphabar;  // :42-49
         const double rhoold = rho;
         rho = std::hypot(alphahat, beta);
@@ -488,27 +485,83 @@ extern "C" int hg_lsmr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* 
         const double zeta = cbar * zetabar;  // :58-59
         zetabar = -sbar * zetabar;
         const double c0 = (k == 1) ? 0.0 : (thetabar * rho) / (rhoold * rhobarold);  // :64
-        HG_TRY(hg_k_lsmr_update(ctx, n, dx, h, hbar, v, k == 1 ? 1 : 0, c0, zeta / (rho * rhobar),
+        HG_TRY(hg_k_lsmr_update(ctx, nl, dx, h, hbar, v, k == 1 ? 1 : 0, c0, zeta / (rho * rhobar),
                                 thetanew / rho, g.have_xt ? g.xt.p : nullptr, g.stat.p, &np));  // :61-67
         double en = 0, rn = 0, arn = 0;
         HG_TRY(g.norm_from_stat(np, 7, &en));
-        HG_TRY(g.residual(dx, r, &rn));  // :69
-        {
-            hg_spmv_epilogue ep;
-            ep.stat = g.stat.p;
-            HG_TRY(hg_k_spmv(ctx, g.At, r, nullptr, ep, &np));  // norm(A.'*r)  :71
-            HG_TRY(g.norm_from_stat(np, 8, &arn));
-        }
-        res_hist[k - 1] = rn / (g.norm_b + eps);                      // :70
-        ar_hist[k - 1] = arn / (normA * std::max(rn, eps));           // :71
-        if (g.have_xt) err_hist[k - 1] = en / g.norm_xt;              // :72-74
-        if (extras && extras->X_hist)
-            HG_CUDA(cudaMemcpy(extras->X_hist + (size_t)(k - 1) * n, dx, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        HG_TRY(g.residual(dx, r, &rn));                                    // :69
+        HG_TRY(g.apply_At(r, nullptr, nullptr, 0.0, nullptr, 0.0, true, &np));  // norm(A.'*r)  :71
+        HG_TRY(g.norm_from_stat(np, 8, &arn));
+        res_hist[k - 1] = rn / (g.norm_b + eps);              // :70
+        ar_hist[k - 1] = arn / (normA * std::max(rn, eps));   // :71
+        if (g.have_xt) err_hist[k - 1] = en / g.norm_xt;      // :72-74
+        if (extras && extras->X_hist) HG_TRY(g.fetch_x(dx, extras->X_hist + (size_t)(k - 1) * n));
         if (res_hist[k - 1] < tol) break;  // :76
     }
     if (k > maxit) k = maxit;
     *iters = k;
-    HG_CUDA(cudaMemcpyAsync(x, dx, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    HG_CUDA(cudaStreamSynchronize(st));
-    return HG_OK;
+    return g.fetch_x(dx, x);
+}
+
+}  // namespace
+
+extern "C" int hg_hybrid_lsqr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At, const double* b,
+                                     const double* x_true, double tol, int maxit, double lambda, double* x,
+                                     double* error_norm, double* residual_norm, int* niters,
+                                     hg_extras* extras) {
+    HG_REQUIRE(b, "hg_hybrid_lsqr_solver: NULL argument");
+    return hybrid_lsqr_impl(ctx, nullptr, A, At, b, x_true, tol, maxit, lambda, x, error_norm, residual_norm,
+                            niters, extras);
+}
+
+extern "C" int hg_hybrid_lsmr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At, const double* b,
+                                     const double* x_true, double tol, int maxit, double lambda, double* x,
+                                     double* error_norm, double* residual_norm, int* niters,
+                                     hg_extras* extras) {
+    HG_REQUIRE(b, "hg_hybrid_lsmr_solver: NULL argument");
+    return hybrid_lsmr_impl(ctx, nullptr, A, At, b, x_true, tol, maxit, lambda, x, error_norm, residual_norm,
+                            niters, extras);
+}
+
+extern "C" int hg_lsqr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At, const double* b,
+                              const double* x_true, double tol, int maxit, double* x, double* error_norm,
+                              double* residual_norm, int* niters, hg_extras* extras) {
+    HG_REQUIRE(b, "hg_lsqr_solver: NULL argument");
+    return lsqr_impl(ctx, nullptr, A, At, b, x_true, tol, maxit, x, error_norm, residual_norm, niters, extras);
+}
+
+extern "C" int hg_lsmr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At, const double* b,
+                              const double* x_true, double tol, int maxit, double* x, double* err_hist,
+                              double* res_hist, double* ar_hist, int* iters, hg_extras* extras) {
+    HG_REQUIRE(b, "hg_lsmr_solver: NULL argument");
+    return lsmr_impl(ctx, nullptr, A, At, b, x_true, tol, maxit, x, err_hist, res_hist, ar_hist, iters, extras);
+}
+
+// Sharded GKB solvers (GKB row).  which: 0 hybrid_lsqr, 1 hybrid_lsmr, 2 lsqr,
+// 3 lsmr.  A_p: this rank's row block of A; At_p: its transpose or NULL; b_p: its m_p entries
+// of b; x_true / x: full n-vectors (x_true may be NULL for lsmr); ar_hist only for lsmr.
+extern "C" int hg_dist_gkb_solver(int which, hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_p,
+                                  const hg_matrix* At_p, const double* b_p, const double* x_true, double tol,
+                                  int maxit, double lambda, double* x, double* error_norm,
+                                  double* residual_norm, double* ar_hist, int* niters, hg_extras* extras) {
+    HG_REQUIRE(comm, "hg_dist_gkb_solver: NULL communicator");
+    HG_REQUIRE(A_p && (b_p || A_p->rows == 0), "hg_dist_gkb_solver: NULL argument");
+    switch (which) {
+        case 0:
+            return hybrid_lsqr_impl(ctx, comm, A_p, At_p, b_p, x_true, tol, maxit, lambda, x, error_norm,
+                                    residual_norm, niters, extras);
+        case 1:
+            return hybrid_lsmr_impl(ctx, comm, A_p, At_p, b_p, x_true, tol, maxit, lambda, x, error_norm,
+                                    residual_norm, niters, extras);
+        case 2:
+            return lsqr_impl(ctx, comm, A_p, At_p, b_p, x_true, tol, maxit, x, error_norm, residual_norm, niters,
+                             extras);
+        case 3:
+            HG_REQUIRE(ar_hist, "hg_dist_gkb_solver: ar_hist is required for lsmr");
+            return lsmr_impl(ctx, comm, A_p, At_p, b_p, x_true, tol, maxit, x, error_norm, residual_norm, ar_hist,
+                             niters, extras);
+        default:
+            hg_set_error("hg_dist_gkb_solver: unknown solver %d", which);
+            return HG_ERR_INVALID;
+    }
 }

@@ -135,3 +135,42 @@ def gcv_prepare(comm, A_p, B_p, b_p, m, k_gcv, gcv_type):
     check(ctx._lib.hg_dist_gcv_prepare(ctx._h, comm._h, A_p._h, B_p._h, _ptr(b_p), int(m), int(k_gcv),
                                        {"ab": 0, "ba": 1}[gcv_type], C.byref(h)))
     return GcvProblem(h, ctx._lib)
+
+
+def _dist_gkb(which, comm, A_p, b_p, x_true, tol, maxit, lam, At_p):
+    ctx = comm.ctx
+    n = A_p.shape[1]
+    maxit = int(maxit)
+    b_p = _vec(b_p, A_p.shape[0], "b_p")
+    xt = _vec(x_true, n, "x_true") if x_true is not None and np.size(x_true) > 0 else None
+    x, err, res, ar = np.zeros(n), np.zeros(maxit), np.zeros(maxit), np.zeros(maxit)
+    niters = C.c_int()
+    check(ctx._lib.hg_dist_gkb_solver(which, ctx._h, comm._h, A_p._h, At_p._h if At_p is not None else None,
+                                      _ptr(b_p), _ptr(xt), float(tol), maxit, float(lam or 0.0), _ptr(x), _ptr(err),
+                                      _ptr(res), _ptr(ar), C.byref(niters), None))
+    k = niters.value
+    if which == 3:
+        return x, err[:k], res[:k], ar[:k], k
+    return x, err[:k], res[:k], k
+
+
+def hybrid_lsqr_solver(comm, A_p, b_p, x_true, tol, maxit, lam, *, At_p=None):
+    """Sharded ``hybrid_lsqr_solver.m`` (``A_p``: this rank's row block of ``A``)."""
+    return _dist_gkb(0, comm, A_p, b_p, x_true, tol, maxit, lam, At_p)
+
+
+def hybrid_lsmr_solver(comm, A_p, b_p, x_true, tol, maxit, lam, *, At_p=None):
+    """Sharded ``hybrid_lsmr_solver.m``."""
+    return _dist_gkb(1, comm, A_p, b_p, x_true, tol, maxit, lam, At_p)
+
+
+def lsqr_solver(comm, A_p, b_p, x_true, tol, maxit, *, At_p=None):
+    """Sharded ``lsqr_solver.m``."""
+    return _dist_gkb(2, comm, A_p, b_p, x_true, tol, maxit, None, At_p)
+
+
+def lsmr_solver(comm, A_p, b_p, x_true=None, tol=1e-6, maxit=None, *, At_p=None):
+    """Sharded ``lsmr_solver.m`` (five outputs)."""
+    if maxit is None:
+        maxit = min(A_p.shape[1], 10 ** 9)
+    return _dist_gkb(3, comm, A_p, b_p, x_true, tol, maxit, None, At_p)

@@ -273,6 +273,14 @@ int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_
  * hg_gcv_fminbnd on every rank (identical H on all ranks). b_p: this rank's m_p entries. */
 int hg_dist_gcv_prepare(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_p, const hg_matrix* B_p,
                         const double* b_p, int64_t m, int k_gcv, int gcv_type, hg_gcv** out);
+/* Sharded Golub-Kahan solvers.  which: 0 hybrid_lsqr_solver, 1 hybrid_lsmr_solver, 2 lsqr_solver,
+ * 3 lsmr_solver.  A_p: this rank's detector-row block of A (m_p x n); At_p: its transpose or NULL
+ * (built on the device); b_p: its m_p entries of b; x_true, x: full n-vectors (x_true may be NULL
+ * for lsmr_solver); lambda is ignored by 2 and 3; ar_hist is required by 3 only. */
+int hg_dist_gkb_solver(int which, hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_p, const hg_matrix* At_p,
+                       const double* b_p, const double* x_true, double tol, int maxit, double lambda,
+                       double* x, double* error_norm, double* residual_norm, double* ar_hist, int* niters,
+                       hg_extras* extras);
 
 #ifdef __cplusplus
 }

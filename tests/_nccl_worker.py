@@ -85,6 +85,19 @@ for f_dev, f_orc in ((hgd.hybrid_ba_gmres_rtp, oracle.hybrid_ba_gmres_rtp),
         assert np.max(np.abs(ress - reso) / reso) < 1e-8
         assert np.max(np.abs(errs - erro) / erro) < 1e-8
         assert np.linalg.norm(xs - xo) / np.linalg.norm(xo) < 1e-8
+# sharded Golub-Kahan solvers vs the oracle (first 8 iterations: see tests/test_gpu_solvers.py)
+for name in ("hybrid_lsqr_solver", "hybrid_lsmr_solver", "lsqr_solver", "lsmr_solver"):
+    f_dev, f_orc = getattr(hgd, name), getattr(oracle, name)
+    if name.startswith("hybrid"):
+        out_d = f_dev(comm, dA, b[lo:hi], x_true, 1e-6, 8, lam)
+        out_o = f_orc(A, b, x_true, 1e-6, 8, lam)
+    else:
+        out_d = f_dev(comm, dA, b[lo:hi], x_true, 1e-6, 8)
+        out_o = f_orc(A, b, x_true, 1e-6, 8)
+    assert out_d[-1] == out_o[-1], name
+    for hd, ho in zip(out_d[1:-1], out_o[1:-1]):
+        assert np.max(np.abs(hd - ho) / np.abs(ho)) < 1e-8, (name, np.max(np.abs(hd - ho) / np.abs(ho)))
+    assert np.linalg.norm(out_d[0] - out_o[0]) / np.linalg.norm(out_o[0]) < 1e-8, name
 print("NCCL_OK", rank, worst, flush=True)
 ar.close()
 comm.close()
