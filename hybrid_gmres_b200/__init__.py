@@ -10,6 +10,10 @@ from . import _lib
 _lib.load()  # fail loudly if the CUDA library has not been built
 
 from .api import (  # noqa: E402,F401
+    ABgmres_hybrid_bounds,
+    ABgmres_nonhybrid_bounds,
+    BAgmres_hybrid_bounds,
+    BAgmres_nonhybrid_bounds,
     Arnoldi,
     Context,
     DeviceMatrix,

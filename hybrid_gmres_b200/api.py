@@ -513,3 +513,48 @@ def fminbnd_gcv(A, B, b, m, k_gcv, gcv_type, lo=1e-9, hi=1e-1, tolx=1e-8, *, ctx
     lam, fval, cnt, _ = prob.fminbnd(lo, hi, tolx)
     prob.close()
     return lam, fval, cnt
+
+
+# ---------------------------------------------------------------------------
+# project-then-regularise solvers
+# ---------------------------------------------------------------------------
+def _ptr_solver(kind, hybrid, A, B, b, x_true, tol, maxit, lam, ctx, extras):
+    ctx = _ctx_of(ctx, A, B)
+    maxit = int(maxit)
+    with _Uploaded(ctx, A, B) as (dA, dB):
+        m, n = dA.shape
+        b = _vec(b, m, "b")
+        x_true = _vec(x_true, n, "x_true")
+        x, err, res = np.zeros(n), np.zeros(maxit), np.zeros(maxit)
+        niters, x_valid = C.c_int(), C.c_int()
+        ex, bufs = _extras(maxit, n, extras is not None)
+        check(ctx._lib.hg_gmres_ptr(ctx._h, kind, hybrid, dA._h, dB._h, _ptr(b), _ptr(x_true), float(tol), maxit,
+                                    float(lam), _ptr(x), _ptr(err), _ptr(res), C.byref(niters), C.byref(x_valid),
+                                    C.byref(ex) if ex else None))
+    k = niters.value
+    if extras is not None:
+        extras.update(H=bufs["H"], beta=float(bufs["beta"][0]), X=bufs["X"][:, :k])
+    return (x if x_valid.value else None), err[:k], res[:k], k
+
+
+def ABgmres_hybrid_bounds(A, B, b, x_true, tol, maxit, lam, DeltaM=None, *, ctx=None, extras=None):
+    """First four outputs ``(x, error_norm, residual_norm, niters)`` of
+    ``ABgmres_hybrid_bounds.m`` — the PTR hybrid AB-GMRES solve.  ``DeltaM`` only feeds the
+    filter-factor bounds (``phi``, ``dphi``), which are out of scope, and is ignored."""
+    return _ptr_solver(0, 1, A, B, b, x_true, tol, maxit, lam, ctx, extras)
+
+
+def BAgmres_hybrid_bounds(A, B, b, x_true, tol, maxit, lam, DeltaM=None, *, ctx=None, extras=None):
+    """First four outputs of ``BAgmres_hybrid_bounds.m`` (PTR hybrid BA-GMRES)."""
+    return _ptr_solver(1, 1, A, B, b, x_true, tol, maxit, lam, ctx, extras)
+
+
+def ABgmres_nonhybrid_bounds(A, B, b, x_true, tol, maxit, DeltaM=None, *, ctx=None, extras=None):
+    """First four outputs of ``ABgmres_nonhybrid_bounds.m`` (plain AB-GMRES)."""
+    return _ptr_solver(0, 0, A, B, b, x_true, tol, maxit, 0.0, ctx, extras)
+
+
+def BAgmres_nonhybrid_bounds(A, B, b, x_true, tol, maxit, DeltaM=None, *, ctx=None, extras=None):
+    """First four outputs of ``BAgmres_nonhybrid_bounds.m`` (plain BA-GMRES; the reference
+    applies the pre-multiplied ``B*A``, this applies ``B*(A*q)``)."""
+    return _ptr_solver(1, 0, A, B, b, x_true, tol, maxit, 0.0, ctx, extras)

@@ -593,3 +593,132 @@ extern "C" int hg_gcv_destroy(hg_gcv* g) {
     delete g;
     return HG_OK;
 }
+
+// ===========================================================================
+// Project-then-regularise (PTR) solvers — the solve path of ABgmres_hybrid_bounds.m:11-41,
+// BAgmres_hybrid_bounds.m:11-40 and their non-hybrid siblings.  These
+// are what every GCV-driven script calls after fminbnd (plot_error_vs_mismatch_norm.m:53-57,
+// analyze_regularization.m:106-107).  Unshifted Arnoldi in m-space (AB: x = B*z) or n-space
+// (BA); projected problem: Tikhonov on H (hybrid) or plain least squares.  The filter-factor
+// bound outputs (phi, dphi; dense eig of A*B / B*A) are out of scope.
+// ===========================================================================
+extern "C" int hg_gmres_ptr(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* A, const hg_matrix* B,
+                            const double* b, const double* x_true, double tol, int maxit, double lambda,
+                            double* x, double* error_norm, double* residual_norm, int* niters, int* x_valid,
+                            hg_extras* extras) {
+    HG_REQUIRE(ctx && A && B && b && x_true && x && error_norm && residual_norm && niters,
+               "hg_gmres_ptr: NULL argument");
+    HG_REQUIRE(kind == 0 || kind == 1, "hg_gmres_ptr: kind must be 0 (AB) or 1 (BA)");
+    HG_REQUIRE(maxit >= 1, "hg_gmres_ptr: maxit must be >= 1");
+    HG_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = A->cols, m = A->rows;
+    ArnoldiHolder holder;
+    HG_TRY(hg_arnoldi_create(ctx, A, B, kind == 0 ? HG_SPACE_M : HG_SPACE_N, maxit, &holder.a));
+    hg_arnoldi* a = holder.a;
+    DBuf d_x, d_xt, d_y, d_z, stat_e, stat_r;
+    PinBuf h_y, h_s;
+    HG_TRY(d_x.alloc((size_t)n));
+    HG_TRY(d_xt.alloc((size_t)n));
+    HG_TRY(d_y.alloc((size_t)maxit + 1));
+    HG_TRY(d_z.alloc((size_t)m));
+    HG_TRY(stat_e.alloc((size_t)std::max(n, m) / 8 + 1024));
+    HG_TRY(stat_r.alloc((size_t)std::max(n, m) / 8 + 1024));
+    HG_TRY(h_y.alloc((size_t)maxit + 1));
+    HG_TRY(h_s.alloc(8));
+    HG_CUDA(cudaMemsetAsync(d_x.p, 0, (size_t)n * 8, ctx->stream));
+    HG_CUDA(cudaMemcpyAsync(d_xt.p, x_true, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    HG_TRY(hg_arnoldi_set_rhs(a, b));
+    double nb2 = 0, nx2 = 0;
+    HG_TRY(hg_norm2_sync(ctx, a->d_b, m, &nb2));
+    HG_TRY(hg_norm2_sync(ctx, d_xt.p, n, &nx2));
+    const double norm_b = std::sqrt(nb2), norm_xt = std::sqrt(nx2);
+    HG_TRY(hg_arnoldi_reset(a, 0.0));  // r0 = b (AB, :11-12) or B*b (BA, :12-13); unshifted operator (:25)
+    HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double beta = a->h_beta[0];
+    for (int i = 0; i < maxit; ++i) error_norm[i] = residual_norm[i] = 0.0;
+    hgd::HessenbergLS ls;
+    hgd::BorderedCholesky chol;
+    std::vector<double> rhs(maxit, 0.0), grow(maxit + 1, 0.0);
+    bool chol_ok = true;
+    if (hybrid) chol.reset(maxit, lambda);
+    else ls.reset(maxit, beta);
+    bool have_x = false;
+    const int ldh = a->ldh();
+    int k;
+    for (k = 1; k <= maxit; ++k) {
+        HG_TRY(hg_arnoldi_steps(a, 1));
+        HG_CUDA(cudaStreamSynchronize(ctx->stream));
+        const double* H = a->h_H;
+        const double* hcol = H + (size_t)(k - 1) * ldh;
+        if (hcol[k] == 0.0) break;  // :31
+        if (hybrid) {
+            // yk = (Hk'*Hk + lambda*I) \ (Hk'*tk): Hk'*Hk grows by bordering (column k adds row k+1,
+            // which is zero in every earlier column), so the row Cholesky is continued    (:34-36)
+            for (int j = 0; j < k; ++j) {
+                double acc = 0.0;
+                const double* hj = H + (size_t)j * ldh;
+                for (int t = 0; t <= std::min(j, k - 1) + 1; ++t) acc += hj[t] * hcol[t];
+                grow[j] = acc;
+            }
+            rhs[k - 1] = beta * hcol[0];
+            if (chol_ok) chol_ok = chol.add_row(grow.data());
+            if (chol_ok) {
+                chol.solve(rhs.data(), h_y.p);
+            } else {
+                std::vector<double> M((size_t)k * k);
+                for (int j = 0; j < k; ++j)
+                    for (int i2 = 0; i2 < k; ++i2) {
+                        double acc = 0.0;
+                        for (int t = 0; t <= k; ++t) acc += H[(size_t)i2 * ldh + t] * H[(size_t)j * ldh + t];
+                        M[(size_t)j * k + i2] = acc + (i2 == j ? lambda : 0.0);
+                    }
+                hgd::solve_square(k, M.data(), k, rhs.data(), h_y.p);
+            }
+        } else {
+            ls.add_column(hcol);  // yk = Hk \ [beta;0]   (ABgmres_nonhybrid_bounds.m:34-35)
+            ls.solve(h_y.p);
+        }
+        HG_CUDA(cudaMemcpyAsync(d_y.p, h_y.p, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+        int np_e = 0, np_r = 0;
+        if (kind == 1) {
+            // xk = Q(:,1:k)*yk                                                    (BA :37)
+            HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n, k, d_y.p, 1.0, nullptr, d_x.p, d_xt.p, stat_e.p, &np_e));
+        } else {
+            // zk = Q(:,1:k)*yk ; xk = B*zk                                        (AB :37-38)
+            HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, m, k, d_y.p, 1.0, nullptr, d_z.p, nullptr, nullptr, nullptr));
+            hg_spmv_epilogue ep;
+            ep.ref = d_xt.p;
+            ep.stat = stat_e.p;
+            HG_TRY(hg_k_spmv(ctx, B, d_z.p, d_x.p, ep, &np_e));
+        }
+        {
+            hg_spmv_epilogue ep;  // norm(b - A*xk)                                (:40)
+            ep.alpha = -1.0;
+            ep.z1 = a->d_b;
+            ep.g1 = 1.0;
+            ep.stat = stat_r.p;
+            HG_TRY(hg_k_spmv(ctx, A, d_x.p, nullptr, ep, &np_r));
+        }
+        HG_TRY(hg_k_reduce(ctx, stat_e.p, np_e, 1, ctx->d_scalars + 1, false, nullptr, true));
+        HG_TRY(hg_k_reduce(ctx, stat_r.p, np_r, 1, ctx->d_scalars + 2, false, nullptr, true));
+        HG_CUDA(cudaMemcpyAsync(h_s.p, ctx->d_scalars + 1, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (extras && extras->X_hist)
+            HG_CUDA(cudaMemcpyAsync(extras->X_hist + (size_t)(k - 1) * n, d_x.p, (size_t)n * 8,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+        HG_CUDA(cudaStreamSynchronize(ctx->stream));
+        have_x = true;
+        error_norm[k - 1] = h_s.p[0] / norm_xt;     // :41
+        residual_norm[k - 1] = h_s.p[1] / norm_b;   // :40
+        if (residual_norm[k - 1] <= tol) break;     // :83
+    }
+    if (k > maxit) k = maxit;
+    *niters = k;
+    HG_CUDA(cudaMemcpyAsync(x, d_x.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (x_valid) *x_valid = have_x ? 1 : 0;  // `x = xk` (:86) is undefined after a breakdown at k = 1
+    if (extras) {
+        if (extras->beta) *extras->beta = beta;
+        if (extras->H) memcpy(extras->H, a->h_H, (size_t)ldh * maxit * 8);
+    }
+    return HG_OK;
+}

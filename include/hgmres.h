@@ -214,6 +214,16 @@ int hg_hybrid_ba_gmres_rtp(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, 
                            double* error_norm, double* residual_norm, int* niters, int* x_valid,
                            const hg_solver_opts* opts, hg_extras* extras);
 
+/* Project-then-regularise solvers — the solve path (first four outputs) of
+ *   kind 0, hybrid 1: ABgmres_hybrid_bounds.m:11-41      kind 1, hybrid 1: BAgmres_hybrid_bounds.m:11-40
+ *   kind 0, hybrid 0: ABgmres_nonhybrid_bounds.m:12-40   kind 1, hybrid 0: BAgmres_nonhybrid_bounds.m:12-39
+ * Unshifted Arnoldi in m-space (AB, x = B*z) or n-space (BA); y_k from Tikhonov on H_k (hybrid)
+ * or H_k \ beta*e1.  The filter-factor bound outputs (phi, dphi, DeltaM) are out of scope.
+ * x_valid is 0 when `x = xk` would be undefined in the reference (breakdown at k = 1). */
+int hg_gmres_ptr(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* A, const hg_matrix* B, const double* b,
+                 const double* x_true, double tol, int maxit, double lambda, double* x, double* error_norm,
+                 double* residual_norm, int* niters, int* x_valid, hg_extras* extras);
+
 /* gcv_function(lambda,A,B,b,m,k_gcv,gcv_type): the lambda-independent Arnoldi
  * (gcv_function.m:4-32) runs ONCE in hg_gcv_prepare; hg_gcv_eval is the
  * projected part (:33-58) on the host.  gcv_type: 0 'ab', 1 'ba'. */

@@ -33,3 +33,9 @@ from .solvers import (  # noqa: F401
     arnoldi,
 )
 from .fminbnd import fminbnd  # noqa: F401
+from .ptr import (  # noqa: F401,E402
+    ABgmres_hybrid_bounds,
+    ABgmres_nonhybrid_bounds,
+    BAgmres_hybrid_bounds,
+    BAgmres_nonhybrid_bounds,
+)

@@ -158,3 +158,29 @@ def test_ct_generator_properties():
     assert 1e-4 < rel < 0.1
     Bq = ct.backprojector_perturbed(A, 1e-2)
     assert abs(sp.linalg.norm(Bq - A.T) - 1e-2) < 1e-12
+
+
+def test_all_four_title_claims_with_the_ptr_solvers():
+    """run_equivalence_plots.m:33,44,55,66 and run_ptr_rtp_comparison.m:29 with the reference's
+    own solver pairs (SURVEY App. A magnitudes)."""
+    from oracle import ptr
+    A, B, b, x_true = _problem()
+
+    def X(f, *a):
+        e = {}
+        f(*a, extras=e)
+        return e["X"]
+
+    rel = lambda P, Q, k: np.linalg.norm(P[:, k] - Q[:, k]) / np.linalg.norm(Q[:, k])
+    ba, lsmr = X(ptr.BAgmres_nonhybrid_bounds, A, B, b, x_true, 0.0, 8), X(oracle.lsmr_solver, A, b, x_true, 0.0, 8)
+    ab, lsqr = X(ptr.ABgmres_nonhybrid_bounds, A, B, b, x_true, 0.0, 8), X(oracle.lsqr_solver, A, b, x_true, 0.0, 8)
+    assert rel(ba, lsmr, 0) < 1e-15 and rel(ba, lsmr, 2) < 1e-12 and rel(ba, lsmr, 4) < 1e-6
+    assert rel(ab, lsqr, 0) < 1e-15 and rel(ab, lsqr, 2) < 1e-12 and rel(ab, lsqr, 4) < 1e-6
+    hba = X(ptr.BAgmres_hybrid_bounds, A, B, b, x_true, 0.0, 8, 1e-3)
+    hlsmr = X(oracle.hybrid_lsmr_solver, A, b, x_true, 0.0, 8, 1e-3)
+    assert rel(hba, hlsmr, 0) < 1e-15 and max(rel(hba, hlsmr, k) for k in range(5)) < 1e-5  # GKB breaks down at k~6
+    hab = X(ptr.ABgmres_hybrid_bounds, A, B, b, x_true, 0.0, 8, 1e-3)
+    hlsqr = X(oracle.hybrid_lsqr_solver, A, b, x_true, 0.0, 8, 1e-3)
+    assert min(rel(hab, hlsqr, k) for k in range(8)) > 1e-2  # "(≠)"
+    rtp = X(oracle.hybrid_ba_gmres_rtp, A, B, b, x_true, 0.0, 8, 1e-3)
+    assert min(rel(hba, rtp, k) for k in range(8)) > 1e-2  # PTR ≠ RTP
