@@ -97,6 +97,7 @@ PROTOTYPES = {
     "hg_gcv_get": (_i, [_vp, _vp, c_double_p]),
     "hg_gcv_fminbnd": (_i, [_vp, _d, _d, _d, c_double_p, c_double_p, c_int_p, _vp, _i]),
     "hg_gcv_destroy": (_i, [_vp]),
+    "hg_gcv_surface": (_i, [_vp, _vp, _i, _vp, _vp]),
     "hg_gcv_from_H": (_i, [_vp, _i, _i, _d, _d, c_void_pp]),
     "hg_host_hessenberg_ls": (_i, [_vp, _i, _i, _d, _vp]),
     "hg_host_solve_square": (_i, [_i, _vp, _i, _vp, _vp]),

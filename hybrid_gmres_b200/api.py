@@ -449,6 +449,15 @@ class GcvProblem:
         check(self._lib.hg_gcv_get(self._h, _ptr(H), C.byref(beta)))
         return H, beta.value
 
+    def surface(self, lambdas, k: int):
+        """``compute_gcv_surface`` of ``plot_gcv_surface.m:58-102``: returns
+        ``(gcv_surface[len(lambdas), k], gcv_path[k])`` from the one Arnoldi run held here."""
+        lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+        surf = np.zeros((lambdas.shape[0], k), order="F")
+        path = np.zeros(k)
+        check(self._lib.hg_gcv_surface(self._h, _ptr(lambdas), lambdas.shape[0], _ptr(surf), _ptr(path)))
+        return surf, path
+
     def fminbnd(self, lo, hi, tolx=1e-4, trace_cap=600):
         """MATLAB ``fminbnd(@(l) gcv_function(l,...), lo, hi, optimset('TolX',tolx))``.
         Returns ``(lambda, fval, funccount, trace)``."""

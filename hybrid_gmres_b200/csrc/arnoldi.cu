@@ -722,3 +722,32 @@ extern "C" int hg_gmres_ptr(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* 
     }
     return HG_OK;
 }
+
+// plot_gcv_surface.m:58-102 (compute_gcv_surface) given the Arnoldi factorisation already held by
+// the handle: GCV over a (lambda, k) grid and the per-iteration grid minimiser lambda_k — the
+// "Arnoldi once, GCV for many (lambda,k)" form.  surface is nl x k
+// column-major (zero in the columns from a `H(k+1,k) < 1e-12` breakdown on, as the reference
+// leaves them, :85), path has k entries.
+extern "C" int hg_gcv_surface(const hg_gcv* g, const double* lambdas, int nl, double* surface, double* path) {
+    HG_REQUIRE(g && lambdas && surface && path && nl >= 1, "hg_gcv_surface: bad argument");
+    const int K = g->k, ldh = g->k + 1;
+    for (size_t i = 0; i < (size_t)nl * K; ++i) surface[i] = 0.0;
+    for (int k = 0; k < K; ++k) path[k] = 0.0;
+    std::vector<double> sq, sv;
+    for (int k = 1; k <= K; ++k) {
+        if (g->H[(size_t)(k - 1) * ldh + k] < 1e-12) break;  // :85
+        sq.assign((size_t)k * k, 0.0);
+        for (int j = 0; j < k; ++j)
+            for (int i = 0; i < k; ++i) sq[(size_t)j * k + i] = g->H[(size_t)j * ldh + i];
+        sv.assign(k, 0.0);
+        hgd::singular_values(k, sq.data(), k, sv.data());  // :111
+        int best = 0;
+        for (int i = 0; i < nl; ++i) {
+            const double v = hgd::gcv_value(lambdas[i], g->H.data(), ldh, k, g->beta, g->trace_m, sv.data());
+            surface[(size_t)(k - 1) * nl + i] = v;
+            if (v < surface[(size_t)(k - 1) * nl + best]) best = i;  // first minimum, as MATLAB's min (:99)
+        }
+        path[k - 1] = lambdas[best];
+    }
+    return HG_OK;
+}

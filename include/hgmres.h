@@ -236,6 +236,10 @@ int hg_gcv_get(const hg_gcv* g, double* H, double* beta);
 int hg_gcv_fminbnd(const hg_gcv* g, double lo, double hi, double tolx, double* lambda,
                    double* fval, int* funccount, double* trace, int trace_cap);
 int hg_gcv_destroy(hg_gcv* g);
+/* plot_gcv_surface.m:58-102 (compute_gcv_surface) from the factorisation held by the handle:
+ * surface (nl x k_gcv, column-major) = GCV(lambda_i, k) with H(1:k+1,1:k); path[k-1] = the grid
+ * minimiser lambda_k.  Columns from a `H(k+1,k) < 1e-12` breakdown on stay zero (:85). */
+int hg_gcv_surface(const hg_gcv* g, const double* lambdas, int nl, double* surface, double* path);
 /* Host-only constructor from an existing Arnoldi factorisation (no device work):
  * H is (k+1) x k column-major with leading dimension ldh, trace_m is m ('ab') or
  * n ('ba') (gcv_function.m:46-50).  This is plot_gcv_surface.m:58-122's "Arnoldi

@@ -176,3 +176,23 @@ def test_mex_gateway_parses_and_binds_the_abi():
                "hg_hybrid_lsqr_solver", "hg_hybrid_lsmr_solver", "hg_lsqr_solver", "hg_lsmr_solver",
                "hg_matrix_from_csc", "hg_matrix_from_dense"):
         assert fn in txt
+
+
+def test_gcv_surface_host_matches_oracle():
+    """hg_gcv_surface (host-side, from a given H) against plot_gcv_surface.m's compute_gcv_surface."""
+    import hybrid_gmres_b200 as hg
+    from oracle.gcv_surface import compute_gcv_surface
+    from oracle.generators import add_noise
+    from oracle.solvers import gcv_arnoldi
+    A, b_exact, x_true = oracle.generate_test_problem("shaw", 32)
+    rng = np.random.default_rng(0)
+    B = A.T + 1e-4 * rng.standard_normal(A.shape)  # plot_gcv_surface.m:14-15
+    b = add_noise(b_exact, 1e-2, 0)
+    lams = np.logspace(-8, -1, 25)
+    for t in ("ab", "ba"):
+        surf_o, path_o = compute_gcv_surface(t, A, B, b, 12, range(1, 13), lams)
+        H, beta = gcv_arnoldi(A, B, b, 32, 12, t)
+        surf, path = hg.GcvProblem.from_H(H, beta, 32).surface(lams, 12)
+        assert surf.shape == surf_o.shape
+        assert np.allclose(surf, surf_o, rtol=1e-6, atol=0)
+        assert np.array_equal(path, path_o)
