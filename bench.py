@@ -88,7 +88,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_workload(hg, ctx, name, rank=0, world=1, dist=None):
+def build_workload(hg, ctx, name, rank=0, world=1, dist=None, order="natural"):
     """Matrices are generated on the device.  world > 1: this rank's detector-row block A_p and
     the matching column block B^p; b is the matching slice."""
     w = WORKLOADS[name]
@@ -113,6 +113,14 @@ def build_workload(hg, ctx, name, rank=0, world=1, dist=None):
         dist.all_reduce(t)
         nb2 = float(t.item())
     b = b_exact + NOISE * math.sqrt(nb2) * e[lo:hi] / np.linalg.norm(e)  # run_2D_phantom.m:18-19
+    if order.startswith("tile"):
+        # n-space in tile x tile pixel blocks (hg_matrix_permute): A(:,q), B(q,:), x_true(q)
+        from hybrid_gmres_b200.ct import tile_permutation
+        q = tile_permutation(N, int(order[4:]))
+        dA2, dB2 = dA.permute(None, q), dB.permute(q, None)
+        dA.close()
+        dB.close()
+        dA, dB, x_true = dA2, dB2, np.ascontiguousarray(x_true[q])
     return dA, dB, b, x_true, w["maxit"]
 
 
@@ -150,6 +158,8 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=20, help="iterations of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nspace-order", default="tile4", choices=["natural", "tile4", "tile8"],
+                    help="pixel order of the n-space on the device (hg_matrix_permute)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -174,7 +184,7 @@ def main():
     if args.impl == "reference":
         dA, dB, b, x_true, maxit = build_workload(hg, ctx, args.workload)
     else:
-        dA, dB, b, x_true, maxit = build_workload(hg, ctx, args.workload, rank, world, dist)
+        dA, dB, b, x_true, maxit = build_workload(hg, ctx, args.workload, rank, world, dist, args.nspace_order)
     m, n = dA.shape
     nnzA, nnzB = dA.nnz, dB.nnz
     if dist is not None:
@@ -184,6 +194,7 @@ def main():
     cores = len(os.sched_getaffinity(0))
     config = {"workload": args.workload, "m": m, "n": n, "nnz_A": nnzA, "nnz_B": nnzB, "maxit": maxit,
               "lambda": LAMBDA, "orth": "cgs2", "B": "pixel-driven (unmatched)",
+              "nspace_order": args.nspace_order, "spmv_form": {"A": dA.spmv_form, "B": dB.spmv_form},
               "parallelism": (f"A row-sharded / B column-sharded x{world}, NCCL reduce-scatter + all-gather + "
                               "3 all-reduce per step") if world > 1 else "single",
               "l2": "inputs (A+B = %.1f GB) exceed the 126 MB L2; no flush needed" % ((nnzA + nnzB) * 12 / 1e9)}

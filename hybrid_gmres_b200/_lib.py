@@ -52,6 +52,8 @@ PROTOTYPES = {
     "hg_matrix_from_csc": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _vp, c_void_pp]),
     "hg_matrix_from_dense": (_i, [_vp, _i64, _i64, _vp, _i64, c_void_pp]),
     "hg_matrix_transpose": (_i, [_vp, _vp, c_void_pp]),
+    "hg_matrix_permute": (_i, [_vp, _vp, _vp, _vp, c_void_pp]),
+    "hg_matrix_spmv_form": (_i, [_vp, _vp, c_int_p]),
     "hg_matrix_info": (_i, [_vp, c_int64_p, c_int64_p, c_int64_p]),
     "hg_matrix_download_csr": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "hg_matrix_destroy": (_i, [_vp]),

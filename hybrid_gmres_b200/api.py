@@ -18,6 +18,8 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
+import time
 import weakref
 
 import numpy as np
@@ -31,6 +33,8 @@ __all__ = [
     "lsqr_solver", "lsmr_solver", "gcv_function", "gcv_prepare", "fminbnd_gcv",
     "KERNEL_CLASSES", "set_option",
 ]
+
+_TRACE = os.environ.get("HG_TRACE") is not None
 
 KERNEL_CLASSES = {"spmv": 0, "multidot": 1, "lincomb": 2, "vector": 3, "reduce": 4, "setup": 5}
 
@@ -187,6 +191,25 @@ class DeviceMatrix:
         check(self.ctx._lib.hg_matrix_transpose(self.ctx._h, self._h, C.byref(h)))
         return DeviceMatrix(h, self.ctx)
 
+    def permute(self, rowperm=None, colperm=None) -> "DeviceMatrix":
+        """``M(rowperm, colperm)`` (gather convention, 0-based) as a new device matrix."""
+        rp = None if rowperm is None else np.ascontiguousarray(rowperm, dtype=np.int32)
+        cp = None if colperm is None else np.ascontiguousarray(colperm, dtype=np.int32)
+        if rp is not None and rp.shape[0] != self.shape[0]:
+            raise ValueError("permute: rowperm has the wrong length")
+        if cp is not None and cp.shape[0] != self.shape[1]:
+            raise ValueError("permute: colperm has the wrong length")
+        h = C.c_void_p()
+        check(self.ctx._lib.hg_matrix_permute(self.ctx._h, self._h, _ptr(rp), _ptr(cp), C.byref(h)))
+        return DeviceMatrix(h, self.ctx)
+
+    @property
+    def spmv_form(self) -> str:
+        """Which SpMV kernel this matrix runs with ("csr", "sell32" or "stream")."""
+        f = C.c_int()
+        check(self.ctx._lib.hg_matrix_spmv_form(self.ctx._h, self._h, C.byref(f)))
+        return ("csr", "sell32", "stream")[f.value]
+
     def download(self):
         """Return ``(indptr[int64], indices[int32], data[float64])``."""
         indptr = np.empty(self.shape[0] + 1, dtype=np.int64)
@@ -262,13 +285,19 @@ def _extras(maxit, n, want, want_x=True, aux=False):
     return ex, bufs
 
 
-def _rtp(fn_name, A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras):
+def _rtp(fn_name, A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm=None):
     ctx = _ctx_of(ctx, A, B)
     maxit = int(maxit)
     with _Uploaded(ctx, A, B) as (dA, dB):
         m, n = dA.shape
         b = _vec(b, m, "b")
         x_true = _vec(x_true, n, "x_true")
+        if nperm is not None:
+            # run the n-space of the solve in the caller's cache-friendly order: A(:,q), B(q,:),
+            # x_true(q) — an orthogonal similarity of B*A + lambda*I (hgmres.h: hg_matrix_permute)
+            nperm = np.ascontiguousarray(nperm, dtype=np.int32)
+            dA, dB = dA.permute(None, nperm), dB.permute(nperm, None)
+            x_true = np.ascontiguousarray(x_true[nperm])
         x = np.zeros(n)
         err = np.zeros(maxit)
         res = np.zeros(maxit)
@@ -276,24 +305,44 @@ def _rtp(fn_name, A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras):
         opts = HgSolverOpts()
         opts.residual_mode = int(residual_mode)
         ex, bufs = _extras(maxit, n, extras is not None)
+        t0 = time.perf_counter()
         check(getattr(ctx._lib, fn_name)(ctx._h, dA._h, dB._h, _ptr(b), _ptr(x_true), float(tol), maxit,
                                          float(lam), _ptr(x), _ptr(err), _ptr(res), C.byref(niters),
                                          C.byref(x_valid), C.byref(opts), C.byref(ex) if ex else None))
+        if _TRACE:
+            print(f"[hg trace] {fn_name}: C call {1e3 * (time.perf_counter() - t0):.1f} ms", file=sys.stderr)
+        if nperm is not None:
+            dA.close()
+            dB.close()
     k = niters.value
+    if nperm is not None:
+        xu = np.empty_like(x)
+        xu[nperm] = x
+        x = xu
     if extras is not None:
-        extras.update(H=bufs["H"], beta=float(bufs["beta"][0]), X=bufs["X"][:, :k])
+        X = bufs["X"][:, :k]
+        if nperm is not None:
+            Xu = np.empty_like(X)
+            Xu[nperm, :] = X
+            X = Xu
+        extras.update(H=bufs["H"], beta=float(bufs["beta"][0]), X=X)
     return (x if x_valid.value else None), err[:k], res[:k], k
 
 
-def hybrid_ab_gmres_rtp(A, B, b, x_true, tol, maxit, lam, *, ctx=None, residual_mode=0, extras=None):
+def hybrid_ab_gmres_rtp(A, B, b, x_true, tol, maxit, lam, *, ctx=None, residual_mode=0, extras=None,
+                        nperm=None):
     """``hybrid_ab_gmres_rtp.m:1`` — same positional arguments and outputs.
-    ``x`` is ``None`` exactly when the reference leaves it unassigned (``:25``)."""
-    return _rtp("hg_hybrid_ab_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras)
+    ``x`` is ``None`` exactly when the reference leaves it unassigned (``:25``).
+    ``nperm`` (optional, e.g. ``ct.tile_permutation(N)``) runs the solve with the n-space in that
+    order on the device; inputs and outputs stay in the caller's order."""
+    return _rtp("hg_hybrid_ab_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm)
 
 
-def hybrid_ba_gmres_rtp(A, B, b, x_true, tol, maxit, lam, *, ctx=None, residual_mode=0, extras=None):
-    """``hybrid_ba_gmres_rtp.m:1`` — same positional arguments and outputs."""
-    return _rtp("hg_hybrid_ba_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras)
+def hybrid_ba_gmres_rtp(A, B, b, x_true, tol, maxit, lam, *, ctx=None, residual_mode=0, extras=None,
+                        nperm=None):
+    """``hybrid_ba_gmres_rtp.m:1`` — same positional arguments and outputs (``nperm``: see
+    :func:`hybrid_ab_gmres_rtp`)."""
+    return _rtp("hg_hybrid_ba_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm)
 
 
 def _gkb(fn_name, A, b, x_true, tol, maxit, lam, ctx, At, extras, five_outputs=False):
@@ -540,9 +589,21 @@ def _ptr_solver(kind, hybrid, A, B, b, x_true, tol, maxit, lam, ctx, extras):
         check(ctx._lib.hg_gmres_ptr(ctx._h, kind, hybrid, dA._h, dB._h, _ptr(b), _ptr(x_true), float(tol), maxit,
                                     float(lam), _ptr(x), _ptr(err), _ptr(res), C.byref(niters), C.byref(x_valid),
                                     C.byref(ex) if ex else None))
+        if nperm is not None:
+            dA.close()
+            dB.close()
     k = niters.value
+    if nperm is not None:
+        xu = np.empty_like(x)
+        xu[nperm] = x
+        x = xu
     if extras is not None:
-        extras.update(H=bufs["H"], beta=float(bufs["beta"][0]), X=bufs["X"][:, :k])
+        X = bufs["X"][:, :k]
+        if nperm is not None:
+            Xu = np.empty_like(X)
+            Xu[nperm, :] = X
+            X = Xu
+        extras.update(H=bufs["H"], beta=float(bufs["beta"][0]), X=X)
     return (x if x_valid.value else None), err[:k], res[:k], k
 
 

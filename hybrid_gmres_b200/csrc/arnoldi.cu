@@ -308,6 +308,10 @@ struct ArnoldiHolder {
 
 enum RtpKind { RTP_AB, RTP_BA };
 
+double wall_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, const double* b,
                const double* x_true, double tol, int maxit, double lambda, double* x,
                double* error_norm, double* residual_norm, int* niters, int* x_valid,
@@ -451,8 +455,11 @@ extern "C" int hg_hybrid_ab_gmres_rtp(hg_ctx* ctx, const hg_matrix* A, const hg_
                                       double lambda, double* x, double* error_norm,
                                       double* residual_norm, int* niters, int* x_valid,
                                       const hg_solver_opts* opts, hg_extras* extras) {
-    return rtp_solver(RTP_AB, ctx, A, B, b, x_true, tol, maxit, lambda, x, error_norm, residual_norm,
-                      niters, x_valid, opts, extras);
+    const double t0 = wall_ms();
+    const int st = rtp_solver(RTP_AB, ctx, A, B, b, x_true, tol, maxit, lambda, x, error_norm, residual_norm,
+                              niters, x_valid, opts, extras);
+    if (getenv("HG_TRACE")) fprintf(stderr, "[hg trace] rtp AB: whole call %.1f ms (incl. release of device buffers)\n", wall_ms() - t0);
+    return st;
 }
 
 extern "C" int hg_hybrid_ba_gmres_rtp(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B,
@@ -460,8 +467,11 @@ extern "C" int hg_hybrid_ba_gmres_rtp(hg_ctx* ctx, const hg_matrix* A, const hg_
                                       double lambda, double* x, double* error_norm,
                                       double* residual_norm, int* niters, int* x_valid,
                                       const hg_solver_opts* opts, hg_extras* extras) {
-    return rtp_solver(RTP_BA, ctx, A, B, b, x_true, tol, maxit, lambda, x, error_norm, residual_norm,
-                      niters, x_valid, opts, extras);
+    const double t0 = wall_ms();
+    const int st = rtp_solver(RTP_BA, ctx, A, B, b, x_true, tol, maxit, lambda, x, error_norm, residual_norm,
+                              niters, x_valid, opts, extras);
+    if (getenv("HG_TRACE")) fprintf(stderr, "[hg trace] rtp BA: whole call %.1f ms (incl. release of device buffers)\n", wall_ms() - t0);
+    return st;
 }
 
 // ===========================================================================

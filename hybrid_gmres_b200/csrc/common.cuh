@@ -80,6 +80,12 @@ struct hg_matrix {
     // streaming-SpMV work partition (lazily built cache, see spmv_stream.cu)
     int64_t* unit_row = nullptr;  // device, n_units+1 row boundaries, nnz balanced
     int n_units = 0;
+    // 32-row sliced copy for the row-per-lane SpMV (lazily built cache, see spmv_sell.cu)
+    int sell_state = 0;           // 0 not examined, 1 built, -1 not eligible
+    int64_t sell_slices = 0, sell_entries = 0;
+    int64_t* sell_ptr = nullptr;  // device, sell_slices+1 entry offsets (multiples of 32)
+    int32_t* sell_col = nullptr;  // device, sell_entries, slice-column-major
+    double* sell_val = nullptr;
 };
 
 // colind / vals are allocated with this many zero entries of tail padding so the
@@ -169,6 +175,12 @@ bool hg_cgs_fused();
 bool hg_spmv_stream_eligible(const hg_matrix* m);
 int hg_k_spmv_stream(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
                      const hg_spmv_epilogue& ep, int* nparts);
+
+// row-per-lane SpMV over 32-row slices (spmv_sell.cu)
+int hg_spmv_mode();
+bool hg_sell_ready(hg_ctx* ctx, const hg_matrix* m);
+int hg_k_spmv_sell(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
+                   const hg_spmv_epilogue& ep, double bytes, int* nparts);
 
 // transposition (matrix.cu)
 int hg_transpose_device(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out);

@@ -485,6 +485,8 @@ int hg_k_spmv(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
     if (nparts) *nparts = 0;
     if (m->rows == 0) return HG_OK;
     if (hg_spmv_stream_eligible(m)) return hg_k_spmv_stream(ctx, m, x, y, ep, nparts);
+    if (hg_spmv_mode() == 0 && hg_sell_ready(ctx, m))
+        return hg_k_spmv_sell(ctx, m, x, y, ep, spmv_bytes(m, ep, y != nullptr), nparts);
     const int tpr = m->tpr;
     const int rpb = kBlock / tpr;
     const int64_t grid = cdiv(m->rows, rpb);

@@ -149,6 +149,34 @@ __global__ void max_row_len_kernel(int64_t rows, const int64_t* __restrict__ ptr
     if (i < rows) atomicMax(out, (unsigned long long)(ptr[i + 1] - ptr[i]));
 }
 
+// ---- permutation ------------------------------------------------------------
+__global__ void perm_row_len_kernel(int64_t rows, const int64_t* __restrict__ rowptr,
+                                    const int32_t* __restrict__ rowperm, int32_t* __restrict__ len) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) {
+        const int64_t src = rowperm ? rowperm[i] : i;
+        len[i] = (int32_t)(rowptr[src + 1] - rowptr[src]);
+    }
+}
+
+// one warp per output row: out row i = in row rowperm[i], column c relabelled to colinv[c]
+__global__ void perm_copy_kernel(int64_t rows, const int64_t* __restrict__ rowptr,
+                                 const int32_t* __restrict__ colind, const double* __restrict__ vals,
+                                 const int32_t* __restrict__ rowperm, const int32_t* __restrict__ colinv,
+                                 const int64_t* __restrict__ optr, int32_t* __restrict__ ocol,
+                                 double* __restrict__ oval) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int64_t src = rowperm ? rowperm[row] : row;
+    const int64_t s = rowptr[src], e = rowptr[src + 1], d = optr[row];
+    for (int64_t i = s + lane; i < e; i += 32) {
+        const int c = colind[i];
+        ocol[d + (i - s)] = colinv ? colinv[c] : c;
+        oval[d + (i - s)] = vals[i];
+    }
+}
+
 }  // namespace
 
 int hg_matrix_alloc(hg_ctx* ctx, int64_t rows, int64_t cols, int64_t nnz, hg_matrix** out) {
@@ -196,6 +224,9 @@ extern "C" int hg_matrix_destroy(hg_matrix* m) {
     if (m->colind) cudaFree(m->colind);
     if (m->vals) cudaFree(m->vals);
     if (m->unit_row) cudaFree(m->unit_row);
+    if (m->sell_ptr) cudaFree(m->sell_ptr);
+    if (m->sell_col) cudaFree(m->sell_col);
+    if (m->sell_val) cudaFree(m->sell_val);
     delete m;
     return HG_OK;
 }
@@ -348,6 +379,67 @@ extern "C" int hg_matrix_from_dense(hg_ctx* ctx, int64_t rows, int64_t cols, con
     return HG_OK;
 }
 
+// Canonicalise a CSR matrix in place: (col, val) of every row sorted by col (ties by the bit
+// pattern of val => deterministic).  Rows up to 16384 entries sort in shared memory.
+static int hg_sort_rows_device(hg_ctx* ctx, hg_matrix* t) {
+    const int64_t tr = t->rows;
+    if (tr == 0 || t->nnz == 0) return HG_OK;
+    int st = HG_OK;
+    unsigned long long* d_max = nullptr;
+    int32_t* sk = nullptr;
+    double* sv = nullptr;
+#define TR_CUDA(call)                                                                    \
+    do {                                                                                 \
+        cudaError_t _e = (call);                                                         \
+        if (_e != cudaSuccess && st == HG_OK) {                                          \
+            hg_set_error("sort rows: %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            st = HG_ERR_CUDA;                                                            \
+        }                                                                                \
+    } while (0)
+    TR_CUDA(cudaMalloc(&d_max, sizeof(unsigned long long)));
+    if (st == HG_OK) TR_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), ctx->stream));
+    if (st == HG_OK) {
+        {
+            hg_launch_scope scope(ctx, HG_K_SETUP, 8.0 * (double)tr);
+            max_row_len_kernel<<<(unsigned)cdiv(tr, kBlock), kBlock, 0, ctx->stream>>>(tr, t->rowptr, d_max);
+            TR_CUDA(cudaGetLastError());
+        }
+        unsigned long long h_max = 0;
+        TR_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, ctx->stream));
+        TR_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (st == HG_OK) {
+            const int cap_max = 16384;  // 12 B per entry -> 192 KB of shared memory
+            int cap = 256;
+            while (cap < (int)std::min<unsigned long long>(h_max, cap_max)) cap <<= 1;
+            const size_t smem = (size_t)cap * 12;
+            if (smem > 48 * 1024)
+                TR_CUDA(cudaFuncSetAttribute(sort_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int64_t grid = std::min<int64_t>(tr, (int64_t)ctx->sm_count * 64);
+            if (st == HG_OK) {
+                hg_launch_scope scope(ctx, HG_K_SETUP, 24.0 * (double)t->nnz);
+                sort_rows_kernel<<<(unsigned)grid, kBlock, smem, ctx->stream>>>(tr, t->rowptr, t->colind, t->vals, cap);
+                TR_CUDA(cudaGetLastError());
+            }
+            if (st == HG_OK && h_max > (unsigned long long)cap) {
+                TR_CUDA(cudaMalloc(&sk, (size_t)t->nnz * 4));
+                TR_CUDA(cudaMalloc(&sv, (size_t)t->nnz * 8));
+                if (st == HG_OK) {
+                    hg_launch_scope scope(ctx, HG_K_SETUP, 24.0 * (double)t->nnz);
+                    sort_long_rows_kernel<<<(unsigned)grid, kBlock, 0, ctx->stream>>>(
+                        tr, t->rowptr, t->colind, t->vals, cap, sk, sv);
+                    TR_CUDA(cudaGetLastError());
+                }
+            }
+        }
+    }
+    if (st == HG_OK) TR_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef TR_CUDA
+    if (d_max) cudaFree(d_max);
+    if (sk) cudaFree(sk);
+    if (sv) cudaFree(sv);
+    return st;
+}
+
 int hg_transpose_device(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out) {
     *out = nullptr;
     HG_REQUIRE(m->rows <= 2147483647LL, "transpose: more than 2^31-1 rows is not supported");
@@ -358,9 +450,6 @@ int hg_transpose_device(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out) {
     int st = HG_OK;
     std::vector<unsigned int> h_cnt;
     std::vector<int64_t> h_ptr;
-    unsigned long long* d_max = nullptr;
-    int32_t* sk = nullptr;
-    double* sv = nullptr;
 #define TR_CUDA(call)                                                                    \
     do {                                                                                 \
         cudaError_t _e = (call);                                                         \
@@ -370,11 +459,7 @@ int hg_transpose_device(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out) {
         }                                                                                \
     } while (0)
     TR_CUDA(cudaMalloc(&cnt, (size_t)(tr + 1) * sizeof(unsigned int)));
-    TR_CUDA(cudaMalloc(&d_max, sizeof(unsigned long long)));
-    if (st == HG_OK) {
-        TR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(tr + 1) * sizeof(unsigned int), ctx->stream));
-        TR_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), ctx->stream));
-    }
+    if (st == HG_OK) TR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(tr + 1) * sizeof(unsigned int), ctx->stream));
     if (st == HG_OK && m->nnz > 0) {
         hg_launch_scope scope(ctx, HG_K_SETUP, 4.0 * (double)m->nnz);
         count_cols_kernel<<<(unsigned)cdiv(m->nnz, kBlock), kBlock, 0, ctx->stream>>>(m->colind, m->nnz, cnt);
@@ -405,45 +490,11 @@ int hg_transpose_device(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out) {
                 m->rows, m->rowptr, m->colind, m->vals, t->rowptr, cnt, t->colind, t->vals);
             TR_CUDA(cudaGetLastError());
         }
-        {
-            hg_launch_scope scope(ctx, HG_K_SETUP, 8.0 * (double)tr);
-            max_row_len_kernel<<<(unsigned)cdiv(tr, kBlock), kBlock, 0, ctx->stream>>>(tr, t->rowptr, d_max);
-            TR_CUDA(cudaGetLastError());
-        }
-        unsigned long long h_max = 0;
-        TR_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, ctx->stream));
-        TR_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (st == HG_OK) {
-            const int cap_max = 16384;  // 12 B per entry -> 192 KB of shared memory
-            int cap = 256;
-            while (cap < (int)std::min<unsigned long long>(h_max, cap_max)) cap <<= 1;
-            const size_t smem = (size_t)cap * 12;
-            if (smem > 48 * 1024)
-                TR_CUDA(cudaFuncSetAttribute(sort_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int64_t grid = std::min<int64_t>(tr, (int64_t)ctx->sm_count * 64);
-            if (st == HG_OK) {
-                hg_launch_scope scope(ctx, HG_K_SETUP, 24.0 * (double)m->nnz);
-                sort_rows_kernel<<<(unsigned)grid, kBlock, smem, ctx->stream>>>(tr, t->rowptr, t->colind, t->vals, cap);
-                TR_CUDA(cudaGetLastError());
-            }
-            if (st == HG_OK && h_max > (unsigned long long)cap) {
-                TR_CUDA(cudaMalloc(&sk, (size_t)m->nnz * 4));
-                TR_CUDA(cudaMalloc(&sv, (size_t)m->nnz * 8));
-                if (st == HG_OK) {
-                    hg_launch_scope scope(ctx, HG_K_SETUP, 24.0 * (double)m->nnz);
-                    sort_long_rows_kernel<<<(unsigned)grid, kBlock, 0, ctx->stream>>>(
-                        tr, t->rowptr, t->colind, t->vals, cap, sk, sv);
-                    TR_CUDA(cudaGetLastError());
-                }
-            }
-        }
+        if (st == HG_OK) st = hg_sort_rows_device(ctx, t);
     }
     if (st == HG_OK) TR_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef TR_CUDA
     if (cnt) cudaFree(cnt);
-    if (d_max) cudaFree(d_max);
-    if (sk) cudaFree(sk);
-    if (sv) cudaFree(sv);
     if (st != HG_OK) {
         hg_matrix_destroy(t);
         return st;
@@ -457,6 +508,96 @@ extern "C" int hg_matrix_transpose(hg_ctx* ctx, const hg_matrix* m, hg_matrix** 
     HG_REQUIRE(ctx && m && out, "hg_matrix_transpose: NULL argument");
     HG_CUDA(cudaSetDevice(ctx->device));
     return hg_transpose_device(ctx, m, out);
+}
+
+static bool invert_perm(const int32_t* perm, int64_t n, std::vector<int32_t>& inv) {
+    inv.assign((size_t)n, -1);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t p = perm[i];
+        if (p < 0 || p >= n || inv[(size_t)p] != -1) return false;
+        inv[(size_t)p] = (int32_t)i;
+    }
+    return true;
+}
+
+extern "C" int hg_matrix_permute(hg_ctx* ctx, const hg_matrix* m, const int32_t* rowperm,
+                                 const int32_t* colperm, hg_matrix** out) {
+    HG_REQUIRE(ctx && m && out, "hg_matrix_permute: NULL argument");
+    HG_REQUIRE(m->rows <= 2147483647LL, "hg_matrix_permute: more than 2^31-1 rows is not supported");
+    HG_CUDA(cudaSetDevice(ctx->device));
+    *out = nullptr;
+    std::vector<int32_t> inv;
+    if (rowperm) HG_REQUIRE(invert_perm(rowperm, m->rows, inv), "hg_matrix_permute: rowperm is not a permutation of 0..rows-1");
+    if (colperm) HG_REQUIRE(invert_perm(colperm, m->cols, inv), "hg_matrix_permute: colperm is not a permutation of 0..cols-1");
+    hg_matrix* t = nullptr;
+    HG_TRY(hg_matrix_alloc(ctx, m->rows, m->cols, m->nnz, &t));
+    int32_t *d_rp = nullptr, *d_ci = nullptr, *d_len = nullptr;
+    int st = HG_OK;
+    std::vector<int32_t> h_len((size_t)m->rows);
+    std::vector<int64_t> h_ptr((size_t)m->rows + 1);
+#define PM_CUDA(call)                                                                    \
+    do {                                                                                 \
+        cudaError_t _e = (call);                                                         \
+        if (_e != cudaSuccess && st == HG_OK) {                                          \
+            hg_set_error("permute: %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            st = HG_ERR_CUDA;                                                            \
+        }                                                                                \
+    } while (0)
+    if (rowperm) {
+        PM_CUDA(cudaMalloc(&d_rp, (size_t)std::max<int64_t>(m->rows, 1) * 4));
+        if (st == HG_OK) PM_CUDA(cudaMemcpyAsync(d_rp, rowperm, (size_t)m->rows * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (colperm) {
+        PM_CUDA(cudaMalloc(&d_ci, (size_t)std::max<int64_t>(m->cols, 1) * 4));
+        if (st == HG_OK) PM_CUDA(cudaMemcpyAsync(d_ci, inv.data(), (size_t)m->cols * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PM_CUDA(cudaMalloc(&d_len, (size_t)std::max<int64_t>(m->rows, 1) * 4));
+    if (st == HG_OK && m->rows > 0) {
+        {
+            hg_launch_scope scope(ctx, HG_K_SETUP, 16.0 * (double)m->rows);
+            perm_row_len_kernel<<<(unsigned)cdiv(m->rows, kBlock), kBlock, 0, ctx->stream>>>(m->rows, m->rowptr, d_rp, d_len);
+            PM_CUDA(cudaGetLastError());
+        }
+        PM_CUDA(cudaMemcpyAsync(h_len.data(), d_len, (size_t)m->rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (st == HG_OK) {
+        int64_t acc = 0;
+        for (int64_t i = 0; i < m->rows; ++i) {
+            h_ptr[(size_t)i] = acc;
+            acc += h_len[(size_t)i];
+        }
+        h_ptr[(size_t)m->rows] = acc;
+        PM_CUDA(cudaMemcpyAsync(t->rowptr, h_ptr.data(), (size_t)(m->rows + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (st == HG_OK && m->nnz > 0) {
+        hg_launch_scope scope(ctx, HG_K_SETUP, 24.0 * (double)m->nnz);
+        perm_copy_kernel<<<(unsigned)cdiv(m->rows * 32, kBlock), kBlock, 0, ctx->stream>>>(
+            m->rows, m->rowptr, m->colind, m->vals, d_rp, d_ci, t->rowptr, t->colind, t->vals);
+        PM_CUDA(cudaGetLastError());
+    }
+    if (st == HG_OK && colperm) st = hg_sort_rows_device(ctx, t);  // relabelled columns: restore canonical order
+    if (st == HG_OK) PM_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef PM_CUDA
+    if (d_rp) cudaFree(d_rp);
+    if (d_ci) cudaFree(d_ci);
+    if (d_len) cudaFree(d_len);
+    if (st != HG_OK) {
+        hg_matrix_destroy(t);
+        return st;
+    }
+    hg_matrix_pick_tpr(t);
+    *out = t;
+    return HG_OK;
+}
+
+extern "C" int hg_matrix_spmv_form(hg_ctx* ctx, const hg_matrix* m, int* form) {
+    HG_REQUIRE(ctx && m && form, "hg_matrix_spmv_form: NULL argument");
+    HG_CUDA(cudaSetDevice(ctx->device));
+    if (hg_spmv_stream_eligible(m)) *form = 2;
+    else if (m->rows > 0 && hg_spmv_mode() == 0 && hg_sell_ready(ctx, m)) *form = 1;
+    else *form = 0;
+    return HG_OK;
 }
 
 extern "C" int hg_matrix_download_csr(hg_ctx* ctx, const hg_matrix* m, int64_t* rowptr,

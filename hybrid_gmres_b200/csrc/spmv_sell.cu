@@ -1,0 +1,246 @@
+// Row-per-lane SpMV over a 32-row sliced copy of a CSR matrix (SELL-32).
+//
+// Why: the row-per-warp CSR kernel (kernels.cu) gathers x for 32 CONSECUTIVE ENTRIES OF ONE
+// ROW per instruction.  For a pixel-driven back-projector B (row = pixel, two detector bins
+// per view) those 32 entries belong to 16 different views, i.e. 16 different 128-byte lines:
+// ncu (profiles/r01_spmv_variants.md) shows the L1 data pipe at 81-85 % of its wavefront peak
+// and the kernel slowing down with the SM clock under the power cap.  Here a lane owns a ROW
+// and the warp walks 32 adjacent rows in lock step: entry j of 32 adjacent pixels is the same
+// view and a window of neighbouring bins, i.e. 1-2 lines per gather, and the matrix stream
+// stays perfectly coalesced because the slice is stored column-major (entry j of lane l at
+// slice_base + 32 j + l).  Same entries, same per-row order as the CSR matrix; only slices
+// whose rows have (nearly) equal length are worth it, so the form is built only when padding
+// costs <= 3 % (B of every CT configuration: exactly 2*views entries per row).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ double ld_stream(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// widths[s] = max row length in slice s
+__global__ void slice_width_kernel(int64_t rows, const int64_t* __restrict__ rowptr,
+                                   int32_t* __restrict__ widths) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int len = row < rows ? (int)(rowptr[row + 1] - rowptr[row]) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && (row >> 5) < ((rows + 31) >> 5)) widths[row >> 5] = len;
+}
+
+// one warp per slice: a row's entries are read coalesced (32 consecutive entries per trip)
+// and scattered to their strided slots; padding slots repeat the row's last column with a
+// zero value so padded gathers stay inside the row's own footprint
+__global__ void __launch_bounds__(kBlock)
+sell_fill_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ rowptr,
+                 const int32_t* __restrict__ colind, const double* __restrict__ vals,
+                 const int64_t* __restrict__ sptr, int32_t* __restrict__ scol,
+                 double* __restrict__ sval) {
+    const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (slice >= nslices) return;
+    const int64_t base = sptr[slice];
+    const int width = (int)((sptr[slice + 1] - base) >> 5);
+    for (int r = 0; r < 32; ++r) {
+        const int64_t row = slice * 32 + r;
+        int64_t s = 0, e = 0;
+        if (row < rows) {
+            s = rowptr[row];
+            e = rowptr[row + 1];
+        }
+        const int len = (int)(e - s);
+        const int padcol = len > 0 ? colind[e - 1] : 0;
+        for (int j = lane; j < width; j += 32) {
+            const int64_t dst = base + (int64_t)j * 32 + r;
+            if (j < len) {
+                scol[dst] = colind[s + j];
+                sval[dst] = vals[s + j];
+            } else {
+                scol[dst] = padcol;
+                sval[dst] = 0.0;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// y[row] = alpha * sum_j val[row,j] * x[col[row,j]] + g1 z1[row] + g2 z2[row]
+// lane = row, warp = slice; software pipelined like the CSR kernel: the stream loads of the
+// next batch are in flight while this batch's gathers resolve.
+// ---------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(kBlock)
+spmv_sell32_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ sptr,
+                   const int* __restrict__ scol, const double* __restrict__ sval,
+                   const double* __restrict__ x, double* __restrict__ y, double alpha,
+                   const double* __restrict__ z1, double g1, const double* __restrict__ z2,
+                   double g2, const double* __restrict__ ref, double* __restrict__ stat) {
+    const int lane = threadIdx.x & 31;
+    const int64_t slice = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    const bool live = slice < nslices;
+    const int64_t s = live ? sptr[slice] : 0;
+    const int64_t e = live ? sptr[slice + 1] : 0;
+    double a[U];
+    int c[U];
+    double v[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = 0.0;
+    int64_t i = s + lane;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        ok[u] = i + u * 32 < e;
+        c[u] = ok[u] ? ld_stream(scol + i + u * 32) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = ok[u] ? ld_stream(sval + i + u * 32) : 0.0;
+    while (i - lane < e) {  // warp uniform
+        double xg[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) xg[u] = ok[u] ? __ldg(x + c[u]) : 0.0;
+        const int64_t in = i + U * 32;
+        int cn[U];
+        double vn[U];
+        bool okn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            okn[u] = in + u * 32 < e;
+            cn[u] = okn[u] ? ld_stream(scol + in + u * 32) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) vn[u] = okn[u] ? ld_stream(sval + in + u * 32) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            a[u] = fma(v[u], xg[u], a[u]);
+            c[u] = cn[u];
+            v[u] = vn[u];
+            ok[u] = okn[u];
+        }
+        i = in;
+    }
+    double sum = 0.0;
+    if (U == 4) sum = (a[0] + a[1]) + (a[2] + a[3]);
+    else
+#pragma unroll
+        for (int u = 0; u < U; ++u) sum += a[u];
+    const int64_t row = slice * 32 + lane;
+    double sq = 0.0;
+    if (live && row < rows) {
+        double out = alpha * sum;
+        if (z1) out += g1 * z1[row];
+        if (z2) out += g2 * z2[row];
+        if (y) y[row] = out;
+        if (stat) {
+            const double d = ref ? out - ref[row] : out;
+            sq = d * d;
+        }
+    }
+    if (stat) {
+        __shared__ double s_red[kBlock / 32];
+        sq = warp_sum(sq);
+        if (lane == 0) s_red[threadIdx.x >> 5] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; ++w) t += s_red[w];
+            stat[blockIdx.x] = t;
+        }
+    }
+}
+
+}  // namespace
+
+// Builds the sliced form when it pays; returns true when m->sell_* are usable.
+// sell_state: 0 not examined, 1 built, -1 not eligible / build failed (CSR kernel is used).
+bool hg_sell_ready(hg_ctx* ctx, const hg_matrix* cm) {
+    hg_matrix* m = const_cast<hg_matrix*>(cm);  // lazily built cache, like unit_row
+    if (m->sell_state != 0) return m->sell_state > 0;
+    m->sell_state = -1;
+    if (m->rows < 64 || m->nnz < 8 * m->rows) return false;  // short rows: TPR<32 CSR kernels do fine
+    const int64_t nslices = cdiv(m->rows, 32);
+    int32_t* d_w = nullptr;
+    if (cudaMalloc(&d_w, (size_t)nslices * 4) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    {
+        hg_launch_scope scope(ctx, HG_K_SETUP, 8.0 * (double)m->rows);
+        slice_width_kernel<<<(unsigned)cdiv(nslices * 32, kBlock), kBlock, 0, ctx->stream>>>(
+            m->rows, m->rowptr, d_w);
+    }
+    std::vector<int32_t> w((size_t)nslices);
+    cudaError_t e = cudaMemcpyAsync(w.data(), d_w, (size_t)nslices * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_w);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    std::vector<int64_t> ptr((size_t)nslices + 1);
+    int64_t acc = 0;
+    for (int64_t s = 0; s < nslices; ++s) {
+        ptr[(size_t)s] = acc;
+        acc += (int64_t)w[(size_t)s] * 32;
+    }
+    ptr[(size_t)nslices] = acc;
+    if ((double)acc > 1.03 * (double)m->nnz) return false;  // ragged rows: padding would cost > 3 % of the stream
+    cudaError_t a = cudaMalloc(&m->sell_ptr, (size_t)(nslices + 1) * 8);
+    if (a == cudaSuccess) a = cudaMalloc(&m->sell_col, (size_t)(acc + kNnzPad) * 4);
+    if (a == cudaSuccess) a = cudaMalloc(&m->sell_val, (size_t)(acc + kNnzPad) * 8);
+    if (a == cudaSuccess)
+        a = cudaMemcpyAsync(m->sell_ptr, ptr.data(), (size_t)(nslices + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (a == cudaSuccess) {
+        hg_launch_scope scope(ctx, HG_K_SETUP, 24.0 * (double)m->nnz);
+        sell_fill_kernel<<<(unsigned)cdiv(nslices * 32, kBlock), kBlock, 0, ctx->stream>>>(
+            m->rows, nslices, m->rowptr, m->colind, m->vals, m->sell_ptr, m->sell_col, m->sell_val);
+        a = cudaGetLastError();
+    }
+    if (a == cudaSuccess) a = cudaStreamSynchronize(ctx->stream);  // `ptr` is pageable host memory
+    if (a != cudaSuccess) {
+        cudaGetLastError();
+        if (m->sell_ptr) cudaFree(m->sell_ptr);
+        if (m->sell_col) cudaFree(m->sell_col);
+        if (m->sell_val) cudaFree(m->sell_val);
+        m->sell_ptr = nullptr;
+        m->sell_col = nullptr;
+        m->sell_val = nullptr;
+        return false;  // out of memory: keep the CSR path
+    }
+    m->sell_slices = nslices;
+    m->sell_entries = acc;
+    m->sell_state = 1;
+    return true;
+}
+
+int hg_k_spmv_sell(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
+                   const hg_spmv_epilogue& ep, double bytes, int* nparts) {
+    const int64_t grid = cdiv(m->sell_slices, kBlock / 32);
+    HG_REQUIRE(grid < (int64_t)2147483647, "spmv: too many rows for one launch");
+    if (nparts && ep.stat) *nparts = (int)grid;
+    hg_launch_scope scope(ctx, HG_K_SPMV, bytes);
+    spmv_sell32_kernel<4><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(
+        m->rows, m->sell_slices, m->sell_ptr, m->sell_col, m->sell_val, x, y, ep.alpha, ep.z1, ep.g1,
+        ep.z2, ep.g2, ep.ref, ep.stat);
+    HG_CUDA(cudaGetLastError());
+    return HG_OK;
+}

@@ -251,6 +251,8 @@ static int spmv_mode() {
     return g_spmv_mode;
 }
 
+int hg_spmv_mode() { return spmv_mode(); }
+
 static int g_cgs_fused = -1;
 bool hg_cgs_fused() {
     if (g_cgs_fused < 0) {

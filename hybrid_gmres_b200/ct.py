@@ -106,3 +106,21 @@ def ct_backprojector_cols(N, angles_deg, p, geometry, col_lo, col_hi, R=None, ct
     check(ctx._lib.hg_ct_backprojector_cols(ctx._h, int(N), int(c.shape[0]), int(p), _geom(geometry), float(R),
                                             _ptr(c), _ptr(s), int(col_lo), int(col_hi), C.byref(h)))
     return DeviceMatrix(h, ctx)
+
+
+def tile_permutation(N: int, tile: int = 4) -> np.ndarray:
+    """Pixel order that keeps ``tile x tile`` blocks of the N x N image contiguous: ``perm[new] = old``
+    with ``old`` the column-major pixel index of ``x_true(:)``.  A 4 x 4 tile of doubles is one 128-byte
+    line, so a ray of the projector touches ~5 pixels per gathered line instead of 1-2 when it runs
+    across the image columns (the L1 wavefront count of the SpMV gather, profiles/r01_spmv_variants.md).
+    Use as ``A.permute(None, perm)``, ``B.permute(perm, None)``, ``x_true[perm]``; ``x[perm] = x_tiled``."""
+    if N % tile:
+        raise ValueError("tile_permutation: N must be a multiple of the tile size")
+    nt = N // tile
+    tr, tc, ir, ic = np.meshgrid(np.arange(nt), np.arange(nt), np.arange(tile), np.arange(tile), indexing="ij")
+    # new index = ((tile_col * nt + tile_row) * tile + in_col) * tile + in_row  (column-major at both levels)
+    new = ((tc * nt + tr) * tile + ic) * tile + ir
+    old = (tc * tile + ic) * N + (tr * tile + ir)
+    perm = np.empty(N * N, dtype=np.int32)
+    perm[new.ravel()] = old.ravel()
+    return perm

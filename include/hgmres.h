@@ -61,8 +61,9 @@ typedef struct hg_gcv hg_gcv;         /* memoised gcv_function Arnoldi       */
 const char* hg_last_error(void);
 int hg_version(void);
 
-/* Tuning knobs.  "spmv_mode": 0 auto (default; also env HG_SPMV=v1|v2), 1 force the
- * row-per-warp SpMV, 2 force the TMA-staged streaming SpMV.
+/* Tuning knobs.  "spmv_mode": 0 auto (default; also env HG_SPMV=v1|v2): row-per-lane kernel over
+ * 32-row slices when rows have near-equal length (padding <= 3 %), else the row-per-warp CSR kernel;
+ * 1 force the row-per-warp CSR SpMV, 2 force the TMA-staged streaming SpMV.
  * "cgs_fused": 0 (default; env HG_CGS_FUSED=1 enables) fuses the first CGS2 update with the
  * second-pass dot products (basis crosses HBM three times per step instead of four; measured
  * slower than the two separate streaming kernels on B200, see profiles/r01_cgs_fusion.md). */
@@ -112,6 +113,17 @@ int hg_matrix_from_dense(hg_ctx* ctx, int64_t rows, int64_t cols, const double* 
                          hg_matrix** out);
 /* out = M^T as a new CSR matrix, column indices sorted within each row. */
 int hg_matrix_transpose(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out);
+/* out = M(rowperm, colperm) in MATLAB's gather convention: out row i is M row rowperm[i], out
+ * column j is M column colperm[j] (0-based host arrays; either may be NULL = identity).  Columns are
+ * re-sorted within each row.  Used to run the n-space of a solve in a cache-friendly pixel order
+ * (A(:,q), B(q,:), x_true(q); the iterate comes back as x(q) = x_q) — an orthogonal similarity of the
+ * operator B*A + lambda*I of hybrid_ab_gmres_rtp.m:6, so H, beta and the histories are unchanged up
+ * to summation order. */
+int hg_matrix_permute(hg_ctx* ctx, const hg_matrix* m, const int32_t* rowperm, const int32_t* colperm,
+                      hg_matrix** out);
+/* Which SpMV kernel this matrix runs with: 0 CSR row-per-thread-group, 1 row-per-lane over 32-row
+ * slices (built lazily when rows of a slice have near-equal length), 2 TMA-staged streaming. */
+int hg_matrix_spmv_form(hg_ctx* ctx, const hg_matrix* m, int* form);
 int hg_matrix_info(const hg_matrix* m, int64_t* rows, int64_t* cols, int64_t* nnz);
 int hg_matrix_download_csr(hg_ctx* ctx, const hg_matrix* m, int64_t* rowptr, int32_t* colind,
                            double* vals);

@@ -184,3 +184,71 @@ def test_streaming_spmv_in_solvers(hg, ctx, ct64, spmv_mode):
         assert a[3] == c[3]
         assert np.linalg.norm(a[0] - c[0]) / np.linalg.norm(a[0]) < 1e-10
         assert np.max(np.abs(a[2] - c[2]) / a[2]) < 1e-10
+
+
+# ---------------------------------------------------------------------------
+# row-per-lane SpMV over 32-row slices, and n-space permutations
+# ---------------------------------------------------------------------------
+def _uniform_rows(rows, cols, per_row, rng, ragged=0):
+    """CSR matrix with `per_row` entries in every row (minus up to `ragged` in random rows)."""
+    lens = np.full(rows, per_row) - (rng.integers(0, ragged + 1, rows) if ragged else 0)
+    indptr = np.concatenate([[0], np.cumsum(lens)])
+    indices = np.concatenate([np.sort(rng.choice(cols, l, replace=False)) for l in lens]).astype(np.int32)
+    return sp.csr_matrix((rng.standard_normal(indices.shape[0]), indices, indptr), shape=(rows, cols))
+
+
+@pytest.mark.parametrize("rows,per_row,ragged", [(64, 8, 0), (1000, 37, 0), (4099, 64, 1), (288, 130, 0)])
+def test_spmv_sliced_form_matches_csr(hg, ctx, rows, per_row, ragged):
+    rng = np.random.default_rng(10)
+    M = _uniform_rows(rows, 700, per_row, rng, ragged)
+    d = hg.DeviceMatrix.from_any(M, ctx)
+    assert d.spmv_form == "sell32"
+    x = rng.standard_normal(M.shape[1])
+    y = d.matvec(x)
+    assert _rel(y, M @ x) < RTOL
+    assert np.array_equal(d.matvec(x), y)  # deterministic
+    hg.set_option("spmv_mode", 1)
+    try:
+        d1 = hg.DeviceMatrix.from_any(M, ctx)
+        assert d1.spmv_form == "csr"
+        y1 = d1.matvec(x)
+    finally:
+        hg.set_option("spmv_mode", 0)
+    assert _rel(y, y1) < RTOL
+
+
+def test_spmv_ragged_rows_stay_csr(hg, ctx, ct64):
+    A, B = ct64[0], ct64[1]
+    dA = hg.DeviceMatrix.from_any(A, ctx)
+    assert dA.spmv_form == "csr"  # ray lengths vary by more than 3 % inside a slice
+
+
+def test_pixel_backprojector_uses_sliced_form(hg, ctx, ct48_unmatched):
+    A, B, b, x_true = ct48_unmatched
+    dB = hg.DeviceMatrix.from_any(B, ctx)
+    assert dB.spmv_form == "sell32"
+    u = np.random.default_rng(11).standard_normal(B.shape[1])
+    assert _rel(dB.matvec(u), B @ u) < RTOL
+
+
+def test_permute_bit_exact(hg, ctx, ct48_unmatched):
+    from hybrid_gmres_b200.ct import tile_permutation
+    A, B = ct48_unmatched[0], ct48_unmatched[1]
+    q = tile_permutation(48, 4)
+    rng = np.random.default_rng(12)
+    r = rng.permutation(A.shape[0]).astype(np.int32)
+    for M, rp, cp in ((A, None, q), (B, q, None), (A, r, q)):
+        d = hg.DeviceMatrix.from_any(M, ctx).permute(rp, cp)
+        ref = M.tocsr()
+        if rp is not None:
+            ref = ref[rp, :]
+        if cp is not None:
+            ref = ref[:, cp]
+        ref = ref.tocsr()
+        ref.sort_indices()
+        indptr, indices, data = d.download()
+        assert np.array_equal(indptr, ref.indptr)
+        assert np.array_equal(indices, ref.indices)
+        assert np.array_equal(data, ref.data)
+    with pytest.raises(hg._lib.HgError):
+        hg.DeviceMatrix.from_any(A, ctx).permute(None, np.zeros(A.shape[1], dtype=np.int32))

@@ -273,3 +273,23 @@ def test_cgs_fused_option_matches_default(hg, ctx, ct64):
     assert np.max(_colwise(e1["H"], e0["H"], r0[3])) < 1e-11
     assert np.max(np.abs(r0[2] - r1[2]) / r0[2]) < 1e-11
     assert np.linalg.norm(r0[0] - r1[0]) / np.linalg.norm(r0[0]) < 1e-11
+
+
+@pytest.mark.parametrize("solver", ["hybrid_ab_gmres_rtp", "hybrid_ba_gmres_rtp"])
+def test_nspace_permutation_is_a_similarity(hg, ctx, ct48_unmatched, solver):
+    """Running the n-space in 4x4-tile pixel order (hg_matrix_permute) changes only the summation
+    order: same H, beta, histories and iterate as the natural order."""
+    from hybrid_gmres_b200.ct import tile_permutation
+    A, B, b, x_true = ct48_unmatched
+    f = getattr(hg, solver)
+    e0, e1 = {}, {}
+    x0, err0, res0, k0 = f(A, B, b, x_true, 0.0, 30, 1e-2, ctx=ctx, extras=e0)
+    x1, err1, res1, k1 = f(A, B, b, x_true, 0.0, 30, 1e-2, ctx=ctx, extras=e1, nperm=tile_permutation(48, 4))
+    assert k0 == k1 == 30
+    assert abs(e0["beta"] - e1["beta"]) <= 1e-13 * abs(e0["beta"])
+    for j in range(30):
+        assert np.linalg.norm(e0["H"][:, j] - e1["H"][:, j]) <= 1e-10 * np.linalg.norm(e0["H"][:, j])
+    assert np.max(np.abs(res0 - res1) / res0) < 1e-10
+    assert np.max(np.abs(err0 - err1) / err0) < 1e-10
+    assert np.linalg.norm(x0 - x1) <= 1e-10 * np.linalg.norm(x0)
+    assert np.linalg.norm(e0["X"] - e1["X"]) <= 1e-10 * np.linalg.norm(e0["X"])
