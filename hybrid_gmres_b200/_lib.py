@@ -64,6 +64,7 @@ PROTOTYPES = {
     "hg_comm_unique_id": (_i, [_vp]),
     "hg_comm_init": (_i, [_vp, _i, _i, _vp, c_void_pp]),
     "hg_comm_destroy": (_i, [_vp]),
+    "hg_comm_transport": (_i, [_vp, c_int_p, C.c_char_p, _i]),
     "hg_darnoldi_create": (_i, [_vp, _vp, _vp, _vp, _i, c_void_pp]),
     "hg_darnoldi_destroy": (_i, [_vp]),
     "hg_darnoldi_set_rhs": (_i, [_vp, _vp]),

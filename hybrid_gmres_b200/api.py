@@ -36,7 +36,7 @@ __all__ = [
 
 _TRACE = os.environ.get("HG_TRACE") is not None
 
-KERNEL_CLASSES = {"spmv": 0, "multidot": 1, "lincomb": 2, "vector": 3, "reduce": 4, "setup": 5}
+KERNEL_CLASSES = {"spmv": 0, "multidot": 1, "lincomb": 2, "vector": 3, "reduce": 4, "setup": 5, "comm": 6}
 
 
 def _ptr(a):
@@ -589,21 +589,9 @@ def _ptr_solver(kind, hybrid, A, B, b, x_true, tol, maxit, lam, ctx, extras):
         check(ctx._lib.hg_gmres_ptr(ctx._h, kind, hybrid, dA._h, dB._h, _ptr(b), _ptr(x_true), float(tol), maxit,
                                     float(lam), _ptr(x), _ptr(err), _ptr(res), C.byref(niters), C.byref(x_valid),
                                     C.byref(ex) if ex else None))
-        if nperm is not None:
-            dA.close()
-            dB.close()
     k = niters.value
-    if nperm is not None:
-        xu = np.empty_like(x)
-        xu[nperm] = x
-        x = xu
     if extras is not None:
-        X = bufs["X"][:, :k]
-        if nperm is not None:
-            Xu = np.empty_like(X)
-            Xu[nperm, :] = X
-            X = Xu
-        extras.update(H=bufs["H"], beta=float(bufs["beta"][0]), X=X)
+        extras.update(H=bufs["H"], beta=float(bufs["beta"][0]), X=bufs["X"][:, :k])
     return (x if x_valid.value else None), err[:k], res[:k], k
 
 

@@ -142,6 +142,16 @@ int hg_k_lincomb(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, con
                  double s, const double* z, double* out, const double* ref, double* stat,
                  int* nparts);
 
+// same, with the result rows also stored to up to 16 further destinations (peer-GPU copies of the
+// vector: the all-gather of the sharded Arnoldi is done by the producing kernel, dist_peer.cu)
+struct hg_out_list {
+    double* p[16];
+    int n = 0;
+};
+int hg_k_lincomb_push(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* c,
+                      double s, const double* z, double* out, const double* ref, double* stat,
+                      int* nparts, const hg_out_list* extra);
+
 // fused CGS2 middle stage: w1 = w0 - V h ; partials[j*ntiles + tile] = sum_tile V[:,j].*w1
 int hg_update_dot_ntiles(int64_t n);
 int hg_k_update_dot(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* h,

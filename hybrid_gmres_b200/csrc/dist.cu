@@ -15,15 +15,14 @@
 
 #include <algorithm>
 
-#include "common.cuh"
+#include "dist_internal.h"
 
 namespace {
 
-typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclDouble = 8 };  // ncclFloat64
-enum { ncclSum = 0 };
+enum { ncclChar = 0, ncclDouble = 8 };  // ncclInt8, ncclFloat64
+enum { ncclSum = 0, ncclMin = 3 };
 
 struct NcclApi {
     void* lib = nullptr;
@@ -81,10 +80,19 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 }  // namespace
 
-struct hg_comm {
-    ncclComm_t comm = nullptr;
-    int rank = 0, nranks = 1;
-};
+int hg_nccl_allgather_bytes(hg_comm* c, const void* d_send, void* d_recv, size_t bytes_per_rank, cudaStream_t st) {
+    HG_NCCL(g_nccl.AllGather(d_send, d_recv, bytes_per_rank, ncclChar, c->comm, st));
+    return HG_OK;
+}
+int hg_nccl_allreduce_min(hg_comm* c, double* d_buf, cudaStream_t st) {
+    HG_NCCL(g_nccl.AllReduce(d_buf, d_buf, 1, ncclDouble, ncclMin, c->comm, st));
+    return HG_OK;
+}
+int hg_nccl_barrier(hg_comm* c, cudaStream_t st) {
+    HG_NCCL(g_nccl.AllReduce(c->ctx->d_scalars + 60, c->ctx->d_scalars + 60, 1, ncclDouble, ncclSum, c->comm, st));
+    HG_CUDA(cudaStreamSynchronize(st));
+    return HG_OK;
+}
 
 extern "C" int hg_comm_unique_id(void* out128) {
     HG_REQUIRE(out128, "hg_comm_unique_id: NULL");
@@ -107,6 +115,7 @@ extern "C" int hg_comm_init(hg_ctx* ctx, int nranks, int rank, const void* id128
     }
     c->rank = rank;
     c->nranks = nranks;
+    c->ctx = ctx;
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
     int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
@@ -121,8 +130,17 @@ extern "C" int hg_comm_init(hg_ctx* ctx, int nranks, int rank, const void* id128
 
 extern "C" int hg_comm_destroy(hg_comm* c) {
     if (!c) return HG_OK;
+    hg_peer_destroy(c);  // collective when a peer workspace exists
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     delete c;
+    return HG_OK;
+}
+
+/* 0: NCCL collectives between the kernels, 1: NVLink peer memory inside the kernels */
+extern "C" int hg_comm_transport(hg_comm* c, int* transport, char* why, int why_len) {
+    HG_REQUIRE(c && transport, "hg_comm_transport: NULL argument");
+    *transport = c->transport;
+    if (why && why_len > 0) snprintf(why, (size_t)why_len, "%s", c->why);
     return HG_OK;
 }
 
@@ -144,6 +162,9 @@ struct hg_darnoldi {
     double *partials = nullptr, *stat = nullptr;
     double shift = 0.0;
     bool have_rhs = false, started = false;
+    bool peer = false;  // NVLink peer-memory transport (dist_peer.cu): q_full / w_part live in the workspace
+    int qbuf = 0;       // which half of the double-buffered replicated q holds the current vector
+    int64_t row0 = 0;   // first global row of this rank's slice
     int ldh() const { return kmax + 1; }
 };
 
@@ -152,7 +173,9 @@ int hg_multidot_nslabs(const hg_ctx* ctx, int64_t n);
 extern "C" int hg_darnoldi_destroy(hg_darnoldi* a) {
     if (!a) return HG_OK;
     cudaStreamSynchronize(a->ctx->stream);
-    cudaFree(a->Q); cudaFree(a->T); cudaFree(a->q_full); cudaFree(a->w_part);
+    if (a->peer) hg_peer_release(a->comm, a);
+    else { cudaFree(a->q_full); cudaFree(a->w_part); }
+    cudaFree(a->Q); cudaFree(a->T);
     cudaFree(a->w0); cudaFree(a->w1); cudaFree(a->d_H); cudaFree(a->d_hcur); cudaFree(a->d_s);
     cudaFree(a->partials); cudaFree(a->stat);
     if (a->h_H) cudaFreeHost(a->h_H);
@@ -193,10 +216,19 @@ extern "C" int hg_darnoldi_create(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A
         if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(cnt, 1) * sizeof(double));
         if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, std::max<size_t>(cnt, 1) * sizeof(double), ctx->stream);
     };
+    a->row0 = (int64_t)comm->rank * a->n_p;
+    a->peer = hg_peer_acquire(comm, a->n_pad, kmax, a);  // collective; every rank takes the same decision
+    if (!a->peer && hg_dist_transport_wanted() == 2) {
+        hg_set_error("hg_darnoldi_create: peer-memory transport requested (HG_DIST=peer) but unavailable: %s", comm->why);
+        hg_darnoldi_destroy(a);
+        return HG_ERR_STATE;
+    }
     alloc(&a->Q, (size_t)a->ldq * (kmax + 1));
     alloc(&a->T, (size_t)a->ldt * (kmax + 1));
-    alloc(&a->q_full, (size_t)a->n_pad);
-    alloc(&a->w_part, (size_t)a->n_pad);
+    if (!a->peer) {
+        alloc(&a->q_full, (size_t)a->n_pad);
+        alloc(&a->w_part, (size_t)a->n_pad);
+    }
     alloc(&a->w0, (size_t)a->n_p);
     alloc(&a->w1, (size_t)a->n_p);
     alloc(&a->d_H, (size_t)a->ldh() * kmax);
@@ -252,6 +284,24 @@ extern "C" int hg_darnoldi_reset(hg_darnoldi* a, double shift) {
     HG_CUDA(cudaMemsetAsync(a->d_H, 0, (size_t)a->ldh() * a->kmax * sizeof(double), st));
     // r0 = B*b = sum_p B^p b_p  (hybrid_ba_gmres_rtp.m:7-9)
     hg_spmv_epilogue ep;
+    if (a->peer) {
+        hg_comm* c = a->comm;
+        int ns = 0, npp = 0;
+        a->qbuf = 0;
+        HG_TRY(hg_k_spmv(ctx, a->B, a->T, hg_peer_ypart(c), ep, nullptr));
+        HG_TRY(hg_k_peer_signal(c, HG_FLAG_Y));
+        // r0 slice (pulled) goes to every rank's replicated vector un-normalised; the norm
+        // all-reduce is also the barrier for those stores; then everybody scales locally
+        HG_TRY(hg_k_pull_multidot(c, a->row0, nullptr, 0.0, a->Q, a->Q, a->ldq, a->n_p, 0, a->partials, &ns));
+        hg_out_list push;
+        hg_peer_push_list(c, a->qbuf, a->row0, &push);
+        HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->n_p, 0, a->d_hcur, 1.0, a->Q, nullptr, nullptr, a->stat, &npp, &push));
+        HG_TRY(hg_k_reduce_allreduce(c, a->stat, npp, 1, a->d_s + 1, nullptr, false, true));  // beta
+        HG_TRY(hg_k_scale2(c, hg_peer_qfull(c, a->qbuf), a->n_pad, a->Q, a->n_p, a->d_s + 1));
+        HG_CUDA(cudaMemcpyAsync(a->h_beta, a->d_s + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+        a->started = true;
+        return HG_OK;
+    }
     HG_TRY(hg_k_spmv(ctx, a->B, a->T, a->w_part, ep, nullptr));
     HG_NCCL(g_nccl.ReduceScatter(a->w_part, a->Q, (size_t)a->n_p, ncclDouble, ncclSum, a->comm->comm, st));
     int np = 0;
@@ -271,6 +321,31 @@ static int darnoldi_step(hg_darnoldi* a, int kk) {
     double* qnext = a->Q + (size_t)kk * a->ldq;
     double* Hcol = a->d_H + (size_t)(kk - 1) * a->ldh();
     hg_spmv_epilogue ep;
+    if (a->peer) {
+        // the collectives run inside the kernels, over NVLink peer memory (dist_peer.cu)
+        hg_comm* c = a->comm;
+        int ns = 0, np = 0;
+        HG_TRY(hg_k_spmv(ctx, a->A, hg_peer_qfull(c, a->qbuf), tcol, ep, nullptr));  // u_p = A_p q
+        HG_TRY(hg_k_spmv(ctx, a->B, tcol, hg_peer_ypart(c), ep, nullptr));           // partial B^p u_p
+        HG_TRY(hg_k_peer_signal(c, HG_FLAG_Y));
+        // w0 = sum_p (B^p u_p)[slice] + shift*q[slice], fused with h1 = Q_k' w0
+        HG_TRY(hg_k_pull_multidot(c, a->row0, q_slice, a->shift, a->w0, a->Q, a->ldq, a->n_p, kk, a->partials, &ns));
+        HG_TRY(hg_k_reduce_allreduce(c, a->partials, ns, kk, a->d_hcur, Hcol, false, false));
+        HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr, nullptr, nullptr));
+        HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->n_p, kk, a->w1, a->partials, &ns));
+        HG_TRY(hg_k_reduce_allreduce(c, a->partials, ns, kk, a->d_hcur, Hcol, true, false));  // H(1:k,k) = h1 + h2
+        // v = w1 - Q h2: rows go to the local basis AND to every rank's replicated vector (all-gather
+        // by the producing kernel); the norm all-reduce is the barrier for them
+        a->qbuf ^= 1;
+        hg_out_list push;
+        hg_peer_push_list(c, a->qbuf, a->row0, &push);
+        HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w1, qnext, nullptr, a->stat, &np, &push));
+        HG_TRY(hg_k_reduce_allreduce(c, a->stat, np, 1, Hcol + kk, nullptr, false, true));     // H(k+1,k) = norm(v)
+        HG_TRY(hg_k_scale2(c, hg_peer_qfull(c, a->qbuf), a->n_pad, qnext, a->n_p, Hcol + kk));  // q_{k+1} = v / H(k+1,k)
+        HG_CUDA(cudaMemcpyAsync(a->h_H + (size_t)(kk - 1) * a->ldh(), Hcol, (size_t)(kk + 1) * 8,
+                                cudaMemcpyDeviceToHost, st));
+        return HG_OK;
+    }
     HG_TRY(hg_k_spmv(ctx, a->A, a->q_full, tcol, ep, nullptr));       // u_p = A_p q
     HG_TRY(hg_k_spmv(ctx, a->B, tcol, a->w_part, ep, nullptr));       // partial B^p u_p
     HG_NCCL(g_nccl.ReduceScatter(a->w_part, a->w1, (size_t)a->n_p, ncclDouble, ncclSum, a->comm->comm, st));
@@ -314,6 +389,7 @@ extern "C" int hg_darnoldi_steps(hg_darnoldi* a, int nsteps) {
 extern "C" int hg_darnoldi_get(hg_darnoldi* a, double* H, int ldh, double* beta, int* ksteps) {
     HG_REQUIRE(a, "hg_darnoldi_get: NULL");
     HG_CUDA(cudaStreamSynchronize(a->ctx->stream));
+    if (a->peer) HG_TRY(hg_peer_check(a->comm));
     if (H) {
         HG_REQUIRE(ldh >= a->ldh(), "hg_darnoldi_get: ldh too small");
         for (int j = 0; j < a->kmax; ++j)
@@ -441,8 +517,12 @@ extern "C" int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg
         if (kind == 0) {
             int ns = 0;
             HG_TRY(hg_k_multidot(ctx, a->T, a->ldt, m_p, k + 1, a->T + (size_t)k * a->ldt, a->partials, &ns));
-            HG_TRY(hg_k_reduce(ctx, a->partials, ns, k + 1, d_g.p, false, nullptr, false));
-            HG_NCCL(g_nccl.AllReduce(d_g.p, d_g.p, (size_t)(k + 1), ncclDouble, ncclSum, comm->comm, st));
+            if (a->peer) {
+                HG_TRY(hg_k_reduce_allreduce(comm, a->partials, ns, k + 1, d_g.p, nullptr, false, false));
+            } else {
+                HG_TRY(hg_k_reduce(ctx, a->partials, ns, k + 1, d_g.p, false, nullptr, false));
+                HG_NCCL(g_nccl.AllReduce(d_g.p, d_g.p, (size_t)(k + 1), ncclDouble, ncclSum, comm->comm, st));
+            }
             HG_CUDA(cudaMemcpyAsync(h_g.p, d_g.p, (size_t)(k + 1) * 8, cudaMemcpyDeviceToHost, st));
         }
         HG_CUDA(cudaStreamSynchronize(st));
@@ -471,9 +551,14 @@ extern "C" int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg
         int np_e = 0, np_r = 0;
         HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n_p, k, d_y.p, 1.0, nullptr, d_x.p, d_xt.p, stat_e.p, &np_e));
         HG_TRY(hg_k_lincomb(ctx, a->T + a->ldt, a->ldt, m_p, k, d_y.p, -1.0, a->T, nullptr, nullptr, stat_r.p, &np_r));
-        HG_TRY(hg_k_reduce(ctx, stat_e.p, np_e, 1, ctx->d_scalars + 1, false, nullptr, false));
-        HG_TRY(hg_k_reduce(ctx, stat_r.p, np_r, 1, ctx->d_scalars + 2, false, nullptr, false));
-        HG_NCCL(g_nccl.AllReduce(ctx->d_scalars + 1, ctx->d_scalars + 1, 2, ncclDouble, ncclSum, comm->comm, st));
+        if (a->peer) {
+            HG_TRY(hg_k_reduce_allreduce(comm, stat_e.p, np_e, 1, ctx->d_scalars + 1, nullptr, false, false));
+            HG_TRY(hg_k_reduce_allreduce(comm, stat_r.p, np_r, 1, ctx->d_scalars + 2, nullptr, false, false));
+        } else {
+            HG_TRY(hg_k_reduce(ctx, stat_e.p, np_e, 1, ctx->d_scalars + 1, false, nullptr, false));
+            HG_TRY(hg_k_reduce(ctx, stat_r.p, np_r, 1, ctx->d_scalars + 2, false, nullptr, false));
+            HG_NCCL(g_nccl.AllReduce(ctx->d_scalars + 1, ctx->d_scalars + 1, 2, ncclDouble, ncclSum, comm->comm, st));
+        }
         HG_CUDA(cudaMemcpyAsync(h_s.p, ctx->d_scalars + 1, 16, cudaMemcpyDeviceToHost, st));
         HG_CUDA(cudaStreamSynchronize(st));
         have_x = true;
@@ -486,6 +571,7 @@ extern "C" int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg
     HG_NCCL(g_nccl.AllGather(d_x.p, d_xfull.p, (size_t)n_p, ncclDouble, comm->comm, st));
     HG_CUDA(cudaMemcpyAsync(x, d_xfull.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     HG_CUDA(cudaStreamSynchronize(st));
+    if (a->peer) HG_TRY(hg_peer_check(comm));
     if (x_valid) *x_valid = have_x ? 1 : 0;
     if (extras) {
         if (extras->beta) *extras->beta = beta;

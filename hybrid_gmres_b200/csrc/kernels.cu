@@ -210,11 +210,12 @@ reduce_kernel(const double* __restrict__ partials, int np, double* __restrict__ 
 // Threads own two consecutive rows (one 16-byte load per column), eight
 // independent column loads in flight per thread.
 // ---------------------------------------------------------------------------
+template <bool PUSH>
 __global__ void __launch_bounds__(kBlock)
 lincomb_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
                const double* __restrict__ c, double s, const double* __restrict__ z,
                double* __restrict__ out, const double* __restrict__ ref,
-               double* __restrict__ stat) {
+               double* __restrict__ stat, hg_out_list extra) {
     extern __shared__ double sc[];
     for (int j = threadIdx.x; j < k; j += blockDim.x) sc[j] = s * c[j];
     __syncthreads();
@@ -245,6 +246,10 @@ lincomb_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
             ay = fma(sc[j], v.y, ay);
         }
         if (out) *reinterpret_cast<double2*>(out + r) = make_double2(ax, ay);
+        if (PUSH) {  // the same rows into further (peer-GPU) destinations
+#pragma unroll 4
+            for (int d = 0; d < extra.n; ++d) *reinterpret_cast<double2*>(extra.p[d] + r) = make_double2(ax, ay);
+        }
         if (stat) {
             double dx = ax, dy = ay;
             if (ref) {
@@ -258,6 +263,8 @@ lincomb_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
         double ax = z ? z[r] : 0.0;
         for (int j = 0; j < k; ++j) ax = fma(sc[j], ld_stream(V + (int64_t)j * ld + r), ax);
         if (out) out[r] = ax;
+        if (PUSH)
+            for (int d = 0; d < extra.n; ++d) extra.p[d][r] = ax;
         if (stat) {
             const double dx = ref ? ax - ref[r] : ax;
             sq = dx * dx;
@@ -514,7 +521,7 @@ int hg_k_spmv(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
     return HG_OK;
 }
 
-static int multidot_slab_rows(const hg_ctx* ctx, int64_t n) {
+int hg_multidot_slab_rows(const hg_ctx* ctx, int64_t n) {
     // aim for ~4 CTAs per SM; slab a multiple of 256 rows in [256, 4096]
     int64_t target = cdiv(n, (int64_t)ctx->sm_count * 4);
     int64_t R = cdiv(target, 256) * 256;
@@ -524,12 +531,12 @@ static int multidot_slab_rows(const hg_ctx* ctx, int64_t n) {
 }
 
 int hg_multidot_nslabs(const hg_ctx* ctx, int64_t n) {
-    return (int)cdiv(n, multidot_slab_rows(ctx, n));
+    return (int)cdiv(n, hg_multidot_slab_rows(ctx, n));
 }
 
 int hg_k_multidot(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* w,
                   double* partials, int* nslabs) {
-    const int R = multidot_slab_rows(ctx, n);
+    const int R = hg_multidot_slab_rows(ctx, n);
     const int ns = (int)cdiv(n, R);
     if (nslabs) *nslabs = ns;
     if (k <= 0 || n <= 0) return HG_OK;
@@ -550,9 +557,9 @@ int hg_k_reduce(hg_ctx* ctx, const double* partials, int np, int k, double* out,
     return HG_OK;
 }
 
-int hg_k_lincomb(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* c,
-                 double s, const double* z, double* out, const double* ref, double* stat,
-                 int* nparts) {
+int hg_k_lincomb_push(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* c,
+                      double s, const double* z, double* out, const double* ref, double* stat,
+                      int* nparts, const hg_out_list* extra) {
     const int64_t grid = cdiv(cdiv(n, 2), kBlock);
     if (nparts) *nparts = stat ? (int)grid : 0;
     if (n <= 0) return HG_OK;
@@ -560,11 +567,22 @@ int hg_k_lincomb(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, con
     if (z) bytes += 8.0 * (double)n;
     if (out) bytes += 8.0 * (double)n;
     if (ref) bytes += 8.0 * (double)n;
+    if (extra) bytes += 8.0 * (double)n * extra->n;
     hg_launch_scope scope(ctx, HG_K_LINCOMB, bytes);
-    lincomb_kernel<<<(unsigned)grid, kBlock, (size_t)(k > 0 ? k : 1) * sizeof(double),
-                     ctx->stream>>>(V, ld, n, k, c, s, z, out, ref, stat);
+    const size_t smem = (size_t)(k > 0 ? k : 1) * sizeof(double);
+    if (extra && extra->n > 0)
+        lincomb_kernel<true><<<(unsigned)grid, kBlock, smem, ctx->stream>>>(V, ld, n, k, c, s, z, out, ref, stat, *extra);
+    else
+        lincomb_kernel<false><<<(unsigned)grid, kBlock, smem, ctx->stream>>>(V, ld, n, k, c, s, z, out, ref, stat,
+                                                                            hg_out_list());
     HG_CUDA(cudaGetLastError());
     return HG_OK;
+}
+
+int hg_k_lincomb(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* c,
+                 double s, const double* z, double* out, const double* ref, double* stat,
+                 int* nparts) {
+    return hg_k_lincomb_push(ctx, V, ld, n, k, c, s, z, out, ref, stat, nparts, nullptr);
 }
 
 int hg_update_dot_ntiles(int64_t n) { return (int)cdiv(n, kTileRows); }

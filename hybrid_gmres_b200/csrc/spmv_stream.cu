@@ -262,6 +262,8 @@ bool hg_cgs_fused() {
     return g_cgs_fused != 0;
 }
 
+void hg_dist_transport_set(int v);
+
 extern "C" int hg_set_option(const char* name, int value) {
     HG_REQUIRE(name, "hg_set_option: NULL name");
     if (strcmp(name, "cgs_fused") == 0) {
@@ -271,6 +273,11 @@ extern "C" int hg_set_option(const char* name, int value) {
     if (strcmp(name, "spmv_mode") == 0) {
         HG_REQUIRE(value >= 0 && value <= 2, "hg_set_option: spmv_mode must be 0, 1 or 2");
         g_spmv_mode = value;
+        return HG_OK;
+    }
+    if (strcmp(name, "dist_transport") == 0) {
+        HG_REQUIRE(value >= 0 && value <= 2, "hg_set_option: dist_transport must be 0 (auto), 1 (nccl) or 2 (peer)");
+        hg_dist_transport_set(value);
         return HG_OK;
     }
     hg_set_error("hg_set_option: unknown option '%s'", name);

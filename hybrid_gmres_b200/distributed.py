@@ -38,6 +38,15 @@ class Communicator:
         check(ctx._lib.hg_comm_init(ctx._h, world, rank, _ptr(np.ascontiguousarray(uid)), C.byref(h)))
         self._h = h
 
+    @property
+    def transport(self) -> str:
+        """``"peer: ..."`` (collectives inside the kernels over NVLink peer memory) or ``"nccl: ..."`` —
+        decided collectively when a sharded Arnoldi is created (``hg_comm_transport``)."""
+        t = C.c_int()
+        why = C.create_string_buffer(256)
+        check(self.ctx._lib.hg_comm_transport(self._h, C.byref(t), why, 256))
+        return ("nccl: " if t.value == 0 else "peer: ") + why.value.decode()
+
     def close(self):
         if getattr(self, "_h", None):
             self.ctx._lib.hg_comm_destroy(self._h)

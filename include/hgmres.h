@@ -66,7 +66,8 @@ int hg_version(void);
  * 1 force the row-per-warp CSR SpMV, 2 force the TMA-staged streaming SpMV.
  * "cgs_fused": 0 (default; env HG_CGS_FUSED=1 enables) fuses the first CGS2 update with the
  * second-pass dot products (basis crosses HBM three times per step instead of four; measured
- * slower than the two separate streaming kernels on B200, see profiles/r01_cgs_fusion.md). */
+ * slower than the two separate streaming kernels on B200, see profiles/r01_cgs_fusion.md).
+ * "dist_transport": see hg_comm_transport. */
 int hg_set_option(const char* name, int value);
 
 /* ---- context ------------------------------------------------------------ */
@@ -87,7 +88,8 @@ typedef enum hg_kernel_class {
     HG_K_VECTOR = 3,   /* scale / axpby / fused LSQR-LSMR vector updates     */
     HG_K_REDUCE = 4,   /* second-stage deterministic reductions              */
     HG_K_SETUP = 5,    /* transpose / conversion / generators                */
-    HG_K_NCLASSES = 6
+    HG_K_COMM = 6,     /* flag barriers of the NVLink peer-memory transport  */
+    HG_K_NCLASSES = 7
 } hg_kernel_class;
 int hg_ctx_timing_enable(hg_ctx* ctx, int on);
 /* Synchronises, folds pending events, returns totals since the last reset:
@@ -185,6 +187,15 @@ typedef struct hg_darnoldi hg_darnoldi;
 int hg_comm_unique_id(void* out128);
 int hg_comm_init(hg_ctx* ctx, int nranks, int rank, const void* id128, hg_comm** out);
 int hg_comm_destroy(hg_comm* c);
+/* How the sharded Arnoldi step moves data between ranks.  1: NVLink peer memory — the
+ * reduce-scatter of B^p u_p is pulled by the CTAs of the first CGS2 multi-dot, the coefficient
+ * all-reduces are a P2P inbox exchange inside the second-stage reduction, the all-gather of
+ * q_{k+1} is pushed by the normalisation kernel (csrc/dist_peer.cu; workspace mapped with cudaIpc).
+ * 0: ncclReduceScatter / ncclAllReduce / ncclAllGather calls between the kernels.  The choice is
+ * made collectively when a sharded Arnoldi is created: option "dist_transport" / env HG_DIST =
+ * auto (0, default: peer memory when every rank can map every other rank), nccl (1), peer (2:
+ * fail instead of falling back).  `why` (optional) receives a one-line description. */
+int hg_comm_transport(hg_comm* c, int* transport, char* why, int why_len);
 /* Sharded n-space Arnoldi.  A_p: this rank's detector-row block of A (m_p x n); B_p: the
  * matching column block of B (n x m_p, local column indices).  Krylov vectors are sharded in
  * equal row slices of n_p = roundup32(ceil(n/P)) entries (zero padded). */

@@ -27,25 +27,44 @@ A, B, b, x_true = ct.make_ct_problem(N, nv, "fan", "pixel")
 n = A.shape[1]
 A_p, B_p, (lo, hi) = sharding.shard_host_matrices(A, B, P, rank)
 dA, dB = hg.DeviceMatrix.from_any(A_p, ctx), hg.DeviceMatrix.from_any(B_p, ctx)
-ar = ShardedArnoldi(comm, dA, dB, K)
-ar.set_rhs(b[lo:hi])
-ar.reset(lam)
-ar.steps(K)
-H, beta, k = ar.get()
 op = lambda v: np.asarray(B @ (A @ v)).ravel() + lam * v
 Qo, Ho, betao, _ = oracle.arnoldi(op, np.asarray(B @ b).ravel(), K, orth="cgs2")
-assert k == K
-assert abs(beta - betao) / betao < 1e-13, (beta, betao)
-worst = max(np.linalg.norm(H[:j + 2, j] - Ho[:j + 2, j]) / np.linalg.norm(Ho[:j + 2, j]) for j in range(K))
-assert worst < 1e-10, worst
-q, r0 = ar.q_slice(K)
-seg = Qo[r0:min(r0 + ar.n_p, n), K]
-assert np.linalg.norm(q[:seg.shape[0]] - seg) < 1e-9 and np.all(q[seg.shape[0]:] == 0)
-# all ranks hold bit-identical H (replicated host projected problem relies on it)
-t = torch.from_numpy(H.copy()).cuda()
-t0 = t.clone()
-dist.broadcast(t0, src=0)
-assert torch.equal(t, t0)
+H_by_transport = {}
+worst = 0.0
+# dist_transport 1: NCCL collectives between the kernels; 2: NVLink peer memory inside the kernels
+# (required, no fall-back); then 0 = auto for the rest of the worker
+for mode in (1, 2, 0):
+    hg.set_option("dist_transport", mode)
+    ar = ShardedArnoldi(comm, dA, dB, K)
+    assert comm.transport.startswith("nccl" if mode == 1 else "peer"), (mode, comm.transport)
+    for rep in range(2):  # a second cycle re-uses the workspace, flags and inbox slots
+        ar.set_rhs(b[lo:hi])
+        ar.reset(lam)
+        ar.steps(K // 2)
+        ar.steps(K - K // 2)
+        H, beta, k = ar.get()
+        assert k == K
+        assert abs(beta - betao) / betao < 1e-13, (beta, betao)
+        w = max(np.linalg.norm(H[:j + 2, j] - Ho[:j + 2, j]) / np.linalg.norm(Ho[:j + 2, j]) for j in range(K))
+        assert w < 1e-10, (mode, w)
+        worst = max(worst, w)
+        if rep == 0:
+            H_by_transport[mode] = H.copy()
+        else:
+            assert np.array_equal(H, H_by_transport[mode])  # deterministic
+    q, r0 = ar.q_slice(K)
+    seg = Qo[r0:min(r0 + ar.n_p, n), K]
+    assert np.linalg.norm(q[:seg.shape[0]] - seg) < 1e-9 and np.all(q[seg.shape[0]:] == 0)
+    # all ranks hold bit-identical H (replicated host projected problem relies on it)
+    t = torch.from_numpy(H.copy()).cuda()
+    t0 = t.clone()
+    dist.broadcast(t0, src=0)
+    assert torch.equal(t, t0), mode
+    ar.close()
+dH = np.linalg.norm(H_by_transport[1] - H_by_transport[2]) / np.linalg.norm(H_by_transport[1])
+assert dH < 1e-12, dH
+assert np.array_equal(H_by_transport[0], H_by_transport[2])
+print("TRANSPORT", rank, comm.transport, "|H_nccl - H_peer|/|H| =", dH, flush=True)
 
 # sharded device generators == host shards
 angles = np.arange(nv) * (360.0 / nv)
