@@ -42,6 +42,7 @@ PROTOTYPES = {
     "hg_ctx_create": (_i, [_i, _vp, c_void_pp]),
     "hg_ctx_destroy": (_i, [_vp]),
     "hg_ctx_sync": (_i, [_vp]),
+    "hg_ctx_trim": (_i, [_vp]),
     "hg_ctx_launch_count": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "hg_ctx_timing_enable": (_i, [_vp, _i]),
     "hg_ctx_timing_get": (_i, [_vp, _i, c_double_p, C.POINTER(C.c_uint64), c_double_p]),
@@ -52,7 +53,7 @@ PROTOTYPES = {
     "hg_matrix_from_csc": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _vp, c_void_pp]),
     "hg_matrix_from_dense": (_i, [_vp, _i64, _i64, _vp, _i64, c_void_pp]),
     "hg_matrix_transpose": (_i, [_vp, _vp, c_void_pp]),
-    "hg_matrix_permute": (_i, [_vp, _vp, _vp, _vp, c_void_pp]),
+    "hg_matrix_permute": (_i, [_vp, _vp, _vp, _vp, _i, c_void_pp]),
     "hg_matrix_spmv_form": (_i, [_vp, _vp, c_int_p]),
     "hg_matrix_info": (_i, [_vp, c_int64_p, c_int64_p, c_int64_p]),
     "hg_matrix_download_csr": (_i, [_vp, _vp, _vp, _vp, _vp]),

@@ -77,6 +77,10 @@ class Context:
     def sync(self):
         check(self._lib.hg_ctx_sync(self._h))
 
+    def trim(self):
+        """Return the cached device buffers (``hg_ctx_trim``) to the driver."""
+        check(self._lib.hg_ctx_trim(self._h))
+
     @property
     def launch_count(self) -> int:
         out = C.c_uint64()
@@ -191,8 +195,9 @@ class DeviceMatrix:
         check(self.ctx._lib.hg_matrix_transpose(self.ctx._h, self._h, C.byref(h)))
         return DeviceMatrix(h, self.ctx)
 
-    def permute(self, rowperm=None, colperm=None) -> "DeviceMatrix":
-        """``M(rowperm, colperm)`` (gather convention, 0-based) as a new device matrix."""
+    def permute(self, rowperm=None, colperm=None, sort=True) -> "DeviceMatrix":
+        """``M(rowperm, colperm)`` (gather convention, 0-based) as a new device matrix.  ``sort=False``
+        keeps the entries of a row in their order (new column labels only; enough for products)."""
         rp = None if rowperm is None else np.ascontiguousarray(rowperm, dtype=np.int32)
         cp = None if colperm is None else np.ascontiguousarray(colperm, dtype=np.int32)
         if rp is not None and rp.shape[0] != self.shape[0]:
@@ -200,7 +205,8 @@ class DeviceMatrix:
         if cp is not None and cp.shape[0] != self.shape[1]:
             raise ValueError("permute: colperm has the wrong length")
         h = C.c_void_p()
-        check(self.ctx._lib.hg_matrix_permute(self.ctx._h, self._h, _ptr(rp), _ptr(cp), C.byref(h)))
+        check(self.ctx._lib.hg_matrix_permute(self.ctx._h, self._h, _ptr(rp), _ptr(cp), 0 if sort else 1,
+                                              C.byref(h)))
         return DeviceMatrix(h, self.ctx)
 
     @property
@@ -296,7 +302,7 @@ def _rtp(fn_name, A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, 
             # run the n-space of the solve in the caller's cache-friendly order: A(:,q), B(q,:),
             # x_true(q) — an orthogonal similarity of B*A + lambda*I (hgmres.h: hg_matrix_permute)
             nperm = np.ascontiguousarray(nperm, dtype=np.int32)
-            dA, dB = dA.permute(None, nperm), dB.permute(nperm, None)
+            dA, dB = dA.permute(None, nperm, sort=False), dB.permute(nperm, None)
             x_true = np.ascontiguousarray(x_true[nperm])
         x = np.zeros(n)
         err = np.zeros(maxit)

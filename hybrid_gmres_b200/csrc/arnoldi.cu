@@ -43,16 +43,16 @@ struct hg_arnoldi {
 extern "C" int hg_arnoldi_destroy(hg_arnoldi* a) {
     if (!a) return HG_OK;
     cudaStreamSynchronize(a->ctx->stream);
-    cudaFree(a->Q);
-    cudaFree(a->T);
-    if (a->space == HG_SPACE_M) cudaFree(a->d_b);
-    cudaFree(a->w0);
-    cudaFree(a->w1);
-    cudaFree(a->d_H);
-    cudaFree(a->d_hcur);
-    cudaFree(a->d_beta);
-    cudaFree(a->partials);
-    cudaFree(a->stat);
+    hg_dfree(a->Q);
+    hg_dfree(a->T);
+    if (a->space == HG_SPACE_M) hg_dfree(a->d_b);
+    hg_dfree(a->w0);
+    hg_dfree(a->w1);
+    hg_dfree(a->d_H);
+    hg_dfree(a->d_hcur);
+    hg_dfree(a->d_beta);
+    hg_dfree(a->partials);
+    hg_dfree(a->stat);
     if (a->h_H) cudaFreeHost(a->h_H);
     if (a->h_beta) cudaFreeHost(a->h_beta);
     delete a;
@@ -99,7 +99,7 @@ extern "C" int hg_arnoldi_create(hg_ctx* ctx, const hg_matrix* A, const hg_matri
     const size_t nstat = (size_t)std::max(a->nq, a->nt) / 8 + 1024;
     cudaError_t e = cudaSuccess;
     auto alloc = [&](double** p, size_t n) {
-        if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(n, 1) * sizeof(double));
+        if (e == cudaSuccess) e = hg_dmalloc(ctx, p, std::max<size_t>(n, 1) * sizeof(double));
     };
     alloc(&a->Q, (size_t)a->ldq * (kmax + 1));
     alloc(&a->T, a->store_t ? (size_t)a->ldt * (kmax + 1) : (size_t)a->ldt);
@@ -203,13 +203,15 @@ static int arnoldi_step(hg_arnoldi* a, int kk) {
         // v -= Q h1 and h2 = Q' v in one kernel: the second read of the Q tile is an L2 hit
         HG_TRY(hg_k_update_dot(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, a->w0, a->w1, a->partials, &ns));
     } else {
-        HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr,
-                            nullptr, nullptr));
+        // the updates sweep the rows backwards: they start on the part of Q the forward multi-dot
+        // sweep just left in L2, and leave the low rows there for the next forward sweep
+        HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr,
+                                 nullptr, nullptr, nullptr, hg_cgs_alternate()));
         HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->nq, kk, a->w1, a->partials, &ns));
     }
     HG_TRY(hg_k_reduce(ctx, a->partials, ns, kk, Hcol, true, a->d_hcur, false));
-    HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, -1.0, a->w1, qnext, nullptr,
-                        a->stat, &np));
+    HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, -1.0, a->w1, qnext, nullptr,
+                             a->stat, &np, nullptr, hg_cgs_alternate()));
     // H(k+1,k) = norm(v) ; Q(:,k+1) = v / H(k+1,k)       (:24,26)
     HG_TRY(hg_k_reduce(ctx, a->stat, np, 1, Hcol + kk, false, nullptr, true));
     HG_TRY(hg_k_scale_div(ctx, qnext, a->nq, Hcol + kk));

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "hgmres.h"
@@ -68,7 +69,21 @@ struct hg_ctx {
     size_t partials_cap = 0;       // in doubles
     double* d_scalars = nullptr;   // 64 device doubles
     double* h_scalars = nullptr;   // 64 pinned doubles
+    // device-buffer cache (hg_dmalloc / hg_dfree): released blocks >= 1 MB wait here for the next
+    // request of (nearly) the same size, so repeated solver calls neither cudaMalloc nor cudaFree
+    std::multimap<size_t, void*> pool_free;
+    size_t pool_cached = 0;
 };
+
+// Stream-ordered reuse: a cached block is only handed to requests of the context that released it,
+// and every consumer of a context runs on its one stream.
+cudaError_t hg_dmalloc_bytes(hg_ctx* ctx, void** p, size_t bytes);
+template <class T>
+inline cudaError_t hg_dmalloc(hg_ctx* ctx, T** p, size_t bytes) {
+    return hg_dmalloc_bytes(ctx, reinterpret_cast<void**>(p), bytes);
+}
+void hg_dfree(void* p);           // nullptr ok; blocks from hg_dmalloc go back to their context's cache
+void hg_pool_trim(hg_ctx* ctx);   // cudaFree everything cached
 
 struct hg_matrix {
     hg_ctx* ctx = nullptr;
@@ -150,7 +165,8 @@ struct hg_out_list {
 };
 int hg_k_lincomb_push(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* c,
                       double s, const double* z, double* out, const double* ref, double* stat,
-                      int* nparts, const hg_out_list* extra);
+                      int* nparts, const hg_out_list* extra, bool reverse = false);
+bool hg_cgs_alternate();  // option "cgs_alternate" (default off): CGS2 updates sweep the rows backwards
 
 // fused CGS2 middle stage: w1 = w0 - V h ; partials[j*ntiles + tile] = sum_tile V[:,j].*w1
 int hg_update_dot_ntiles(int64_t n);

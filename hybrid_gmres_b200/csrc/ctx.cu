@@ -1,7 +1,94 @@
 // Context, error reporting, launch accounting and per-class event timing.
 #include "common.cuh"
 
+#include <mutex>
+#include <unordered_map>
+
 static thread_local char g_err[1024] = "";
+
+// ---- device-buffer cache ------------------------------------------------------
+namespace {
+struct PoolRec {
+    hg_ctx* ctx;
+    size_t size;
+};
+std::mutex g_pool_mu;
+std::unordered_map<void*, PoolRec> g_pool_live;  // every block handed out by hg_dmalloc_bytes
+constexpr size_t kPoolMinBytes = (size_t)1 << 20;
+
+size_t pool_cap_bytes() {
+    static size_t cap = [] {
+        const char* e = getenv("HG_POOL_GB");
+        const double gb = e ? atof(e) : 64.0;
+        return (size_t)(gb * 1073741824.0);
+    }();
+    return cap;
+}
+}  // namespace
+
+cudaError_t hg_dmalloc_bytes(hg_ctx* ctx, void** p, size_t bytes) {
+    *p = nullptr;
+    const size_t want = (std::max<size_t>(bytes, 1) + 511) / 512 * 512;
+    if (want >= kPoolMinBytes && pool_cap_bytes() > 0) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto it = ctx->pool_free.lower_bound(want);
+        if (it != ctx->pool_free.end() && it->first <= want + want / 8) {
+            *p = it->second;
+            ctx->pool_cached -= it->first;
+            g_pool_live[*p] = PoolRec{ctx, it->first};
+            ctx->pool_free.erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {  // give the cache back to the driver and try once more
+        cudaGetLastError();
+        hg_pool_trim(ctx);
+        e = cudaMalloc(p, want);
+    }
+    if (e == cudaSuccess && want >= kPoolMinBytes) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        g_pool_live[*p] = PoolRec{ctx, want};
+    }
+    return e;
+}
+
+void hg_dfree(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto it = g_pool_live.find(p);
+        if (it != g_pool_live.end()) {
+            const PoolRec rec = it->second;
+            g_pool_live.erase(it);
+            if (rec.ctx && rec.ctx->pool_cached + rec.size <= pool_cap_bytes()) {
+                rec.ctx->pool_free.emplace(rec.size, p);
+                rec.ctx->pool_cached += rec.size;
+                return;
+            }
+        }
+    }
+    cudaFree(p);
+}
+
+void hg_pool_trim(hg_ctx* ctx) {
+    std::vector<void*> blocks;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (auto& kv : ctx->pool_free) blocks.push_back(kv.second);
+        ctx->pool_free.clear();
+        ctx->pool_cached = 0;
+    }
+    if (!blocks.empty()) cudaStreamSynchronize(ctx->stream);
+    for (void* b : blocks) cudaFree(b);
+}
+
+extern "C" int hg_ctx_trim(hg_ctx* ctx) {
+    HG_REQUIRE(ctx, "hg_ctx_trim: ctx is NULL");
+    HG_CUDA(cudaSetDevice(ctx->device));
+    hg_pool_trim(ctx);
+    return HG_OK;
+}
 
 void hg_set_error(const char* fmt, ...) {
     va_list ap;
@@ -63,6 +150,12 @@ extern "C" int hg_ctx_destroy(hg_ctx* ctx) {
         ctx->event_pool.push_back(p.e1);
     }
     for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
+    hg_pool_trim(ctx);
+    {   // blocks still held by live objects outlive the context: they will be cudaFree'd directly
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (auto& kv : g_pool_live)
+            if (kv.second.ctx == ctx) kv.second.ctx = nullptr;
+    }
     if (ctx->d_partials) cudaFree(ctx->d_partials);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);

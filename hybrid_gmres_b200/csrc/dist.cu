@@ -174,10 +174,10 @@ extern "C" int hg_darnoldi_destroy(hg_darnoldi* a) {
     if (!a) return HG_OK;
     cudaStreamSynchronize(a->ctx->stream);
     if (a->peer) hg_peer_release(a->comm, a);
-    else { cudaFree(a->q_full); cudaFree(a->w_part); }
-    cudaFree(a->Q); cudaFree(a->T);
-    cudaFree(a->w0); cudaFree(a->w1); cudaFree(a->d_H); cudaFree(a->d_hcur); cudaFree(a->d_s);
-    cudaFree(a->partials); cudaFree(a->stat);
+    else { hg_dfree(a->q_full); hg_dfree(a->w_part); }
+    hg_dfree(a->Q); hg_dfree(a->T);
+    hg_dfree(a->w0); hg_dfree(a->w1); hg_dfree(a->d_H); hg_dfree(a->d_hcur); hg_dfree(a->d_s);
+    hg_dfree(a->partials); hg_dfree(a->stat);
     if (a->h_H) cudaFreeHost(a->h_H);
     if (a->h_beta) cudaFreeHost(a->h_beta);
     delete a;
@@ -213,7 +213,7 @@ extern "C" int hg_darnoldi_create(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A
     const int nslabs = hg_multidot_nslabs(ctx, std::max(a->n_p, a->m_p));
     cudaError_t e = cudaSuccess;
     auto alloc = [&](double** p, size_t cnt) {
-        if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(cnt, 1) * sizeof(double));
+        if (e == cudaSuccess) e = hg_dmalloc(ctx, p, std::max<size_t>(cnt, 1) * sizeof(double));
         if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, std::max<size_t>(cnt, 1) * sizeof(double), ctx->stream);
     };
     a->row0 = (int64_t)comm->rank * a->n_p;
@@ -331,7 +331,8 @@ static int darnoldi_step(hg_darnoldi* a, int kk) {
         // w0 = sum_p (B^p u_p)[slice] + shift*q[slice], fused with h1 = Q_k' w0
         HG_TRY(hg_k_pull_multidot(c, a->row0, q_slice, a->shift, a->w0, a->Q, a->ldq, a->n_p, kk, a->partials, &ns));
         HG_TRY(hg_k_reduce_allreduce(c, a->partials, ns, kk, a->d_hcur, Hcol, false, false));
-        HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr, nullptr, nullptr));
+        HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr, nullptr, nullptr,
+                                 nullptr, hg_cgs_alternate()));
         HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->n_p, kk, a->w1, a->partials, &ns));
         HG_TRY(hg_k_reduce_allreduce(c, a->partials, ns, kk, a->d_hcur, Hcol, true, false));  // H(1:k,k) = h1 + h2
         // v = w1 - Q h2: rows go to the local basis AND to every rank's replicated vector (all-gather
@@ -339,7 +340,8 @@ static int darnoldi_step(hg_darnoldi* a, int kk) {
         a->qbuf ^= 1;
         hg_out_list push;
         hg_peer_push_list(c, a->qbuf, a->row0, &push);
-        HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w1, qnext, nullptr, a->stat, &np, &push));
+        HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w1, qnext, nullptr, a->stat, &np, &push,
+                                 hg_cgs_alternate()));
         HG_TRY(hg_k_reduce_allreduce(c, a->stat, np, 1, Hcol + kk, nullptr, false, true));     // H(k+1,k) = norm(v)
         HG_TRY(hg_k_scale2(c, hg_peer_qfull(c, a->qbuf), a->n_pad, qnext, a->n_p, Hcol + kk));  // q_{k+1} = v / H(k+1,k)
         HG_CUDA(cudaMemcpyAsync(a->h_H + (size_t)(kk - 1) * a->ldh(), Hcol, (size_t)(kk + 1) * 8,

@@ -215,11 +215,14 @@ __global__ void __launch_bounds__(kBlock)
 lincomb_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
                const double* __restrict__ c, double s, const double* __restrict__ z,
                double* __restrict__ out, const double* __restrict__ ref,
-               double* __restrict__ stat, hg_out_list extra) {
+               double* __restrict__ stat, hg_out_list extra, int reverse) {
     extern __shared__ double sc[];
     for (int j = threadIdx.x; j < k; j += blockDim.x) sc[j] = s * c[j];
     __syncthreads();
-    const int64_t r = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * 2;
+    // reverse: walk the rows from the end, so a kernel that follows a forward sweep over the same
+    // basis (the CGS2 multi-dot) starts on the rows that sweep left in L2
+    const int64_t blk = reverse ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
+    const int64_t r = (blk * kBlock + threadIdx.x) * 2;
     double sq = 0.0;
     if (r + 1 < n) {
         double ax = 0.0, ay = 0.0;
@@ -272,7 +275,7 @@ lincomb_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
     }
     if (stat) {
         const double t = block_sum(sq);
-        if (threadIdx.x == 0) stat[blockIdx.x] = t;
+        if (threadIdx.x == 0) stat[blk] = t;
     }
 }
 
@@ -559,7 +562,7 @@ int hg_k_reduce(hg_ctx* ctx, const double* partials, int np, int k, double* out,
 
 int hg_k_lincomb_push(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* c,
                       double s, const double* z, double* out, const double* ref, double* stat,
-                      int* nparts, const hg_out_list* extra) {
+                      int* nparts, const hg_out_list* extra, bool reverse) {
     const int64_t grid = cdiv(cdiv(n, 2), kBlock);
     if (nparts) *nparts = stat ? (int)grid : 0;
     if (n <= 0) return HG_OK;
@@ -571,10 +574,10 @@ int hg_k_lincomb_push(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k
     hg_launch_scope scope(ctx, HG_K_LINCOMB, bytes);
     const size_t smem = (size_t)(k > 0 ? k : 1) * sizeof(double);
     if (extra && extra->n > 0)
-        lincomb_kernel<true><<<(unsigned)grid, kBlock, smem, ctx->stream>>>(V, ld, n, k, c, s, z, out, ref, stat, *extra);
+        lincomb_kernel<true><<<(unsigned)grid, kBlock, smem, ctx->stream>>>(V, ld, n, k, c, s, z, out, ref, stat, *extra, reverse ? 1 : 0);
     else
         lincomb_kernel<false><<<(unsigned)grid, kBlock, smem, ctx->stream>>>(V, ld, n, k, c, s, z, out, ref, stat,
-                                                                            hg_out_list());
+                                                                            hg_out_list(), reverse ? 1 : 0);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }
@@ -582,7 +585,7 @@ int hg_k_lincomb_push(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k
 int hg_k_lincomb(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* c,
                  double s, const double* z, double* out, const double* ref, double* stat,
                  int* nparts) {
-    return hg_k_lincomb_push(ctx, V, ld, n, k, c, s, z, out, ref, stat, nparts, nullptr);
+    return hg_k_lincomb_push(ctx, V, ld, n, k, c, s, z, out, ref, stat, nparts, nullptr, false);
 }
 
 int hg_update_dot_ntiles(int64_t n) { return (int)cdiv(n, kTileRows); }

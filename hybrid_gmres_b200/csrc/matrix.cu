@@ -192,9 +192,9 @@ int hg_matrix_alloc(hg_ctx* ctx, int64_t rows, int64_t cols, int64_t nnz, hg_mat
     m->rows = rows;
     m->cols = cols;
     m->nnz = nnz;
-    cudaError_t e = cudaMalloc(&m->rowptr, (size_t)(rows + 1) * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&m->colind, (size_t)(nnz + kNnzPad) * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&m->vals, (size_t)(nnz + kNnzPad) * sizeof(double));
+    cudaError_t e = hg_dmalloc(ctx, &m->rowptr, (size_t)(rows + 1) * sizeof(int64_t));
+    if (e == cudaSuccess) e = hg_dmalloc(ctx, &m->colind, (size_t)(nnz + kNnzPad) * sizeof(int32_t));
+    if (e == cudaSuccess) e = hg_dmalloc(ctx, &m->vals, (size_t)(nnz + kNnzPad) * sizeof(double));
     if (e == cudaSuccess) e = cudaMemsetAsync(m->colind + nnz, 0, kNnzPad * sizeof(int32_t), ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->vals + nnz, 0, kNnzPad * sizeof(double), ctx->stream);
     if (e != cudaSuccess) {
@@ -220,13 +220,13 @@ void hg_matrix_pick_tpr(hg_matrix* m) {
 
 extern "C" int hg_matrix_destroy(hg_matrix* m) {
     if (!m) return HG_OK;
-    if (m->rowptr) cudaFree(m->rowptr);
-    if (m->colind) cudaFree(m->colind);
-    if (m->vals) cudaFree(m->vals);
+    hg_dfree(m->rowptr);
+    hg_dfree(m->colind);
+    hg_dfree(m->vals);
     if (m->unit_row) cudaFree(m->unit_row);
-    if (m->sell_ptr) cudaFree(m->sell_ptr);
-    if (m->sell_col) cudaFree(m->sell_col);
-    if (m->sell_val) cudaFree(m->sell_val);
+    hg_dfree(m->sell_ptr);
+    hg_dfree(m->sell_col);
+    hg_dfree(m->sell_val);
     delete m;
     return HG_OK;
 }
@@ -521,7 +521,7 @@ static bool invert_perm(const int32_t* perm, int64_t n, std::vector<int32_t>& in
 }
 
 extern "C" int hg_matrix_permute(hg_ctx* ctx, const hg_matrix* m, const int32_t* rowperm,
-                                 const int32_t* colperm, hg_matrix** out) {
+                                 const int32_t* colperm, int flags, hg_matrix** out) {
     HG_REQUIRE(ctx && m && out, "hg_matrix_permute: NULL argument");
     HG_REQUIRE(m->rows <= 2147483647LL, "hg_matrix_permute: more than 2^31-1 rows is not supported");
     HG_CUDA(cudaSetDevice(ctx->device));
@@ -576,7 +576,8 @@ extern "C" int hg_matrix_permute(hg_ctx* ctx, const hg_matrix* m, const int32_t*
             m->rows, m->rowptr, m->colind, m->vals, d_rp, d_ci, t->rowptr, t->colind, t->vals);
         PM_CUDA(cudaGetLastError());
     }
-    if (st == HG_OK && colperm) st = hg_sort_rows_device(ctx, t);  // relabelled columns: restore canonical order
+    // relabelled columns: restore the canonical order unless the caller only runs products with it
+    if (st == HG_OK && colperm && !(flags & HG_PERMUTE_KEEP_ENTRY_ORDER)) st = hg_sort_rows_device(ctx, t);
     if (st == HG_OK) PM_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef PM_CUDA
     if (d_rp) cudaFree(d_rp);

@@ -47,38 +47,47 @@ __global__ void slice_width_kernel(int64_t rows, const int64_t* __restrict__ row
     if ((threadIdx.x & 31) == 0 && (row >> 5) < ((rows + 31) >> 5)) widths[row >> 5] = len;
 }
 
-// one warp per slice: a row's entries are read coalesced (32 consecutive entries per trip)
-// and scattered to their strided slots; padding slots repeat the row's last column with a
-// zero value so padded gathers stay inside the row's own footprint
-__global__ void __launch_bounds__(kBlock)
+// one warp per slice, 32 x 32 tiles through shared memory: a row's entries are read coalesced
+// (32 consecutive entries per trip), the slice columns are written coalesced (32 consecutive rows
+// per trip); padding slots repeat the row's last column with a zero value so padded gathers stay
+// inside the row's own footprint
+constexpr int kFillBlock = 96;  // 3 warps: 3 x 32 x 33 x 12 B = 38 KB of static shared memory
+
+__global__ void __launch_bounds__(kFillBlock)
 sell_fill_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ rowptr,
                  const int32_t* __restrict__ colind, const double* __restrict__ vals,
                  const int64_t* __restrict__ sptr, int32_t* __restrict__ scol,
                  double* __restrict__ sval) {
+    __shared__ int t_col[kFillBlock / 32][32][33];
+    __shared__ double t_val[kFillBlock / 32][32][33];
     const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (slice >= nslices) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (slice >= nslices) return;  // whole warps leave together; no block-wide barrier below
     const int64_t base = sptr[slice];
     const int width = (int)((sptr[slice + 1] - base) >> 5);
-    for (int r = 0; r < 32; ++r) {
-        const int64_t row = slice * 32 + r;
-        int64_t s = 0, e = 0;
-        if (row < rows) {
-            s = rowptr[row];
-            e = rowptr[row + 1];
+    // lane r keeps the extent of row r of the slice
+    const int64_t my_row = slice * 32 + lane;
+    const int64_t my_s = my_row < rows ? rowptr[my_row] : 0;
+    const int my_len = my_row < rows ? (int)(rowptr[my_row + 1] - my_s) : 0;
+    const int my_pad = my_len > 0 ? colind[my_s + my_len - 1] : 0;
+    for (int j0 = 0; j0 < width; j0 += 32) {
+        for (int r = 0; r < 32; ++r) {
+            const int64_t s = __shfl_sync(0xffffffffu, my_s, r);
+            const int len = __shfl_sync(0xffffffffu, my_len, r);
+            const int pad = __shfl_sync(0xffffffffu, my_pad, r);
+            const int j = j0 + lane;
+            const bool in = j < len;
+            t_col[w][r][lane] = in ? colind[s + j] : pad;
+            t_val[w][r][lane] = in ? vals[s + j] : 0.0;
         }
-        const int len = (int)(e - s);
-        const int padcol = len > 0 ? colind[e - 1] : 0;
-        for (int j = lane; j < width; j += 32) {
-            const int64_t dst = base + (int64_t)j * 32 + r;
-            if (j < len) {
-                scol[dst] = colind[s + j];
-                sval[dst] = vals[s + j];
-            } else {
-                scol[dst] = padcol;
-                sval[dst] = 0.0;
-            }
+        __syncwarp();
+        const int jn = min(32, width - j0);
+        for (int j = 0; j < jn; ++j) {
+            const int64_t dst = base + (int64_t)(j0 + j) * 32 + lane;
+            scol[dst] = t_col[w][lane][j];
+            sval[dst] = t_val[w][lane][j];
         }
+        __syncwarp();
     }
 }
 
@@ -204,23 +213,23 @@ bool hg_sell_ready(hg_ctx* ctx, const hg_matrix* cm) {
     }
     ptr[(size_t)nslices] = acc;
     if ((double)acc > 1.03 * (double)m->nnz) return false;  // ragged rows: padding would cost > 3 % of the stream
-    cudaError_t a = cudaMalloc(&m->sell_ptr, (size_t)(nslices + 1) * 8);
-    if (a == cudaSuccess) a = cudaMalloc(&m->sell_col, (size_t)(acc + kNnzPad) * 4);
-    if (a == cudaSuccess) a = cudaMalloc(&m->sell_val, (size_t)(acc + kNnzPad) * 8);
+    cudaError_t a = hg_dmalloc(ctx, &m->sell_ptr, (size_t)(nslices + 1) * 8);
+    if (a == cudaSuccess) a = hg_dmalloc(ctx, &m->sell_col, (size_t)(acc + kNnzPad) * 4);
+    if (a == cudaSuccess) a = hg_dmalloc(ctx, &m->sell_val, (size_t)(acc + kNnzPad) * 8);
     if (a == cudaSuccess)
         a = cudaMemcpyAsync(m->sell_ptr, ptr.data(), (size_t)(nslices + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
     if (a == cudaSuccess) {
         hg_launch_scope scope(ctx, HG_K_SETUP, 24.0 * (double)m->nnz);
-        sell_fill_kernel<<<(unsigned)cdiv(nslices * 32, kBlock), kBlock, 0, ctx->stream>>>(
+        sell_fill_kernel<<<(unsigned)cdiv(nslices * 32, kFillBlock), kFillBlock, 0, ctx->stream>>>(
             m->rows, nslices, m->rowptr, m->colind, m->vals, m->sell_ptr, m->sell_col, m->sell_val);
         a = cudaGetLastError();
     }
     if (a == cudaSuccess) a = cudaStreamSynchronize(ctx->stream);  // `ptr` is pageable host memory
     if (a != cudaSuccess) {
         cudaGetLastError();
-        if (m->sell_ptr) cudaFree(m->sell_ptr);
-        if (m->sell_col) cudaFree(m->sell_col);
-        if (m->sell_val) cudaFree(m->sell_val);
+        hg_dfree(m->sell_ptr);
+        hg_dfree(m->sell_col);
+        hg_dfree(m->sell_val);
         m->sell_ptr = nullptr;
         m->sell_col = nullptr;
         m->sell_val = nullptr;

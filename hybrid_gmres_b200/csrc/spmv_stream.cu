@@ -253,6 +253,15 @@ static int spmv_mode() {
 
 int hg_spmv_mode() { return spmv_mode(); }
 
+static int g_cgs_alternate = -1;
+bool hg_cgs_alternate() {
+    if (g_cgs_alternate < 0) {
+        const char* e = getenv("HG_CGS_ALTERNATE");
+        g_cgs_alternate = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured neutral on B200 (647.5 vs 649.1 it/s)
+    }
+    return g_cgs_alternate != 0;
+}
+
 static int g_cgs_fused = -1;
 bool hg_cgs_fused() {
     if (g_cgs_fused < 0) {
@@ -273,6 +282,10 @@ extern "C" int hg_set_option(const char* name, int value) {
     if (strcmp(name, "spmv_mode") == 0) {
         HG_REQUIRE(value >= 0 && value <= 2, "hg_set_option: spmv_mode must be 0, 1 or 2");
         g_spmv_mode = value;
+        return HG_OK;
+    }
+    if (strcmp(name, "cgs_alternate") == 0) {
+        g_cgs_alternate = value ? 1 : 0;
         return HG_OK;
     }
     if (strcmp(name, "dist_transport") == 0) {

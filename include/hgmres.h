@@ -67,6 +67,9 @@ int hg_version(void);
  * "cgs_fused": 0 (default; env HG_CGS_FUSED=1 enables) fuses the first CGS2 update with the
  * second-pass dot products (basis crosses HBM three times per step instead of four; measured
  * slower than the two separate streaming kernels on B200, see profiles/r01_cgs_fusion.md).
+ * "cgs_alternate": 0 (default; env HG_CGS_ALTERNATE=1 enables) the CGS2 update kernels walk the rows
+ * from the end, so each sweep over the basis starts on the ~100 MB the previous one left in L2
+ * (measured neutral on B200: 647.5 vs 649.1 it/s).
  * "dist_transport": see hg_comm_transport. */
 int hg_set_option(const char* name, int value);
 
@@ -76,6 +79,10 @@ int hg_set_option(const char* name, int value);
 int hg_ctx_create(int device, void* stream, hg_ctx** out);
 int hg_ctx_destroy(hg_ctx* ctx);
 int hg_ctx_sync(hg_ctx* ctx);
+/* Matrices and Krylov workspaces released by this context are cached (up to HG_POOL_GB, default 64)
+ * for the next request of the same size, so repeated solver calls do not cudaMalloc / cudaFree;
+ * hg_ctx_trim returns the cache to the driver. */
+int hg_ctx_trim(hg_ctx* ctx);
 /* number of hand-written kernels launched by this context so far */
 int hg_ctx_launch_count(hg_ctx* ctx, uint64_t* out);
 
@@ -117,12 +124,15 @@ int hg_matrix_from_dense(hg_ctx* ctx, int64_t rows, int64_t cols, const double* 
 int hg_matrix_transpose(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out);
 /* out = M(rowperm, colperm) in MATLAB's gather convention: out row i is M row rowperm[i], out
  * column j is M column colperm[j] (0-based host arrays; either may be NULL = identity).  Columns are
- * re-sorted within each row.  Used to run the n-space of a solve in a cache-friendly pixel order
+ * re-sorted within each row unless flags has HG_PERMUTE_KEEP_ENTRY_ORDER (entries then keep their
+ * order within the row and only get new column labels — enough for products, and what a projector
+ * wants: the entries of a ray stay in traversal order).  Used to run the n-space of a solve in a cache-friendly pixel order
  * (A(:,q), B(q,:), x_true(q); the iterate comes back as x(q) = x_q) — an orthogonal similarity of the
  * operator B*A + lambda*I of hybrid_ab_gmres_rtp.m:6, so H, beta and the histories are unchanged up
  * to summation order. */
+#define HG_PERMUTE_KEEP_ENTRY_ORDER 1
 int hg_matrix_permute(hg_ctx* ctx, const hg_matrix* m, const int32_t* rowperm, const int32_t* colperm,
-                      hg_matrix** out);
+                      int flags, hg_matrix** out);
 /* Which SpMV kernel this matrix runs with: 0 CSR row-per-thread-group, 1 row-per-lane over 32-row
  * slices (built lazily when rows of a slice have near-equal length), 2 TMA-staged streaming. */
 int hg_matrix_spmv_form(hg_ctx* ctx, const hg_matrix* m, int* form);

@@ -252,3 +252,38 @@ def test_permute_bit_exact(hg, ctx, ct48_unmatched):
         assert np.array_equal(data, ref.data)
     with pytest.raises(hg._lib.HgError):
         hg.DeviceMatrix.from_any(A, ctx).permute(None, np.zeros(A.shape[1], dtype=np.int32))
+
+
+def test_permute_keep_entry_order(hg, ctx, ct48_unmatched):
+    """HG_PERMUTE_KEEP_ENTRY_ORDER: entries keep their order within the row (new column labels
+    only) — what the solvers' nperm path uses; products are those of A(:,q)."""
+    from hybrid_gmres_b200.ct import tile_permutation
+    A = ct48_unmatched[0]
+    q = tile_permutation(48, 4)
+    d = hg.DeviceMatrix.from_any(A, ctx).permute(None, q, sort=False)
+    indptr, indices, data = d.download()
+    inv = np.empty_like(q)
+    inv[q] = np.arange(q.shape[0], dtype=q.dtype)
+    As = A.tocsr()
+    assert np.array_equal(indptr, As.indptr)
+    assert np.array_equal(indices, inv[As.indices]) and np.array_equal(data, As.data)
+    x = np.random.default_rng(13).standard_normal(A.shape[1])
+    assert _rel(d.matvec(x[q]), A @ x) < RTOL
+
+
+def test_device_buffer_cache_reuses_blocks(hg, ctx):
+    """Released matrices >= 1 MB are handed to the next upload of the same size (hg_dmalloc);
+    results do not depend on it and hg_ctx_trim empties the cache."""
+    rng = np.random.default_rng(14)
+    M = sp.random(3000, 3000, density=0.05, format="csr", random_state=rng, dtype=np.float64)
+    x = rng.standard_normal(3000)
+    ys = []
+    for _ in range(3):
+        d = hg.DeviceMatrix.from_any(M, ctx)
+        ys.append(d.matvec(x))
+        d.close()
+    assert np.array_equal(ys[0], ys[1]) and np.array_equal(ys[0], ys[2])
+    assert _rel(ys[0], M @ x) < RTOL
+    ctx.trim()
+    d = hg.DeviceMatrix.from_any(M, ctx)
+    assert np.array_equal(d.matvec(x), ys[0])
