@@ -212,7 +212,7 @@ bool hg_sell_ready(hg_ctx* ctx, const hg_matrix* cm) {
         acc += (int64_t)w[(size_t)s] * 32;
     }
     ptr[(size_t)nslices] = acc;
-    if ((double)acc > 1.03 * (double)m->nnz) return false;  // ragged rows: padding would cost > 3 % of the stream
+    if ((double)acc > 1.08 * (double)m->nnz) return false;  // ragged rows: padding would cost > 8 % of the stream
     cudaError_t a = hg_dmalloc(ctx, &m->sell_ptr, (size_t)(nslices + 1) * 8);
     if (a == cudaSuccess) a = hg_dmalloc(ctx, &m->sell_col, (size_t)(acc + kNnzPad) * 4);
     if (a == cudaSuccess) a = hg_dmalloc(ctx, &m->sell_val, (size_t)(acc + kNnzPad) * 8);
