@@ -194,7 +194,8 @@ def main():
     cores = len(os.sched_getaffinity(0))
     config = {"workload": args.workload, "m": m, "n": n, "nnz_A": nnzA, "nnz_B": nnzB, "maxit": maxit,
               "lambda": LAMBDA, "orth": "cgs2", "B": "pixel-driven (unmatched)",
-              "nspace_order": args.nspace_order, "spmv_form": {"A": dA.spmv_form, "B": dB.spmv_form},
+              "nspace_order": args.nspace_order,
+              "spmv_form": {"A": f"{dA.spmv_form}/idx{dA.spmv_index_bits}", "B": f"{dB.spmv_form}/idx{dB.spmv_index_bits}"},
               "parallelism": (f"A row-sharded / B column-sharded x{world}, NCCL reduce-scatter + all-gather + "
                               "3 all-reduce per step") if world > 1 else "single",
               "l2": "inputs (A+B = %.1f GB) exceed the 126 MB L2; no flush needed" % ((nnzA + nnzB) * 12 / 1e9)}
@@ -309,8 +310,9 @@ def main():
         except Exception:
             pass
     forms = config.get("spmv_form", {})
-    kname = " + ".join(f"{'spmv_sell32_kernel<4>' if forms.get(w) == 'sell32' else 'spmv_csr_kernel<32>'} ({w})"
-                       for w in ("A", "B"))
+    knames = {"csr/idx32": "spmv_csr_kernel<32>", "csr/idx16": "spmv_csr16_kernel", "sell32/idx32": "spmv_sell32_kernel<4>",
+              "sell32/idx16": "spmv_sell16_kernel<4>", "stream/idx32": "spmv_stream_kernel"}
+    kname = " + ".join(f"{knames.get(forms.get(w), 'spmv')} ({w})" for w in ("A", "B"))
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src,

@@ -214,7 +214,14 @@ class DeviceMatrix:
         """Which SpMV kernel this matrix runs with ("csr", "sell32" or "stream")."""
         f = C.c_int()
         check(self.ctx._lib.hg_matrix_spmv_form(self.ctx._h, self._h, C.byref(f)))
-        return ("csr", "sell32", "stream")[f.value]
+        return ("csr", "sell32", "stream")[f.value & 15]
+
+    @property
+    def spmv_index_bits(self) -> int:
+        """16 when the SpMV streams 16-bit column offsets from per-group bases, else 32."""
+        f = C.c_int()
+        check(self.ctx._lib.hg_matrix_spmv_form(self.ctx._h, self._h, C.byref(f)))
+        return 16 if f.value & 16 else 32
 
     def download(self):
         """Return ``(indptr[int64], indices[int32], data[float64])``."""
@@ -294,7 +301,10 @@ def _extras(maxit, n, want, want_x=True, aux=False):
 def _rtp(fn_name, A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm=None):
     ctx = _ctx_of(ctx, A, B)
     maxit = int(maxit)
+    t_up = time.perf_counter()
     with _Uploaded(ctx, A, B) as (dA, dB):
+        if _TRACE:
+            print(f"[hg trace] {fn_name}: upload {1e3 * (time.perf_counter() - t_up):.1f} ms", file=sys.stderr)
         m, n = dA.shape
         b = _vec(b, m, "b")
         x_true = _vec(x_true, n, "x_true")
@@ -302,8 +312,12 @@ def _rtp(fn_name, A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, 
             # run the n-space of the solve in the caller's cache-friendly order: A(:,q), B(q,:),
             # x_true(q) — an orthogonal similarity of B*A + lambda*I (hgmres.h: hg_matrix_permute)
             nperm = np.ascontiguousarray(nperm, dtype=np.int32)
+            t_pm = time.perf_counter()
             dA, dB = dA.permute(None, nperm, sort=False), dB.permute(nperm, None)
             x_true = np.ascontiguousarray(x_true[nperm])
+            if _TRACE:
+                print(f"[hg trace] {fn_name}: n-space re-ordering {1e3 * (time.perf_counter() - t_pm):.1f} ms",
+                      file=sys.stderr)
         x = np.zeros(n)
         err = np.zeros(maxit)
         res = np.zeros(maxit)

@@ -53,8 +53,8 @@ extern "C" int hg_arnoldi_destroy(hg_arnoldi* a) {
     hg_dfree(a->d_beta);
     hg_dfree(a->partials);
     hg_dfree(a->stat);
-    if (a->h_H) cudaFreeHost(a->h_H);
-    if (a->h_beta) cudaFreeHost(a->h_beta);
+    hg_hfree(a->h_H);
+    hg_hfree(a->h_beta);
     delete a;
     return HG_OK;
 }
@@ -112,8 +112,8 @@ extern "C" int hg_arnoldi_create(hg_ctx* ctx, const hg_matrix* A, const hg_matri
     alloc(&a->d_beta, 8);
     alloc(&a->partials, npart);
     alloc(&a->stat, nstat);
-    if (e == cudaSuccess) e = cudaMallocHost(&a->h_H, (size_t)a->ldh() * kmax * sizeof(double));
-    if (e == cudaSuccess) e = cudaMallocHost(&a->h_beta, 8 * sizeof(double));
+    if (e == cudaSuccess) e = hg_hmalloc(ctx, &a->h_H, (size_t)a->ldh() * kmax * sizeof(double));
+    if (e == cudaSuccess) e = hg_hmalloc(ctx, &a->h_beta, 8 * sizeof(double));
     if (e != cudaSuccess) {
         hg_set_error("hg_arnoldi_create: allocation failed (basis %lld x %d): %s",
                      (long long)a->nq, kmax + 1, cudaGetErrorString(e));
@@ -275,11 +275,9 @@ namespace {
 
 struct DBuf {
     double* p = nullptr;
-    ~DBuf() {
-        if (p) cudaFree(p);
-    }
+    ~DBuf() { hg_dfree(p); }
     int alloc(size_t n) {
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double));
+        cudaError_t e = hg_dmalloc_cur((void**)&p, std::max<size_t>(n, 1) * sizeof(double));
         if (e != cudaSuccess) {
             hg_set_error("device allocation of %zu doubles failed: %s", n, cudaGetErrorString(e));
             return HG_ERR_NOMEM;
@@ -290,11 +288,9 @@ struct DBuf {
 
 struct PinBuf {
     double* p = nullptr;
-    ~PinBuf() {
-        if (p) cudaFreeHost(p);
-    }
+    ~PinBuf() { hg_hfree(p); }
     int alloc(size_t n) {
-        cudaError_t e = cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(double));
+        cudaError_t e = hg_hmalloc_cur((void**)&p, std::max<size_t>(n, 1) * sizeof(double));
         if (e != cudaSuccess) {
             hg_set_error("pinned allocation of %zu doubles failed: %s", n, cudaGetErrorString(e));
             return HG_ERR_NOMEM;
@@ -331,6 +327,8 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     ArnoldiHolder holder;
     HG_TRY(hg_arnoldi_create(ctx, A, B, HG_SPACE_N, maxit, &holder.a));
     hg_arnoldi* a = holder.a;
+    const double t_created = now();
+    hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
     DBuf d_x, d_xt, d_y, d_g, stat_e, stat_r;
     PinBuf h_y, h_g, h_s;
     HG_TRY(d_x.alloc((size_t)n));
@@ -342,6 +340,7 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     HG_TRY(h_y.alloc((size_t)maxit + 1));
     HG_TRY(h_g.alloc((size_t)maxit + 2));
     HG_TRY(h_s.alloc(8));
+    const double t_bufs = now();
     HG_CUDA(cudaMemsetAsync(d_x.p, 0, (size_t)n * 8, ctx->stream));
     HG_CUDA(cudaMemcpyAsync(d_xt.p, x_true, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     HG_TRY(hg_arnoldi_set_rhs(a, b));
@@ -349,11 +348,15 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     HG_TRY(hg_norm2_sync(ctx, a->d_b, m, &nb2));
     HG_TRY(hg_norm2_sync(ctx, d_xt.p, n, &nx2));
     const double norm_b = std::sqrt(nb2), norm_xt = std::sqrt(nx2);
+    const double t_norms = now();
     HG_TRY(hg_arnoldi_reset(a, lambda));
     HG_CUDA(cudaStreamSynchronize(ctx->stream));
     const double beta = a->h_beta[0];
 
     const double t_setup = now();
+    if (trace)
+        fprintf(stderr, "[hg trace] rtp setup: basis alloc %.1f ms, buffers %.1f ms, rhs + norms %.1f ms, r0 (incl. lazy SpMV forms) %.1f ms\n",
+                t_created - t_begin, t_bufs - t_created, t_norms - t_bufs, t_setup - t_norms);
     for (int i = 0; i < maxit; ++i) error_norm[i] = residual_norm[i] = 0.0;
     hgd::HessenbergLS ls;
     hgd::BorderedCholesky chol;
@@ -627,6 +630,7 @@ extern "C" int hg_gmres_ptr(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* 
     ArnoldiHolder holder;
     HG_TRY(hg_arnoldi_create(ctx, A, B, kind == 0 ? HG_SPACE_M : HG_SPACE_N, maxit, &holder.a));
     hg_arnoldi* a = holder.a;
+    hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
     DBuf d_x, d_xt, d_y, d_z, stat_e, stat_r;
     PinBuf h_y, h_s;
     HG_TRY(d_x.alloc((size_t)n));

@@ -7,11 +7,9 @@
 namespace {
 struct DBuf {
     double* p = nullptr;
-    ~DBuf() {
-        if (p) cudaFree(p);
-    }
+    ~DBuf() { hg_dfree(p); }
     int alloc(size_t n) {
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double));
+        cudaError_t e = hg_dmalloc_cur((void**)&p, std::max<size_t>(n, 1) * sizeof(double));
         if (e != cudaSuccess) {
             hg_set_error("device allocation of %zu doubles failed: %s", n, cudaGetErrorString(e));
             return HG_ERR_NOMEM;
@@ -25,6 +23,7 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 extern "C" int hg_spmv(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y) {
     HG_REQUIRE(ctx && m && x && y, "hg_spmv: NULL argument");
     HG_CUDA(cudaSetDevice(ctx->device));
+    hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
     DBuf dx, dy;
     HG_TRY(dx.alloc((size_t)m->cols));
     HG_TRY(dy.alloc((size_t)m->rows));
@@ -51,6 +50,7 @@ extern "C" int hg_multidot(hg_ctx* ctx, int64_t n, int k, const double* V, int64
     HG_REQUIRE(ctx && V && w && h, "hg_multidot: NULL argument");
     HG_REQUIRE(k >= 0 && n >= 0 && ld >= n, "hg_multidot: bad shape");
     HG_CUDA(cudaSetDevice(ctx->device));
+    hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
     DBuf dV, dw, dh, dp;
     int64_t ldd = 0;
     HG_TRY(upload_basis(ctx, n, k, V, ld, dV, &ldd));
@@ -72,6 +72,7 @@ extern "C" int hg_lincomb(hg_ctx* ctx, int64_t n, int k, const double* V, int64_
     HG_REQUIRE(ctx && V && c && out, "hg_lincomb: NULL argument");
     HG_REQUIRE(k >= 0 && n >= 0 && ld >= n, "hg_lincomb: bad shape");
     HG_CUDA(cudaSetDevice(ctx->device));
+    hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
     DBuf dV, dc, dz, dout, dstat;
     int64_t ldd = 0;
     HG_TRY(upload_basis(ctx, n, k, V, ld, dV, &ldd));

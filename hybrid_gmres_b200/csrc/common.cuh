@@ -73,6 +73,7 @@ struct hg_ctx {
     // request of (nearly) the same size, so repeated solver calls neither cudaMalloc nor cudaFree
     std::multimap<size_t, void*> pool_free;
     size_t pool_cached = 0;
+    std::multimap<size_t, void*> hpool_free;  // pinned host blocks (hg_hmalloc / hg_hfree)
 };
 
 // Stream-ordered reuse: a cached block is only handed to requests of the context that released it,
@@ -83,6 +84,22 @@ inline cudaError_t hg_dmalloc(hg_ctx* ctx, T** p, size_t bytes) {
     return hg_dmalloc_bytes(ctx, reinterpret_cast<void**>(p), bytes);
 }
 void hg_dfree(void* p);           // nullptr ok; blocks from hg_dmalloc go back to their context's cache
+// pinned host memory with the same caching (a solver call in steady state makes no CUDA allocation call:
+// cudaFree / cudaFreeHost were measured to stall for 100-400 ms now and then on a box with tens of GB mapped)
+cudaError_t hg_hmalloc_bytes(hg_ctx* ctx, void** p, size_t bytes);
+template <class T>
+inline cudaError_t hg_hmalloc(hg_ctx* ctx, T** p, size_t bytes) {
+    return hg_hmalloc_bytes(ctx, reinterpret_cast<void**>(p), bytes);
+}
+void hg_hfree(void* p);
+// the context whose cache serves the RAII buffers (DBuf / PinBuf) of the solver running on this thread
+struct hg_alloc_scope {
+    hg_ctx* prev;
+    explicit hg_alloc_scope(hg_ctx* c);
+    ~hg_alloc_scope();
+};
+cudaError_t hg_dmalloc_cur(void** p, size_t bytes);  // current context's cache, else plain cudaMalloc
+cudaError_t hg_hmalloc_cur(void** p, size_t bytes);  // current context's cache, else plain cudaMallocHost
 void hg_pool_trim(hg_ctx* ctx);   // cudaFree everything cached
 
 struct hg_matrix {
@@ -99,8 +116,16 @@ struct hg_matrix {
     int sell_state = 0;           // 0 not examined, 1 built, -1 not eligible
     int64_t sell_slices = 0, sell_entries = 0;
     int64_t* sell_ptr = nullptr;  // device, sell_slices+1 entry offsets (multiples of 32)
-    int32_t* sell_col = nullptr;  // device, sell_entries, slice-column-major
+    int32_t* sell_col = nullptr;  // device, sell_entries, slice-column-major (freed when sell_col16 exists)
     double* sell_val = nullptr;
+    // 16-bit column offsets (spmv_idx16.cu): col = base[group] + col16[entry]
+    uint16_t* sell_col16 = nullptr;  // sell_entries; group = 128 consecutive entries (4 columns of a slice)
+    int32_t* sell_base = nullptr;    // sell_entries / 128
+    int csr16_state = 0;             // 0 not examined, 1 built, -1 not eligible
+    uint16_t* csr_col16 = nullptr;   // nnz, same indexing as colind; group = 32 consecutive entries of a row
+    int32_t* csr_base = nullptr;     // csr_groups
+    int64_t* csr_gptr = nullptr;     // rows+1: first group of each row
+    int64_t csr_groups = 0;
 };
 
 // colind / vals are allocated with this many zero entries of tail padding so the
@@ -207,6 +232,17 @@ int hg_spmv_mode();
 bool hg_sell_ready(hg_ctx* ctx, const hg_matrix* m);
 int hg_k_spmv_sell(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
                    const hg_spmv_epilogue& ep, double bytes, int* nparts);
+
+// 16-bit column offsets (spmv_idx16.cu)
+bool hg_idx16_enabled();      // sliced form streams 16-bit column offsets (default)
+bool hg_idx16_csr_enabled();  // row-per-warp CSR kernel too (opt-in: option spmv_idx16 = 2)
+void hg_sell_compress(hg_ctx* ctx, hg_matrix* m);          // after the sliced copy is built
+bool hg_csr16_ready(hg_ctx* ctx, const hg_matrix* m);      // lazily builds the CSR companion arrays
+int hg_k_spmv_sell16(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
+                     const hg_spmv_epilogue& ep, double bytes, int* nparts);
+int hg_k_spmv_csr16(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
+                    const hg_spmv_epilogue& ep, double bytes, int* nparts);
+void hg_idx16_free(hg_matrix* m);
 
 // transposition (matrix.cu)
 int hg_transpose_device(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out);

@@ -1,6 +1,7 @@
 // Context, error reporting, launch accounting and per-class event timing.
 #include "common.cuh"
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -14,7 +15,8 @@ struct PoolRec {
 };
 std::mutex g_pool_mu;
 std::unordered_map<void*, PoolRec> g_pool_live;  // every block handed out by hg_dmalloc_bytes
-constexpr size_t kPoolMinBytes = (size_t)1 << 20;
+constexpr size_t kPoolMinBytes = 0;  // every size is cached (rounded up to 512 B)
+std::unordered_map<void*, PoolRec> g_hpool_live;  // pinned host blocks handed out by hg_hmalloc_bytes
 
 size_t pool_cap_bytes() {
     static size_t cap = [] {
@@ -71,16 +73,67 @@ void hg_dfree(void* p) {
     cudaFree(p);
 }
 
+cudaError_t hg_hmalloc_bytes(hg_ctx* ctx, void** p, size_t bytes) {
+    *p = nullptr;
+    const size_t want = (std::max<size_t>(bytes, 1) + 511) / 512 * 512;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto it = ctx->hpool_free.lower_bound(want);
+        if (it != ctx->hpool_free.end() && it->first <= 2 * want) {
+            *p = it->second;
+            g_hpool_live[*p] = PoolRec{ctx, it->first};
+            ctx->hpool_free.erase(it);
+            return cudaSuccess;
+        }
+    }
+    const cudaError_t e = cudaMallocHost(p, want);
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        g_hpool_live[*p] = PoolRec{ctx, want};
+    }
+    return e;
+}
+
+void hg_hfree(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto it = g_hpool_live.find(p);
+        if (it != g_hpool_live.end()) {
+            const PoolRec rec = it->second;
+            g_hpool_live.erase(it);
+            if (rec.ctx) {
+                rec.ctx->hpool_free.emplace(rec.size, p);
+                return;
+            }
+        }
+    }
+    cudaFreeHost(p);
+}
+
+static thread_local hg_ctx* g_alloc_ctx = nullptr;
+hg_alloc_scope::hg_alloc_scope(hg_ctx* c) : prev(g_alloc_ctx) { g_alloc_ctx = c; }
+hg_alloc_scope::~hg_alloc_scope() { g_alloc_ctx = prev; }
+cudaError_t hg_dmalloc_cur(void** p, size_t bytes) {
+    return g_alloc_ctx ? hg_dmalloc_bytes(g_alloc_ctx, p, bytes) : cudaMalloc(p, std::max<size_t>(bytes, 1));
+}
+cudaError_t hg_hmalloc_cur(void** p, size_t bytes) {
+    return g_alloc_ctx ? hg_hmalloc_bytes(g_alloc_ctx, p, bytes) : cudaMallocHost(p, std::max<size_t>(bytes, 1));
+}
+
 void hg_pool_trim(hg_ctx* ctx) {
-    std::vector<void*> blocks;
+    std::vector<void*> blocks, hblocks;
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
         for (auto& kv : ctx->pool_free) blocks.push_back(kv.second);
         ctx->pool_free.clear();
         ctx->pool_cached = 0;
+        for (auto& kv : ctx->hpool_free) hblocks.push_back(kv.second);
+        ctx->hpool_free.clear();
     }
-    if (!blocks.empty()) cudaStreamSynchronize(ctx->stream);
+    if (!blocks.empty() || !hblocks.empty()) cudaStreamSynchronize(ctx->stream);
     for (void* b : blocks) cudaFree(b);
+    for (void* b : hblocks) cudaFreeHost(b);
 }
 
 extern "C" int hg_ctx_trim(hg_ctx* ctx) {
@@ -154,6 +207,8 @@ extern "C" int hg_ctx_destroy(hg_ctx* ctx) {
     {   // blocks still held by live objects outlive the context: they will be cudaFree'd directly
         std::lock_guard<std::mutex> lk(g_pool_mu);
         for (auto& kv : g_pool_live)
+            if (kv.second.ctx == ctx) kv.second.ctx = nullptr;
+        for (auto& kv : g_hpool_live)
             if (kv.second.ctx == ctx) kv.second.ctx = nullptr;
     }
     if (ctx->d_partials) cudaFree(ctx->d_partials);

@@ -178,8 +178,8 @@ extern "C" int hg_darnoldi_destroy(hg_darnoldi* a) {
     hg_dfree(a->Q); hg_dfree(a->T);
     hg_dfree(a->w0); hg_dfree(a->w1); hg_dfree(a->d_H); hg_dfree(a->d_hcur); hg_dfree(a->d_s);
     hg_dfree(a->partials); hg_dfree(a->stat);
-    if (a->h_H) cudaFreeHost(a->h_H);
-    if (a->h_beta) cudaFreeHost(a->h_beta);
+    hg_hfree(a->h_H);
+    hg_hfree(a->h_beta);
     delete a;
     return HG_OK;
 }
@@ -236,8 +236,8 @@ extern "C" int hg_darnoldi_create(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A
     alloc(&a->d_s, 8);
     alloc(&a->partials, (size_t)(kmax + 2) * (size_t)(nslabs + 1));
     alloc(&a->stat, (size_t)std::max(a->n_pad, a->m_p) / 8 + 2048);
-    if (e == cudaSuccess) e = cudaMallocHost(&a->h_H, (size_t)a->ldh() * kmax * sizeof(double));
-    if (e == cudaSuccess) e = cudaMallocHost(&a->h_beta, 8 * sizeof(double));
+    if (e == cudaSuccess) e = hg_hmalloc(ctx, &a->h_H, (size_t)a->ldh() * kmax * sizeof(double));
+    if (e == cudaSuccess) e = hg_hmalloc(ctx, &a->h_beta, 8 * sizeof(double));
     if (e != cudaSuccess) {
         hg_set_error("hg_darnoldi_create: allocation failed: %s", cudaGetErrorString(e));
         hg_darnoldi_destroy(a);
@@ -433,9 +433,9 @@ extern "C" int hg_darnoldi_step_bytes(hg_darnoldi* a, int k, double* bytes) {
 namespace {
 struct DBufD {
     double* p = nullptr;
-    ~DBufD() { if (p) cudaFree(p); }
+    ~DBufD() { hg_dfree(p); }
     int alloc(size_t n) {
-        if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double)) != cudaSuccess) {
+        if (hg_dmalloc_cur((void**)&p, std::max<size_t>(n, 1) * sizeof(double)) != cudaSuccess) {
             hg_set_error("device allocation of %zu doubles failed", n);
             return HG_ERR_NOMEM;
         }
@@ -444,9 +444,9 @@ struct DBufD {
 };
 struct PinD {
     double* p = nullptr;
-    ~PinD() { if (p) cudaFreeHost(p); }
+    ~PinD() { hg_hfree(p); }
     int alloc(size_t n) {
-        if (cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(double)) != cudaSuccess) {
+        if (hg_hmalloc_cur((void**)&p, std::max<size_t>(n, 1) * sizeof(double)) != cudaSuccess) {
             hg_set_error("pinned allocation of %zu doubles failed", n);
             return HG_ERR_NOMEM;
         }
@@ -477,6 +477,7 @@ extern "C" int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg
     const int64_t n = a->n, n_p = a->n_p, m_p = a->m_p;
     const int64_t row0 = (int64_t)comm->rank * n_p;
     const int64_t nloc = std::max<int64_t>(0, std::min(n, row0 + n_p) - row0);
+    hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
     DBufD d_x, d_xt, d_y, d_g, stat_e, stat_r, d_xfull;
     PinD h_y, h_g, h_s;
     HG_TRY(d_x.alloc((size_t)n_p)); HG_TRY(d_xt.alloc((size_t)n_p)); HG_TRY(d_y.alloc((size_t)maxit + 1));
@@ -598,6 +599,7 @@ static int dist_gcv_ab(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A_p, const h
     const int64_t ldq = round_up(std::max<int64_t>(m_p, 1), 32);
     const int ldh = k_gcv + 1;
     const int nslabs = hg_multidot_nslabs(ctx, std::max<int64_t>(m_p, 1));
+    hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
     DBufD Q, z, w0, w1, dH, hcur, ds, partials, stat;
     PinD hH;
     HG_TRY(Q.alloc((size_t)ldq * (k_gcv + 1))); HG_TRY(z.alloc((size_t)n)); HG_TRY(w0.alloc((size_t)ldq));

@@ -19,11 +19,9 @@ namespace {
 
 struct DBuf {
     double* p = nullptr;
-    ~DBuf() {
-        if (p) cudaFree(p);
-    }
+    ~DBuf() { hg_dfree(p); }
     int alloc(size_t n, cudaStream_t st = nullptr, bool zero = false) {
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double));
+        cudaError_t e = hg_dmalloc_cur((void**)&p, std::max<size_t>(n, 1) * sizeof(double));
         if (e != cudaSuccess) {
             hg_set_error("device allocation of %zu doubles failed: %s", n, cudaGetErrorString(e));
             return HG_ERR_NOMEM;
@@ -195,6 +193,7 @@ int hybrid_lsqr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
                "hg_hybrid_lsqr_solver: NULL argument");
     HG_REQUIRE(maxit >= 1, "hg_hybrid_lsqr_solver: maxit must be >= 1");
     HG_CUDA(cudaSetDevice(ctx->device));
+    hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
     Gkb g;
     HG_TRY(g.init(ctx, comm, A, At, b, x_true));
     const int64_t m = g.m, nl = g.nl, n = g.n;
@@ -275,6 +274,7 @@ int hybrid_lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
                "hg_hybrid_lsmr_solver: NULL argument");
     HG_REQUIRE(maxit >= 1, "hg_hybrid_lsmr_solver: maxit must be >= 1");
     HG_CUDA(cudaSetDevice(ctx->device));
+    hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
     Gkb g;
     HG_TRY(g.init(ctx, comm, A, At, b, x_true));
     const int64_t m = g.m, nl = g.nl, n = g.n;
@@ -368,6 +368,7 @@ int lsqr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* A
     HG_REQUIRE(ctx && A && x_true && x && error_norm && residual_norm && niters, "hg_lsqr_solver: NULL argument");
     HG_REQUIRE(maxit >= 1, "hg_lsqr_solver: maxit must be >= 1");
     HG_CUDA(cudaSetDevice(ctx->device));
+    hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
     Gkb g;
     HG_TRY(g.init(ctx, comm, A, At, b, x_true));
     const int64_t m = g.m, nl = g.nl, n = g.n;
@@ -431,6 +432,7 @@ int lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* A
     HG_REQUIRE(maxit >= 1, "hg_lsmr_solver: maxit must be >= 1");
     HG_CUDA(cudaSetDevice(ctx->device));
     const double eps = 2.220446049250313e-16;
+    hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
     Gkb g;
     HG_TRY(g.init(ctx, comm, A, At, b, x_true));
     const int64_t m = g.m, nl = g.nl, n = g.n;

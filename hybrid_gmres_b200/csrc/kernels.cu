@@ -481,8 +481,12 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // ===========================================================================
 
 static double spmv_bytes(const hg_matrix* m, const hg_spmv_epilogue& ep, bool store) {
-    // 12*nnz + pw*(r+1) + 8c + 8r (+8r per epilogue vector read)
-    double b = 12.0 * (double)m->nnz + 8.0 * (double)(m->rows + 1) + 8.0 * (double)m->cols;
+    // (8+iw)*nnz + pw*(r+1) + 8c + 8r (+8r per epilogue vector read); iw = 4 bytes per
+    // column index, or 2 + 4/group when the matrix runs with 16-bit offsets (group = 128 or 32 entries)
+    double idx = 4.0 * (double)m->nnz;
+    if (m->sell_state > 0 && m->sell_col16) idx = 2.0 * (double)m->nnz + 4.0 * (double)(m->sell_entries / 128);
+    else if (m->sell_state <= 0 && m->csr16_state > 0) idx = 2.0 * (double)m->nnz + 4.0 * (double)m->csr_groups + 8.0 * (double)m->rows;
+    double b = 8.0 * (double)m->nnz + idx + 8.0 * (double)(m->rows + 1) + 8.0 * (double)m->cols;
     if (store) b += 8.0 * (double)m->rows;
     if (ep.z1) b += 8.0 * (double)m->rows;
     if (ep.z2) b += 8.0 * (double)m->rows;
@@ -495,8 +499,10 @@ int hg_k_spmv(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
     if (nparts) *nparts = 0;
     if (m->rows == 0) return HG_OK;
     if (hg_spmv_stream_eligible(m)) return hg_k_spmv_stream(ctx, m, x, y, ep, nparts);
-    if (hg_spmv_mode() == 0 && hg_sell_ready(ctx, m))
+    if ((hg_spmv_mode() == 0 || hg_spmv_mode() == 3) && hg_sell_ready(ctx, m))
         return hg_k_spmv_sell(ctx, m, x, y, ep, spmv_bytes(m, ep, y != nullptr), nparts);
+    if (m->tpr == 32 && hg_spmv_mode() == 0 && hg_idx16_csr_enabled() && hg_csr16_ready(ctx, m))
+        return hg_k_spmv_csr16(ctx, m, x, y, ep, spmv_bytes(m, ep, y != nullptr), nparts);
     const int tpr = m->tpr;
     const int rpb = kBlock / tpr;
     const int64_t grid = cdiv(m->rows, rpb);

@@ -227,6 +227,7 @@ extern "C" int hg_matrix_destroy(hg_matrix* m) {
     hg_dfree(m->sell_ptr);
     hg_dfree(m->sell_col);
     hg_dfree(m->sell_val);
+    hg_idx16_free(m);
     delete m;
     return HG_OK;
 }
@@ -245,7 +246,7 @@ static int upload_ptr(hg_ctx* ctx, const void* ptr, int bits, int64_t count, int
         return HG_OK;
     }
     int32_t* tmp = nullptr;
-    HG_CUDA(cudaMalloc(&tmp, (size_t)count * 4));
+    HG_CUDA(hg_dmalloc(ctx, &tmp, (size_t)count * 4));
     HG_CUDA(cudaMemcpyAsync(tmp, ptr, (size_t)count * 4, cudaMemcpyHostToDevice, ctx->stream));
     {
         hg_launch_scope scope(ctx, HG_K_SETUP, 12.0 * (double)count);
@@ -253,7 +254,7 @@ static int upload_ptr(hg_ctx* ctx, const void* ptr, int bits, int64_t count, int
     }
     HG_CUDA(cudaGetLastError());
     HG_CUDA(cudaStreamSynchronize(ctx->stream));
-    HG_CUDA(cudaFree(tmp));
+    hg_dfree(tmp);
     return HG_OK;
 }
 
@@ -305,7 +306,7 @@ extern "C" int hg_matrix_from_csc(hg_ctx* ctx, int64_t rows, int64_t cols, int64
         const int64_t chunk = (int64_t)1 << 24;
         int64_t* tmp = nullptr;
         if (st == HG_OK && nnz > 0) {
-            if (cudaMalloc(&tmp, (size_t)std::min(chunk, nnz) * 8) != cudaSuccess) {
+            if (hg_dmalloc(ctx, &tmp, (size_t)std::min(chunk, nnz) * 8) != cudaSuccess) {
                 hg_set_error("hg_matrix_from_csc: staging allocation failed");
                 st = HG_ERR_NOMEM;
             }
@@ -334,7 +335,7 @@ extern "C" int hg_matrix_from_csc(hg_ctx* ctx, int64_t rows, int64_t cols, int64
                 st = HG_ERR_CUDA;
             }
         }
-        if (tmp) cudaFree(tmp);
+        if (tmp) hg_dfree(tmp);
         if (st != HG_OK) {
             hg_matrix_destroy(t);
             return st;
@@ -355,7 +356,7 @@ extern "C" int hg_matrix_from_dense(hg_ctx* ctx, int64_t rows, int64_t cols, con
     HG_TRY(hg_matrix_alloc(ctx, rows, cols, rows * cols, &m));
     double* d_a = nullptr;
     const size_t bytes = (size_t)std::max<int64_t>(lda * cols, 1) * 8;
-    if (cudaMalloc(&d_a, bytes) != cudaSuccess) {
+    if (hg_dmalloc(ctx, &d_a, bytes) != cudaSuccess) {
         hg_matrix_destroy(m);
         hg_set_error("hg_matrix_from_dense: staging allocation failed");
         return HG_ERR_NOMEM;
@@ -369,7 +370,7 @@ extern "C" int hg_matrix_from_dense(hg_ctx* ctx, int64_t rows, int64_t cols, con
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_a);
+    hg_dfree(d_a);
     if (e != cudaSuccess) {
         hg_set_error("hg_matrix_from_dense: %s", cudaGetErrorString(e));
         hg_matrix_destroy(m);
@@ -396,7 +397,7 @@ static int hg_sort_rows_device(hg_ctx* ctx, hg_matrix* t) {
             st = HG_ERR_CUDA;                                                            \
         }                                                                                \
     } while (0)
-    TR_CUDA(cudaMalloc(&d_max, sizeof(unsigned long long)));
+    TR_CUDA(hg_dmalloc(ctx, &d_max, sizeof(unsigned long long)));
     if (st == HG_OK) TR_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), ctx->stream));
     if (st == HG_OK) {
         {
@@ -421,8 +422,8 @@ static int hg_sort_rows_device(hg_ctx* ctx, hg_matrix* t) {
                 TR_CUDA(cudaGetLastError());
             }
             if (st == HG_OK && h_max > (unsigned long long)cap) {
-                TR_CUDA(cudaMalloc(&sk, (size_t)t->nnz * 4));
-                TR_CUDA(cudaMalloc(&sv, (size_t)t->nnz * 8));
+                TR_CUDA(hg_dmalloc(ctx, &sk, (size_t)t->nnz * 4));
+                TR_CUDA(hg_dmalloc(ctx, &sv, (size_t)t->nnz * 8));
                 if (st == HG_OK) {
                     hg_launch_scope scope(ctx, HG_K_SETUP, 24.0 * (double)t->nnz);
                     sort_long_rows_kernel<<<(unsigned)grid, kBlock, 0, ctx->stream>>>(
@@ -434,9 +435,9 @@ static int hg_sort_rows_device(hg_ctx* ctx, hg_matrix* t) {
     }
     if (st == HG_OK) TR_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef TR_CUDA
-    if (d_max) cudaFree(d_max);
-    if (sk) cudaFree(sk);
-    if (sv) cudaFree(sv);
+    if (d_max) hg_dfree(d_max);
+    if (sk) hg_dfree(sk);
+    if (sv) hg_dfree(sv);
     return st;
 }
 
@@ -458,7 +459,7 @@ int hg_transpose_device(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out) {
             st = HG_ERR_CUDA;                                                            \
         }                                                                                \
     } while (0)
-    TR_CUDA(cudaMalloc(&cnt, (size_t)(tr + 1) * sizeof(unsigned int)));
+    TR_CUDA(hg_dmalloc(ctx, &cnt, (size_t)(tr + 1) * sizeof(unsigned int)));
     if (st == HG_OK) TR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(tr + 1) * sizeof(unsigned int), ctx->stream));
     if (st == HG_OK && m->nnz > 0) {
         hg_launch_scope scope(ctx, HG_K_SETUP, 4.0 * (double)m->nnz);
@@ -494,7 +495,7 @@ int hg_transpose_device(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out) {
     }
     if (st == HG_OK) TR_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef TR_CUDA
-    if (cnt) cudaFree(cnt);
+    if (cnt) hg_dfree(cnt);
     if (st != HG_OK) {
         hg_matrix_destroy(t);
         return st;
@@ -544,14 +545,14 @@ extern "C" int hg_matrix_permute(hg_ctx* ctx, const hg_matrix* m, const int32_t*
         }                                                                                \
     } while (0)
     if (rowperm) {
-        PM_CUDA(cudaMalloc(&d_rp, (size_t)std::max<int64_t>(m->rows, 1) * 4));
+        PM_CUDA(hg_dmalloc(ctx, &d_rp, (size_t)std::max<int64_t>(m->rows, 1) * 4));
         if (st == HG_OK) PM_CUDA(cudaMemcpyAsync(d_rp, rowperm, (size_t)m->rows * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (colperm) {
-        PM_CUDA(cudaMalloc(&d_ci, (size_t)std::max<int64_t>(m->cols, 1) * 4));
+        PM_CUDA(hg_dmalloc(ctx, &d_ci, (size_t)std::max<int64_t>(m->cols, 1) * 4));
         if (st == HG_OK) PM_CUDA(cudaMemcpyAsync(d_ci, inv.data(), (size_t)m->cols * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    PM_CUDA(cudaMalloc(&d_len, (size_t)std::max<int64_t>(m->rows, 1) * 4));
+    PM_CUDA(hg_dmalloc(ctx, &d_len, (size_t)std::max<int64_t>(m->rows, 1) * 4));
     if (st == HG_OK && m->rows > 0) {
         {
             hg_launch_scope scope(ctx, HG_K_SETUP, 16.0 * (double)m->rows);
@@ -580,9 +581,9 @@ extern "C" int hg_matrix_permute(hg_ctx* ctx, const hg_matrix* m, const int32_t*
     if (st == HG_OK && colperm && !(flags & HG_PERMUTE_KEEP_ENTRY_ORDER)) st = hg_sort_rows_device(ctx, t);
     if (st == HG_OK) PM_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef PM_CUDA
-    if (d_rp) cudaFree(d_rp);
-    if (d_ci) cudaFree(d_ci);
-    if (d_len) cudaFree(d_len);
+    if (d_rp) hg_dfree(d_rp);
+    if (d_ci) hg_dfree(d_ci);
+    if (d_len) hg_dfree(d_len);
     if (st != HG_OK) {
         hg_matrix_destroy(t);
         return st;
@@ -596,7 +597,10 @@ extern "C" int hg_matrix_spmv_form(hg_ctx* ctx, const hg_matrix* m, int* form) {
     HG_REQUIRE(ctx && m && form, "hg_matrix_spmv_form: NULL argument");
     HG_CUDA(cudaSetDevice(ctx->device));
     if (hg_spmv_stream_eligible(m)) *form = 2;
-    else if (m->rows > 0 && hg_spmv_mode() == 0 && hg_sell_ready(ctx, m)) *form = 1;
+    else if (m->rows > 0 && (hg_spmv_mode() == 0 || hg_spmv_mode() == 3) && hg_sell_ready(ctx, m))
+        *form = m->sell_col16 ? 1 | 16 : 1;
+    else if (m->rows > 0 && m->tpr == 32 && hg_spmv_mode() == 0 && hg_idx16_csr_enabled() && hg_csr16_ready(ctx, m))
+        *form = 0 | 16;
     else *form = 0;
     return HG_OK;
 }

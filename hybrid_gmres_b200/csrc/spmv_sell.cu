@@ -10,7 +10,7 @@
 // stays perfectly coalesced because the slice is stored column-major (entry j of lane l at
 // slice_base + 32 j + l).  Same entries, same per-row order as the CSR matrix; only slices
 // whose rows have (nearly) equal length are worth it, so the form is built only when padding
-// costs <= 3 % (B of every CT configuration: exactly 2*views entries per row).
+// costs <= 8 % (B of every CT configuration: exactly 2*views entries per row).
 #include <algorithm>
 
 #include "common.cuh"
@@ -47,6 +47,55 @@ __global__ void slice_width_kernel(int64_t rows, const int64_t* __restrict__ row
     if ((threadIdx.x & 31) == 0 && (row >> 5) < ((rows + 31) >> 5)) widths[row >> 5] = len;
 }
 
+// Gather locality of the two traversals, sampled: distinct 128-byte lines of x per gathered entry
+// when (a) the 32 lanes hold entry j of 32 adjacent rows (sliced form) and (b) the 32 lanes hold 32
+// consecutive entries of one row (row per warp).  counts = {lines_a, entries_a, lines_b, entries_b}.
+__device__ __forceinline__ int distinct_lines(bool active, int col) {
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    int n = 0;
+    if (active) {
+        const unsigned same = __match_any_sync(mask, col >> 4);
+        const bool leader = (__ffs(same) - 1) == (int)(threadIdx.x & 31);
+        n = __popc(__ballot_sync(mask, leader));
+    }
+    return __shfl_sync(0xffffffffu, n, mask ? __ffs(mask) - 1 : 0);
+}
+
+__global__ void __launch_bounds__(kBlock)
+gather_lines_kernel(int64_t rows, int64_t nslices, int64_t stride, const int64_t* __restrict__ rowptr,
+                    const int32_t* __restrict__ colind, unsigned long long* __restrict__ counts) {
+    const int64_t slice = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * stride;
+    const int lane = threadIdx.x & 31;
+    if (slice >= nslices) return;
+    const int64_t row = slice * 32 + lane;
+    const int64_t s = row < rows ? rowptr[row] : 0;
+    const int len = row < rows ? (int)(rowptr[row + 1] - s) : 0;
+    int width = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) width = max(width, __shfl_xor_sync(0xffffffffu, width, o));
+    unsigned long long la = 0, ea = 0, lb = 0, eb = 0;
+    for (int j = 0; j < width; j += 3) {  // (a) sampled columns of the slice
+        const bool act = j < len;
+        const int c = act ? colind[s + j] : 0;
+        la += distinct_lines(act, c);
+        ea += __popc(__ballot_sync(0xffffffffu, act));
+    }
+    const int64_t s0 = __shfl_sync(0xffffffffu, s, 0);  // (b) the slice's first row
+    const int len0 = __shfl_sync(0xffffffffu, len, 0);
+    for (int i0 = 0; i0 < len0; i0 += 32) {
+        const bool act = i0 + lane < len0;
+        const int c = act ? colind[s0 + i0 + lane] : 0;
+        lb += distinct_lines(act, c);
+        eb += __popc(__ballot_sync(0xffffffffu, act));
+    }
+    if (lane == 0) {
+        atomicAdd(counts + 0, la);
+        atomicAdd(counts + 1, ea);
+        atomicAdd(counts + 2, lb);
+        atomicAdd(counts + 3, eb);
+    }
+}
+
 // one warp per slice, 32 x 32 tiles through shared memory: a row's entries are read coalesced
 // (32 consecutive entries per trip), the slice columns are written coalesced (32 consecutive rows
 // per trip); padding slots repeat the row's last column with a zero value so padded gathers stay
@@ -77,7 +126,10 @@ sell_fill_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ rowp
             const int pad = __shfl_sync(0xffffffffu, my_pad, r);
             const int j = j0 + lane;
             const bool in = j < len;
-            t_col[w][r][lane] = in ? colind[s + j] : pad;
+            const bool exists = slice * 32 + r < rows;
+            // rows past the end of the matrix copy the columns of the slice's first row (zero values),
+            // so a group's column span stays that of real rows (16-bit offsets, spmv_idx16.cu)
+            t_col[w][r][lane] = in ? colind[s + j] : (exists ? pad : t_col[w][0][lane]);
             t_val[w][r][lane] = in ? vals[s + j] : 0.0;
         }
         __syncwarp();
@@ -188,7 +240,7 @@ bool hg_sell_ready(hg_ctx* ctx, const hg_matrix* cm) {
     if (m->rows < 64 || m->nnz < 8 * m->rows) return false;  // short rows: TPR<32 CSR kernels do fine
     const int64_t nslices = cdiv(m->rows, 32);
     int32_t* d_w = nullptr;
-    if (cudaMalloc(&d_w, (size_t)nslices * 4) != cudaSuccess) {
+    if (hg_dmalloc(ctx, &d_w, (size_t)nslices * 4) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
@@ -200,7 +252,7 @@ bool hg_sell_ready(hg_ctx* ctx, const hg_matrix* cm) {
     std::vector<int32_t> w((size_t)nslices);
     cudaError_t e = cudaMemcpyAsync(w.data(), d_w, (size_t)nslices * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_w);
+    hg_dfree(d_w);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return false;
@@ -209,10 +261,41 @@ bool hg_sell_ready(hg_ctx* ctx, const hg_matrix* cm) {
     int64_t acc = 0;
     for (int64_t s = 0; s < nslices; ++s) {
         ptr[(size_t)s] = acc;
-        acc += (int64_t)w[(size_t)s] * 32;
+        acc += (int64_t)((w[(size_t)s] + 3) / 4 * 4) * 32;  // 4-column groups (128 entries) never straddle slices
     }
     ptr[(size_t)nslices] = acc;
-    if ((double)acc > 1.08 * (double)m->nnz) return false;  // ragged rows: padding would cost > 8 % of the stream
+    const int mode = hg_spmv_mode();
+    if (mode != 3) {
+        // padding streams extra bytes; the gathers must be cheaper by more than that.  Pixel-driven
+        // back-projectors: 360 entries in every row, 1-2 lines per gather against ~16 -> sliced form.
+        // Ray-driven projectors: adjacent rays drift apart entry by entry -> row per warp.
+        if ((double)acc > 1.10 * (double)m->nnz) return false;
+        unsigned long long* d_cnt = nullptr;
+        unsigned long long h_cnt[4] = {0, 0, 0, 0};
+        if (hg_dmalloc(ctx, &d_cnt, 32) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        const int64_t stride = std::max<int64_t>(1, nslices / 2048);  // ~2048 sampled slices
+        const int64_t nwarps = cdiv(nslices, stride);
+        cudaError_t g = cudaMemsetAsync(d_cnt, 0, 32, ctx->stream);
+        if (g == cudaSuccess) {
+            hg_launch_scope scope(ctx, HG_K_SETUP, 12.0 * (double)m->nnz / (double)stride);
+            gather_lines_kernel<<<(unsigned)cdiv(nwarps * 32, kBlock), kBlock, 0, ctx->stream>>>(
+                m->rows, nslices, stride, m->rowptr, m->colind, d_cnt);
+            g = cudaGetLastError();
+        }
+        if (g == cudaSuccess) g = cudaMemcpyAsync(h_cnt, d_cnt, 32, cudaMemcpyDeviceToHost, ctx->stream);
+        if (g == cudaSuccess) g = cudaStreamSynchronize(ctx->stream);
+        hg_dfree(d_cnt);
+        if (g != cudaSuccess || h_cnt[1] == 0 || h_cnt[3] == 0) {
+            cudaGetLastError();
+            return false;
+        }
+        const double lines_sliced = (double)h_cnt[0] / (double)h_cnt[1] * ((double)acc / (double)m->nnz);
+        const double lines_rowwarp = (double)h_cnt[2] / (double)h_cnt[3];
+        if (lines_sliced > 0.75 * lines_rowwarp) return false;
+    }
     cudaError_t a = hg_dmalloc(ctx, &m->sell_ptr, (size_t)(nslices + 1) * 8);
     if (a == cudaSuccess) a = hg_dmalloc(ctx, &m->sell_col, (size_t)(acc + kNnzPad) * 4);
     if (a == cudaSuccess) a = hg_dmalloc(ctx, &m->sell_val, (size_t)(acc + kNnzPad) * 8);
@@ -238,11 +321,13 @@ bool hg_sell_ready(hg_ctx* ctx, const hg_matrix* cm) {
     m->sell_slices = nslices;
     m->sell_entries = acc;
     m->sell_state = 1;
+    if (hg_idx16_enabled()) hg_sell_compress(ctx, m);  // 16-bit column offsets when every group spans < 65536
     return true;
 }
 
 int hg_k_spmv_sell(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
                    const hg_spmv_epilogue& ep, double bytes, int* nparts) {
+    if (m->sell_col16) return hg_k_spmv_sell16(ctx, m, x, y, ep, bytes, nparts);
     const int64_t grid = cdiv(m->sell_slices, kBlock / 32);
     HG_REQUIRE(grid < (int64_t)2147483647, "spmv: too many rows for one launch");
     if (nparts && ep.stat) *nparts = (int)grid;

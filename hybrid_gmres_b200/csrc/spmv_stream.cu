@@ -246,7 +246,7 @@ static int spmv_mode() {
     if (g_spmv_mode < 0) {
         const char* e = getenv("HG_SPMV");
         g_spmv_mode = 0;
-        if (e && (e[0] == 'v' || e[0] == 'V')) g_spmv_mode = e[1] == '1' ? 1 : (e[1] == '2' ? 2 : 0);
+        if (e && (e[0] == 'v' || e[0] == 'V')) g_spmv_mode = e[1] == '1' ? 1 : (e[1] == '2' ? 2 : (e[1] == '3' ? 3 : 0));
     }
     return g_spmv_mode;
 }
@@ -272,6 +272,7 @@ bool hg_cgs_fused() {
 }
 
 void hg_dist_transport_set(int v);
+void hg_idx16_set(int v);
 
 extern "C" int hg_set_option(const char* name, int value) {
     HG_REQUIRE(name, "hg_set_option: NULL name");
@@ -280,8 +281,12 @@ extern "C" int hg_set_option(const char* name, int value) {
         return HG_OK;
     }
     if (strcmp(name, "spmv_mode") == 0) {
-        HG_REQUIRE(value >= 0 && value <= 2, "hg_set_option: spmv_mode must be 0, 1 or 2");
+        HG_REQUIRE(value >= 0 && value <= 3, "hg_set_option: spmv_mode must be 0, 1, 2 or 3");
         g_spmv_mode = value;
+        return HG_OK;
+    }
+    if (strcmp(name, "spmv_idx16") == 0) {
+        hg_idx16_set(value);
         return HG_OK;
     }
     if (strcmp(name, "cgs_alternate") == 0) {

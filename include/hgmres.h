@@ -61,9 +61,10 @@ typedef struct hg_gcv hg_gcv;         /* memoised gcv_function Arnoldi       */
 const char* hg_last_error(void);
 int hg_version(void);
 
-/* Tuning knobs.  "spmv_mode": 0 auto (default; also env HG_SPMV=v1|v2): row-per-lane kernel over
- * 32-row slices when rows have near-equal length (padding <= 3 %), else the row-per-warp CSR kernel;
- * 1 force the row-per-warp CSR SpMV, 2 force the TMA-staged streaming SpMV.
+/* Tuning knobs.  "spmv_mode": 0 auto (default; also env HG_SPMV=v1|v2|v3): row-per-lane kernel over
+ * 32-row slices when that traversal gathers fewer 128-byte lines of x per entry than the row-per-warp
+ * one does (sampled at first use; padding <= 10 %), else the row-per-warp CSR kernel; 1 force the
+ * row-per-warp CSR SpMV, 2 force the TMA-staged streaming SpMV, 3 force the sliced form.
  * "cgs_fused": 0 (default; env HG_CGS_FUSED=1 enables) fuses the first CGS2 update with the
  * second-pass dot products (basis crosses HBM three times per step instead of four; measured
  * slower than the two separate streaming kernels on B200, see profiles/r01_cgs_fusion.md).
@@ -133,8 +134,11 @@ int hg_matrix_transpose(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out);
 #define HG_PERMUTE_KEEP_ENTRY_ORDER 1
 int hg_matrix_permute(hg_ctx* ctx, const hg_matrix* m, const int32_t* rowperm, const int32_t* colperm,
                       int flags, hg_matrix** out);
-/* Which SpMV kernel this matrix runs with: 0 CSR row-per-thread-group, 1 row-per-lane over 32-row
- * slices (built lazily when rows of a slice have near-equal length), 2 TMA-staged streaming. */
+/* Which SpMV kernel this matrix runs with: low 4 bits 0 CSR row-per-thread-group, 1 row-per-lane over
+ * 32-row slices (built lazily when rows of a slice have near-equal length), 2 TMA-staged streaming;
+ * bit 4 (value 16) set when the column indices are streamed as 16-bit offsets from per-group bases
+ * (csrc/spmv_idx16.cu: 10 instead of 12 bytes per entry; option "spmv_idx16" / env HG_IDX16: 0 off,
+ * 1 (default) for the sliced form, 2 also for the row-per-warp CSR kernel). */
 int hg_matrix_spmv_form(hg_ctx* ctx, const hg_matrix* m, int* form);
 int hg_matrix_info(const hg_matrix* m, int64_t* rows, int64_t* cols, int64_t* nnz);
 int hg_matrix_download_csr(hg_ctx* ctx, const hg_matrix* m, int64_t* rowptr, int32_t* colind,

@@ -197,30 +197,46 @@ def _uniform_rows(rows, cols, per_row, rng, ragged=0):
     return sp.csr_matrix((rng.standard_normal(indices.shape[0]), indices, indptr), shape=(rows, cols))
 
 
-@pytest.mark.parametrize("rows,per_row,ragged", [(64, 8, 0), (1000, 37, 0), (4099, 64, 1), (288, 130, 0)])
+@pytest.mark.parametrize("rows,per_row,ragged", [(64, 8, 0), (1000, 37, 0), (4099, 64, 1), (257, 130, 0), (333, 50, 7)])
 def test_spmv_sliced_form_matches_csr(hg, ctx, rows, per_row, ragged):
+    """The row-per-lane kernel (forced: spmv_mode 3; random columns would not select it) against
+    SciPy and the row-per-warp kernel, 16- and 32-bit indices, rows not a multiple of 32, ragged tails."""
     rng = np.random.default_rng(10)
     M = _uniform_rows(rows, 700, per_row, rng, ragged)
-    d = hg.DeviceMatrix.from_any(M, ctx)
-    assert d.spmv_form == "sell32"
     x = rng.standard_normal(M.shape[1])
-    y = d.matvec(x)
-    assert _rel(y, M @ x) < RTOL
-    assert np.array_equal(d.matvec(x), y)  # deterministic
-    hg.set_option("spmv_mode", 1)
+    ys = {}
     try:
+        for idx16 in (1, 0):
+            hg.set_option("spmv_idx16", idx16)
+            hg.set_option("spmv_mode", 3)
+            d = hg.DeviceMatrix.from_any(M, ctx)
+            assert d.spmv_form == "sell32" and d.spmv_index_bits == (16 if idx16 else 32)
+            y = d.matvec(x)
+            assert _rel(y, M @ x) < RTOL
+            assert np.array_equal(d.matvec(x), y)  # deterministic
+            ys[idx16] = y
+        hg.set_option("spmv_mode", 1)
         d1 = hg.DeviceMatrix.from_any(M, ctx)
         assert d1.spmv_form == "csr"
         y1 = d1.matvec(x)
     finally:
         hg.set_option("spmv_mode", 0)
-    assert _rel(y, y1) < RTOL
+        hg.set_option("spmv_idx16", 1)
+    assert np.array_equal(ys[0], ys[1])
+    assert _rel(ys[1], y1) < RTOL
+
+
+def test_spmv_random_columns_stay_row_per_warp(hg, ctx):
+    """Auto mode samples the gather locality: with random columns the sliced traversal gathers no
+    fewer lines than the row-per-warp one, so the matrix keeps the CSR kernel."""
+    M = _uniform_rows(2048, 50000, 64, np.random.default_rng(17))
+    assert hg.DeviceMatrix.from_any(M, ctx).spmv_form == "csr"
 
 
 def test_spmv_ragged_rows_stay_csr(hg, ctx, ct64):
     A, B = ct64[0], ct64[1]
     dA = hg.DeviceMatrix.from_any(A, ctx)
-    assert dA.spmv_form == "csr"  # ray lengths vary by more than 3 % inside a slice
+    assert dA.spmv_form == "csr"  # adjacent rays drift apart entry by entry: no gather locality across lanes
 
 
 def test_pixel_backprojector_uses_sliced_form(hg, ctx, ct48_unmatched):
@@ -287,3 +303,47 @@ def test_device_buffer_cache_reuses_blocks(hg, ctx):
     ctx.trim()
     d = hg.DeviceMatrix.from_any(M, ctx)
     assert np.array_equal(d.matvec(x), ys[0])
+
+
+@pytest.mark.parametrize("which", ["A", "B"])
+def test_spmv_16bit_offsets_bit_identical(hg, ctx, ct64, ct48_unmatched, which):
+    """col = base[group] + uint16 offset moves 10 instead of 12 bytes per entry; entry order and
+    arithmetic are those of the 32-bit kernels, so the product is bit-identical."""
+    M = ct64[0] if which == "A" else ct48_unmatched[1]  # ragged rays (row per warp) / uniform pixel rows (sliced)
+    x = np.random.default_rng(15).standard_normal(M.shape[1])
+    assert hg.DeviceMatrix.from_any(M, ctx).spmv_index_bits == (32 if which == "A" else 16)  # defaults
+    hg.set_option("spmv_idx16", 2)  # 16-bit offsets for the row-per-warp kernel too (opt-in)
+    try:
+        d16 = hg.DeviceMatrix.from_any(M, ctx)
+        assert d16.spmv_index_bits == 16 and d16.spmv_form == ("csr" if which == "A" else "sell32")
+        y16 = d16.matvec(x)
+        hg.set_option("spmv_idx16", 0)
+        d32 = hg.DeviceMatrix.from_any(M, ctx)
+        assert d32.spmv_index_bits == 32
+        y32 = d32.matvec(x)
+    finally:
+        hg.set_option("spmv_idx16", 1)
+    assert np.array_equal(y16, y32)
+    assert _rel(y16, M @ x) < RTOL
+
+
+def test_spmv_16bit_offsets_fall_back_on_wide_groups(hg, ctx):
+    """A group of entries spanning >= 65536 columns keeps the matrix on 32-bit indices."""
+    rng = np.random.default_rng(16)
+    rows, cols, per_row = 200, 300000, 64
+    indptr = np.arange(rows + 1) * per_row
+    indices = np.concatenate([np.sort(rng.choice(cols, per_row, replace=False)) for _ in range(rows)]).astype(np.int32)
+    M = sp.csr_matrix((rng.standard_normal(indices.shape[0]), indices, indptr), shape=(rows, cols))
+    d = hg.DeviceMatrix.from_any(M, ctx)
+    assert d.spmv_index_bits == 32
+    x = rng.standard_normal(cols)
+    assert _rel(d.matvec(x), M @ x) < RTOL
+    hg.set_option("spmv_mode", 1)  # the CSR kernel's 16-bit companion falls back the same way
+    hg.set_option("spmv_idx16", 2)
+    try:
+        d1 = hg.DeviceMatrix.from_any(M, ctx)
+        assert d1.spmv_form == "csr" and d1.spmv_index_bits == 32
+        assert _rel(d1.matvec(x), M @ x) < RTOL
+    finally:
+        hg.set_option("spmv_mode", 0)
+        hg.set_option("spmv_idx16", 1)
