@@ -1,0 +1,112 @@
+"""Size-independent properties at BASELINE.json's full sizes, where the oracle is too slow to run:
+the device generators, the SpMV forms and the 64-bit index paths on matrices with MORE THAN 2^31
+non-zeros (one rank's share of configs[4]: 2048^2, ~2.4e9 entries per shard).
+
+* ray-driven projector: ``A*1`` is the chord length of every ray through the image square
+  (closed form from the same slab formulas, oracle/ct.py geometry);
+* pixel-driven back-projector with linear interpolation: the two weights of a view sum to one, so
+  ``B*1`` counts the views in which the pixel projects onto the detector — all of them for the parallel
+  beam with ``p = round(sqrt(2) N)`` bins;
+* linearity and bit-identical reruns; a detector-row block generated on its own gives the
+  corresponding rows of the full product (what the sharded generators rely on).
+"""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _chords(N, angles_deg, p, geometry, R=None):
+    from hybrid_gmres_b200.ct import ray_tables
+    if R is None:
+        R = 2.0 * N
+    c, s, a, b = ray_tables(N, angles_deg, p, geometry, R)
+    c, s = c[:, None], s[:, None]
+    if geometry == "parallel":
+        ox, oy = c * a[None, :], s * a[None, :]
+        dx, dy = np.broadcast_to(-s, ox.shape), np.broadcast_to(c, ox.shape)
+    else:
+        cg, sg = a[None, :], b[None, :]
+        ox, oy = np.broadcast_to(R * c, (c.shape[0], cg.shape[1])), np.broadcast_to(R * s, (c.shape[0], cg.shape[1]))
+        dx, dy = -(c * cg - s * sg), -(s * cg + c * sg)
+    half = N / 2.0
+
+    def slab(o, d):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t1, t2 = (-half - o) / d, (half - o) / d
+        lo, hi = np.minimum(t1, t2), np.maximum(t1, t2)
+        z = d == 0.0
+        inside = (o >= -half) & (o < half)
+        return np.where(z, np.where(inside, -np.inf, np.inf), lo), np.where(z, np.inf, hi)
+
+    xlo, xhi = slab(ox, dx)
+    ylo, yhi = slab(oy, dy)
+    return np.maximum(np.minimum(xhi, yhi) - np.maximum(xlo, ylo), 0.0).ravel()
+
+
+@pytest.mark.parametrize("N,nviews,geometry", [(1024, 180, "fan"), (2048, 450, "parallel")])
+def test_projector_row_sums_are_chord_lengths(hg, ctx, N, nviews, geometry):
+    """(2048, 450): 2.4e9 non-zeros in one matrix — 64-bit row pointers and entry offsets."""
+    from hybrid_gmres_b200.ct import ct_projector, ct_projector_rows, tile_permutation
+    angles = np.arange(nviews) * ((360.0 if geometry == "fan" else 180.0) / nviews)
+    p = int(round(math.sqrt(2.0) * N))
+    A = ct_projector(N, angles, p, geometry, ctx=ctx)
+    if N == 2048:
+        assert A.nnz > 2 ** 31
+    ones = np.ones(A.shape[1])
+    y = A.matvec(ones)
+    ref = _chords(N, angles, p, geometry)
+    assert np.max(np.abs(y - ref)) <= 1e-9 * N
+    assert np.array_equal(A.matvec(ones), y)  # deterministic
+    rng = np.random.default_rng(0)
+    u, v = rng.standard_normal(A.shape[1]), rng.standard_normal(A.shape[1])
+    lin = A.matvec(2.0 * u - 3.0 * v) - (2.0 * A.matvec(u) - 3.0 * A.matvec(v))
+    assert np.linalg.norm(lin) <= 1e-12 * np.linalg.norm(A.matvec(u))
+    # the n-space in 4x4 tiles: same product on the re-ordered vector
+    q = tile_permutation(N, 4)
+    Aq = A.permute(None, q, sort=False)
+    yu = A.matvec(u)
+    A.close()
+    assert np.linalg.norm(Aq.matvec(u[q]) - yu) <= 1e-12 * np.linalg.norm(yu)
+    Aq.close()
+    # one rank's detector-row block, generated on its own
+    m = nviews * p
+    lo, hi = m // 8 * 3, m // 8 * 4
+    Ap = ct_projector_rows(N, angles, p, geometry, lo, hi, ctx=ctx)
+    yp = Ap.matvec(u)  # (the block may pick the other SpMV form: same entries, other summation order)
+    assert np.linalg.norm(yp - yu[lo:hi]) <= 1e-13 * np.linalg.norm(yu[lo:hi])
+    Ap.close()
+    ctx.trim()
+
+
+@pytest.mark.parametrize("N,nviews", [(1024, 180), (2048, 300)])
+def test_backprojector_row_sums_count_views(hg, ctx, N, nviews):
+    """(2048, 300): 2.5e9 non-zeros; the sliced 16-bit-offset form is built and used beyond 2^31 entries."""
+    from hybrid_gmres_b200.ct import ct_backprojector, tile_permutation
+    angles = np.arange(nviews) * (180.0 / nviews)
+    p = int(round(math.sqrt(2.0) * N))
+    B = ct_backprojector(N, angles, p, "parallel", ctx=ctx)
+    assert B.nnz == 2 * nviews * N * N
+    if N == 2048:
+        assert B.nnz > 2 ** 31
+    assert B.spmv_form == "sell32" and B.spmv_index_bits == 16
+    ones = np.ones(B.shape[1])
+    y = B.matvec(ones)
+    assert np.max(np.abs(y - nviews)) <= 1e-12 * nviews
+    u = np.random.default_rng(1).standard_normal(B.shape[1])
+    yu = B.matvec(u)
+    assert np.array_equal(B.matvec(u), yu)
+    hg.set_option("spmv_mode", 1)  # the row-per-warp kernel on the same matrix
+    try:
+        q = tile_permutation(N, 4)
+        Bq = B.permute(q, None)
+        B.close()
+        assert Bq.spmv_form == "csr"
+        yq = Bq.matvec(u)
+    finally:
+        hg.set_option("spmv_mode", 0)
+    assert np.linalg.norm(yq - yu[q]) <= 1e-12 * np.linalg.norm(yu)
+    Bq.close()
+    ctx.trim()
