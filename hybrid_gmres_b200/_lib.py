@@ -82,6 +82,7 @@ PROTOTYPES = {
     "hg_spmv": (_i, [_vp, _vp, _vp, _vp]),
     "hg_multidot": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp]),
     "hg_lincomb": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _d, _vp, _vp, c_double_p]),
+    "hg_cgs_mid": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _vp, _vp]),
     "hg_arnoldi_create": (_i, [_vp, _vp, _vp, _i, _i, c_void_pp]),
     "hg_arnoldi_destroy": (_i, [_vp]),
     "hg_arnoldi_set_rhs": (_i, [_vp, _vp]),

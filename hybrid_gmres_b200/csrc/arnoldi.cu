@@ -199,7 +199,10 @@ static int arnoldi_step(hg_arnoldi* a, int kk) {
     int ns = 0, np = 0;
     HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->nq, kk, a->w0, a->partials, &ns));
     HG_TRY(hg_k_reduce(ctx, a->partials, ns, kk, Hcol, false, a->d_hcur, false));
-    if (hg_cgs_fused()) {
+    if (hg_cgs_fused_mode() == 2 && hg_cgs_staged_nparts(ctx, a->nq, kk) > 0) {
+        // v -= Q h1 and h2 = Q' v in one pass over Q: the tile is staged in shared memory by cp.async
+        HG_TRY(hg_k_cgs_mid_staged(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, a->w0, a->w1, a->partials, &ns));
+    } else if (hg_cgs_fused()) {
         // v -= Q h1 and h2 = Q' v in one kernel: the second read of the Q tile is an L2 hit
         HG_TRY(hg_k_update_dot(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, a->w0, a->w1, a->partials, &ns));
     } else {

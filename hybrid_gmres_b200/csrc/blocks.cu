@@ -94,3 +94,39 @@ extern "C" int hg_lincomb(hg_ctx* ctx, int64_t n, int k, const double* V, int64_
     if (out_norm2) *out_norm2 = ctx->h_scalars[0];
     return HG_OK;
 }
+
+
+// CGS2 middle stage on host arrays: w1 = w0 - V h, d = V' w1.  `fused` != 0 uses the shared-memory
+// staged one-pass kernel (cgs_staged.cu; HG_ERR_INVALID when (n, k) is outside its range), 0 the
+// separate update + multi-dot kernels.
+extern "C" int hg_cgs_mid(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, const double* h,
+                          const double* w0, int fused, double* w1, double* d) {
+    HG_REQUIRE(ctx && V && h && w0 && w1 && d, "hg_cgs_mid: NULL argument");
+    HG_REQUIRE(k >= 1 && n >= 1 && ld >= n, "hg_cgs_mid: bad shape");
+    HG_CUDA(cudaSetDevice(ctx->device));
+    hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
+    DBuf dV, dh, dw0, dw1, dd, dp;
+    int64_t ldd = 0;
+    HG_TRY(upload_basis(ctx, n, k, V, ld, dV, &ldd));
+    HG_TRY(dh.alloc((size_t)k));
+    HG_TRY(dw0.alloc((size_t)ldd));
+    HG_TRY(dw1.alloc((size_t)ldd));
+    HG_TRY(dd.alloc((size_t)k));
+    HG_TRY(dp.alloc((size_t)(k + 1) * (size_t)(std::max<int64_t>(n / 256 + 2, ctx->sm_count) + 1)));
+    HG_CUDA(cudaMemcpyAsync(dh.p, h, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+    HG_CUDA(cudaMemcpyAsync(dw0.p, w0, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int ns = 0;
+    if (fused) {
+        HG_REQUIRE(hg_cgs_staged_nparts(ctx, n, k) > 0, "hg_cgs_mid: (n=%lld, k=%d) is outside the staged kernel's range",
+                   (long long)n, k);
+        HG_TRY(hg_k_cgs_mid_staged(ctx, dV.p, ldd, n, k, dh.p, dw0.p, dw1.p, dp.p, &ns));
+    } else {
+        HG_TRY(hg_k_lincomb(ctx, dV.p, ldd, n, k, dh.p, -1.0, dw0.p, dw1.p, nullptr, nullptr, nullptr));
+        HG_TRY(hg_k_multidot(ctx, dV.p, ldd, n, k, dw1.p, dp.p, &ns));
+    }
+    HG_TRY(hg_k_reduce(ctx, dp.p, ns, k, dd.p, false, nullptr, false));
+    HG_CUDA(cudaMemcpyAsync(w1, dw1.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HG_CUDA(cudaMemcpyAsync(d, dd.p, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HG_OK;
+}

@@ -219,8 +219,15 @@ int hg_norm2_sync(hg_ctx* ctx, const double* x, int64_t n, double* out);
 // reduce `np` partials at ctx->d_partials into d_scalars[slot] (optionally sqrt)
 int hg_reduce_to_scalar(hg_ctx* ctx, int np, int slot, bool do_sqrt);
 
+// TMA-staged fused CGS2 middle stage (cgs_staged.cu): w1 = w0 - V h and partials = V^T w1 in one pass
+// over V.  hg_cgs_staged_nparts: partials per column the kernel writes, 0 when (n, k) is out of range.
+int hg_cgs_staged_nparts(const hg_ctx* ctx, int64_t n, int k);
+int hg_k_cgs_mid_staged(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* h,
+                     const double* w0, double* w1, double* partials, int* nparts);
+
 // options (spmv_stream.cu)
-bool hg_cgs_fused();
+bool hg_cgs_fused();      // 1: L2-re-read fused kernel (update_dot_kernel)
+int hg_cgs_fused_mode();  // 0 separate kernels, 1 update_dot_kernel, 2 shared-memory-staged fused kernel
 
 // streaming SpMV (spmv_stream.cu)
 bool hg_spmv_stream_eligible(const hg_matrix* m);

@@ -15,7 +15,6 @@ struct PoolRec {
 };
 std::mutex g_pool_mu;
 std::unordered_map<void*, PoolRec> g_pool_live;  // every block handed out by hg_dmalloc_bytes
-constexpr size_t kPoolMinBytes = 0;  // every size is cached (rounded up to 512 B)
 std::unordered_map<void*, PoolRec> g_hpool_live;  // pinned host blocks handed out by hg_hmalloc_bytes
 
 size_t pool_cap_bytes() {
@@ -31,7 +30,7 @@ size_t pool_cap_bytes() {
 cudaError_t hg_dmalloc_bytes(hg_ctx* ctx, void** p, size_t bytes) {
     *p = nullptr;
     const size_t want = (std::max<size_t>(bytes, 1) + 511) / 512 * 512;
-    if (want >= kPoolMinBytes && pool_cap_bytes() > 0) {
+    if (pool_cap_bytes() > 0) {  // every size is cached (rounded up to 512 B)
         std::lock_guard<std::mutex> lk(g_pool_mu);
         auto it = ctx->pool_free.lower_bound(want);
         if (it != ctx->pool_free.end() && it->first <= want + want / 8) {
@@ -48,7 +47,7 @@ cudaError_t hg_dmalloc_bytes(hg_ctx* ctx, void** p, size_t bytes) {
         hg_pool_trim(ctx);
         e = cudaMalloc(p, want);
     }
-    if (e == cudaSuccess && want >= kPoolMinBytes) {
+    if (e == cudaSuccess) {
         std::lock_guard<std::mutex> lk(g_pool_mu);
         g_pool_live[*p] = PoolRec{ctx, want};
     }

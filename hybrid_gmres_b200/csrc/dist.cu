@@ -234,7 +234,7 @@ extern "C" int hg_darnoldi_create(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A
     alloc(&a->d_H, (size_t)a->ldh() * kmax);
     alloc(&a->d_hcur, (size_t)kmax + 1);
     alloc(&a->d_s, 8);
-    alloc(&a->partials, (size_t)(kmax + 2) * (size_t)(nslabs + 1));
+    alloc(&a->partials, (size_t)(kmax + 2) * (size_t)(std::max(nslabs, ctx->sm_count) + 1));
     alloc(&a->stat, (size_t)std::max(a->n_pad, a->m_p) / 8 + 2048);
     if (e == cudaSuccess) e = hg_hmalloc(ctx, &a->h_H, (size_t)a->ldh() * kmax * sizeof(double));
     if (e == cudaSuccess) e = hg_hmalloc(ctx, &a->h_beta, 8 * sizeof(double));
@@ -331,9 +331,13 @@ static int darnoldi_step(hg_darnoldi* a, int kk) {
         // w0 = sum_p (B^p u_p)[slice] + shift*q[slice], fused with h1 = Q_k' w0
         HG_TRY(hg_k_pull_multidot(c, a->row0, q_slice, a->shift, a->w0, a->Q, a->ldq, a->n_p, kk, a->partials, &ns));
         HG_TRY(hg_k_reduce_allreduce(c, a->partials, ns, kk, a->d_hcur, Hcol, false, false));
-        HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr, nullptr, nullptr,
-                                 nullptr, hg_cgs_alternate()));
-        HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->n_p, kk, a->w1, a->partials, &ns));
+        if (hg_cgs_fused_mode() == 2 && hg_cgs_staged_nparts(ctx, a->n_p, kk) > 0) {
+            HG_TRY(hg_k_cgs_mid_staged(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, a->w0, a->w1, a->partials, &ns));
+        } else {
+            HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr, nullptr, nullptr,
+                                     nullptr, hg_cgs_alternate()));
+            HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->n_p, kk, a->w1, a->partials, &ns));
+        }
         HG_TRY(hg_k_reduce_allreduce(c, a->partials, ns, kk, a->d_hcur, Hcol, true, false));  // H(1:k,k) = h1 + h2
         // v = w1 - Q h2: rows go to the local basis AND to every rank's replicated vector (all-gather
         // by the producing kernel); the norm all-reduce is the barrier for them

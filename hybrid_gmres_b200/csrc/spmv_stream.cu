@@ -263,13 +263,14 @@ bool hg_cgs_alternate() {
 }
 
 static int g_cgs_fused = -1;
-bool hg_cgs_fused() {
+int hg_cgs_fused_mode() {
     if (g_cgs_fused < 0) {
         const char* e = getenv("HG_CGS_FUSED");
-        g_cgs_fused = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured slower, profiles/r01_cgs_fusion.md
+        g_cgs_fused = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;  // default: shared-memory-staged one-pass kernel
     }
-    return g_cgs_fused != 0;
+    return g_cgs_fused;
 }
+bool hg_cgs_fused() { return hg_cgs_fused_mode() == 1; }
 
 void hg_dist_transport_set(int v);
 void hg_idx16_set(int v);
@@ -277,7 +278,8 @@ void hg_idx16_set(int v);
 extern "C" int hg_set_option(const char* name, int value) {
     HG_REQUIRE(name, "hg_set_option: NULL name");
     if (strcmp(name, "cgs_fused") == 0) {
-        g_cgs_fused = value ? 1 : 0;
+        HG_REQUIRE(value >= 0 && value <= 2, "hg_set_option: cgs_fused must be 0, 1 or 2");
+        g_cgs_fused = value;
         return HG_OK;
     }
     if (strcmp(name, "spmv_mode") == 0) {

@@ -98,13 +98,25 @@ class ShardedArnoldi:
             self._h = None
 
 
-def _dist_rtp(kind, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras):
+def _dist_rtp(kind, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras, nperm=None):
     from ._lib import HgExtras, c_double_p
     ctx = comm.ctx
     maxit = int(maxit)
     n = A_p.shape[1]
     b_p = _vec(b_p, A_p.shape[0], "b_p")
     x_true = _vec(x_true, n, "x_true")
+    own = []
+    if not isinstance(A_p, DeviceMatrix):
+        A_p = DeviceMatrix.from_any(A_p, ctx)
+        own.append(A_p)
+    if not isinstance(B_p, DeviceMatrix):
+        B_p = DeviceMatrix.from_any(B_p, ctx)
+        own.append(B_p)
+    if nperm is not None:  # n-space order of the solve (api._rtp): A_p(:,q), B^p(q,:), x_true(q)
+        nperm = np.ascontiguousarray(nperm, dtype=np.int32)
+        A_p, B_p = A_p.permute(None, nperm, sort=False), B_p.permute(nperm, None)
+        own += [A_p, B_p]
+        x_true = np.ascontiguousarray(x_true[nperm])
     x, err, res = np.zeros(n), np.zeros(maxit), np.zeros(maxit)
     niters, x_valid = C.c_int(), C.c_int()
     ex, bufs = None, None
@@ -116,21 +128,28 @@ def _dist_rtp(kind, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras):
     check(ctx._lib.hg_dist_hybrid_rtp(kind, ctx._h, comm._h, A_p._h, B_p._h, _ptr(b_p), _ptr(x_true), float(tol),
                                       maxit, float(lam), _ptr(x), _ptr(err), _ptr(res), C.byref(niters),
                                       C.byref(x_valid), C.byref(ex) if ex else None))
+    for d in own:
+        d.close()
     k = niters.value
+    if nperm is not None:
+        xu = np.empty_like(x)
+        xu[nperm] = x
+        x = xu
     if extras is not None:
         extras.update(H=bufs["H"], beta=float(bufs["beta"][0]))
     return (x if x_valid.value else None), err[:k], res[:k], k
 
 
-def hybrid_ab_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lam, *, extras=None):
-    """Sharded ``hybrid_ab_gmres_rtp.m``: ``A_p``/``B_p`` are this rank's shards (device
-    matrices), ``b_p`` its slice of ``b``; returns the reference's four outputs on every rank."""
-    return _dist_rtp(0, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras)
+def hybrid_ab_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lam, *, extras=None, nperm=None):
+    """Sharded ``hybrid_ab_gmres_rtp.m``: ``A_p``/``B_p`` are this rank's shards (device matrices, or
+    host matrices uploaded for the call), ``b_p`` its slice of ``b``; returns the reference's four
+    outputs on every rank.  ``nperm``: n-space order on the device, as in the single-GPU solver."""
+    return _dist_rtp(0, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras, nperm)
 
 
-def hybrid_ba_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lam, *, extras=None):
+def hybrid_ba_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lam, *, extras=None, nperm=None):
     """Sharded ``hybrid_ba_gmres_rtp.m``."""
-    return _dist_rtp(1, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras)
+    return _dist_rtp(1, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras, nperm)
 
 
 def gcv_prepare(comm, A_p, B_p, b_p, m, k_gcv, gcv_type):

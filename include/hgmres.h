@@ -65,9 +65,11 @@ int hg_version(void);
  * 32-row slices when that traversal gathers fewer 128-byte lines of x per entry than the row-per-warp
  * one does (sampled at first use; padding <= 10 %), else the row-per-warp CSR kernel; 1 force the
  * row-per-warp CSR SpMV, 2 force the TMA-staged streaming SpMV, 3 force the sliced form.
- * "cgs_fused": 0 (default; env HG_CGS_FUSED=1 enables) fuses the first CGS2 update with the
- * second-pass dot products (basis crosses HBM three times per step instead of four; measured
- * slower than the two separate streaming kernels on B200, see profiles/r01_cgs_fusion.md).
+ * "cgs_fused" / env HG_CGS_FUSED: the first CGS2 update and the second-pass dot products in one pass
+ * over the basis (it crosses HBM three times per step instead of four).  2 (default): tiles staged in
+ * shared memory by cp.async, persistent CTAs (csrc/cgs_staged.cu; 680 -> 728 it/s on the headline
+ * workload); 1: the first attempt that re-reads the tile from L2 (slower than the separate kernels,
+ * profiles/r01_cgs_fusion.md); 0: separate update and multi-dot kernels.
  * "cgs_alternate": 0 (default; env HG_CGS_ALTERNATE=1 enables) the CGS2 update kernels walk the rows
  * from the end, so each sweep over the basis starts on the ~100 MB the previous one left in L2
  * (measured neutral on B200: 647.5 vs 649.1 it/s).
@@ -171,6 +173,11 @@ int hg_multidot(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, cons
                 double* h);
 int hg_lincomb(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, const double* c,
                double s, const double* z, double* out, double* out_norm2);
+/* CGS2 middle stage: w1 = w0 - V h and d = V' w1 (h: k coefficients).  fused != 0: the one-pass kernel
+ * that stages the basis tile in shared memory (csrc/cgs_staged.cu; 24 <= k <= 208 and n >= 256 rows per
+ * SM, else HG_ERR_INVALID); 0: the separate update + multi-dot kernels. */
+int hg_cgs_mid(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, const double* h,
+               const double* w0, int fused, double* w1, double* d);
 
 /* ---- Arnoldi on device-resident data (a1-a4, a9 in SURVEY.md §8a) -------- */
 typedef enum hg_space {

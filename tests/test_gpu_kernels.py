@@ -347,3 +347,32 @@ def test_spmv_16bit_offsets_fall_back_on_wide_groups(hg, ctx):
     finally:
         hg.set_option("spmv_mode", 0)
         hg.set_option("spmv_idx16", 1)
+
+
+@pytest.mark.parametrize("n,k", [(40000, 24), (40000, 40), (40001, 41), (50050, 88), (38000, 89), (41003, 150),
+                                 (39999, 208)])
+def test_cgs_staged_stage_against_numpy(hg, ctx, n, k):
+    """The one-pass CGS2 middle stage (csrc/cgs_staged.cu): `w1 = w0 - V h`, `d = V' w1` — every tile
+    shape (k <= 40 / <= 88 / <= 208), n not a multiple of the tile (odd n: a row pair straddles the end),
+    against NumPy and against the separate kernels, bit-identical reruns."""
+    rng = np.random.default_rng(20 + k)
+    V = np.asfortranarray(rng.standard_normal((n, k)))
+    h = rng.standard_normal(k)
+    w0 = rng.standard_normal(n)
+    lib = ctx._lib
+    outs = []
+    for fused in (1, 1, 0):
+        w1, d = np.zeros(n), np.zeros(k)
+        hg._lib.check(lib.hg_cgs_mid(ctx._h, n, k, V.ctypes.data, n, h.ctypes.data, w0.ctypes.data, fused,
+                                     w1.ctypes.data, d.ctypes.data))
+        outs.append((w1, d))
+    ref_w1 = w0 - V @ h
+    ref_d = V.T @ ref_w1
+    scale = np.linalg.norm(V, axis=0) * np.linalg.norm(ref_w1)
+    for w1, d in outs:
+        assert _rel(w1, ref_w1) < 1e-14
+        assert np.max(np.abs(d - ref_d) / scale) < 1e-14
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    with pytest.raises(hg._lib.HgError):  # outside its range the staged kernel refuses (callers fall back)
+        hg._lib.check(lib.hg_cgs_mid(ctx._h, 1000, 8, V.ctypes.data, n, h.ctypes.data, w0.ctypes.data, 1,
+                                     np.zeros(1000).ctypes.data, np.zeros(8).ctypes.data))

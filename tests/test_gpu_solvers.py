@@ -267,7 +267,7 @@ def test_cgs_fused_option_matches_default(hg, ctx, ct64):
             r = hg.hybrid_ba_gmres_rtp(A, B, b, x_true, 1e-6, 45, 1e-2, ctx=ctx, extras=ex)
             out[fused] = (r, ex)
     finally:
-        hg.set_option("cgs_fused", 0)
+        hg.set_option("cgs_fused", 2)
     (r0, e0), (r1, e1) = out[0], out[1]
     assert r0[3] == r1[3]
     assert np.max(_colwise(e1["H"], e0["H"], r0[3])) < 1e-11
@@ -293,3 +293,46 @@ def test_nspace_permutation_is_a_similarity(hg, ctx, ct48_unmatched, solver):
     assert np.max(np.abs(err0 - err1) / err0) < 1e-10
     assert np.linalg.norm(x0 - x1) <= 1e-10 * np.linalg.norm(x0)
     assert np.linalg.norm(e0["X"] - e1["X"]) <= 1e-10 * np.linalg.norm(e0["X"])
+
+
+def test_cgs_staged_fused_stage_keeps_the_arnoldi_factorisation(hg, ctx):
+    """cgs_fused = 2 (default): `w1 = w0 - V h1` and `V' w1` in one pass over the basis, tiles staged in
+    shared memory by cp.async (csrc/cgs_staged.cu).  n = 65536 rows >= 256 per SM so the kernel is used, and
+    k runs through its three tile shapes (k <= 40, <= 88, <= 208).  On this problem H itself is ill
+    determined beyond k ~ 40 (switching the SpMV kernel alone moves column 44 by 3e-2), so the comparison
+    with the separate kernels is on the first 38 columns and the full run is judged by what CGS2 must
+    deliver: an orthonormal basis and the Arnoldi relation (B A + lambda I) Q_k = Q_{k+1} H, plus
+    bit-identical reruns."""
+    import scipy.sparse as sp
+    from hybrid_gmres_b200.ct import ct_backprojector, ct_projector, shepp_logan
+    N, K, lam = 256, 100, 1e-2
+    angles = np.arange(180) * 2.0
+    dA = ct_projector(N, angles, None, "fan", ctx=ctx)
+    dB = ct_backprojector(N, angles, None, "fan", ctx=ctx)
+    b = dA.matvec(shepp_logan(N))
+    out = {}
+    Q = None
+    try:
+        for fused in (0, 2, 2):
+            hg.set_option("cgs_fused", fused)
+            ar = hg.Arnoldi(dA, dB, "n", K)
+            ar.set_rhs(b)
+            ar.reset(lam)
+            ar.steps(K)
+            out.setdefault(fused, []).append(ar.get())
+            if fused == 2 and Q is None:
+                Q = np.column_stack([ar.q(j) for j in range(K + 1)])
+            ar.close()
+    finally:
+        hg.set_option("cgs_fused", 2)
+    (H0, beta0, k0), (H2, beta2, k2), (H2b, _, _) = out[0][0], out[2][0], out[2][1]
+    assert k0 == k2 == K and beta0 == beta2
+    assert np.array_equal(H2, H2b)  # deterministic
+    for j in range(38):
+        assert np.linalg.norm(H2[:j + 2, j] - H0[:j + 2, j]) <= 1e-9 * np.linalg.norm(H0[:j + 2, j]), j
+    assert np.max(np.abs(Q.T @ Q - np.eye(K + 1))) < 1e-12
+    A = sp.csr_matrix(tuple(reversed(dA.download())), shape=dA.shape)
+    B = sp.csr_matrix(tuple(reversed(dB.download())), shape=dB.shape)
+    MQ = B @ (A @ Q[:, :K]) + lam * Q[:, :K]
+    R = MQ - Q @ H2
+    assert np.max(np.linalg.norm(R, axis=0) / np.linalg.norm(MQ, axis=0)) < 1e-12
