@@ -31,6 +31,8 @@ WORKLOADS = {
     "ct512_fan_180v_pixelB_k200": dict(N=512, n_views=180, geometry="fan", maxit=200),
     "ct256_fan_180v_pixelB_k100": dict(N=256, n_views=180, geometry="fan", maxit=100),
     "ct64_par_180v_pixelB_k80": dict(N=64, n_views=180, geometry="parallel", maxit=80),
+    # BASELINE configs[4]: 2048^2, 3600 views x 2896 detectors (19 G + 30 G non-zeros): 8 GPUs only
+    "ct2048_par_3600v_pixelB_k200": dict(N=2048, n_views=3600, geometry="parallel", maxit=200),
 }
 LAMBDA = 1e-2  # run_2D_phantom.m:8
 NOISE = 0.01   # BASELINE config 1
@@ -117,9 +119,12 @@ def build_workload(hg, ctx, name, rank=0, world=1, dist=None, order="natural"):
         # n-space in tile x tile pixel blocks (hg_matrix_permute): A(:,q), B(q,:), x_true(q)
         from hybrid_gmres_b200.ct import tile_permutation
         q = tile_permutation(N, int(order[4:]))
-        dA2, dB2 = dA.permute(None, q), dB.permute(q, None)
+        dA2 = dA.permute(None, q, sort=False)
         dA.close()
+        ctx.trim()  # the shards of configs[4] are tens of GB: do not keep released copies cached
+        dB2 = dB.permute(q, None)
         dB.close()
+        ctx.trim()
         dA, dB, x_true = dA2, dB2, np.ascontiguousarray(x_true[q])
     return dA, dB, b, x_true, w["maxit"]
 
