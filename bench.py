@@ -91,19 +91,21 @@ class ClockSampler:
 
 
 def build_workload(hg, ctx, name, rank=0, world=1, dist=None, order="natural"):
-    """Matrices are generated on the device.  world > 1: this rank's detector-row block A_p and
-    the matching column block B^p; b is the matching slice."""
+    """Matrices are generated on the device.  world > 1: this rank's detector rows (whole views) A_p and
+    the matching columns B^p; b is the matching part of the sinogram."""
     w = WORKLOADS[name]
     N, nv, geom = w["N"], w["n_views"], w["geometry"]
     angles = np.arange(nv) * ((360.0 if geom == "fan" else 180.0) / nv)
     p = int(round(math.sqrt(2.0) * N))
-    from hybrid_gmres_b200.ct import ct_backprojector_cols, ct_projector_rows, shepp_logan
-    from hybrid_gmres_b200.sharding import uniform_row_blocks
+    from hybrid_gmres_b200.ct import ct_backprojector, ct_projector, shepp_logan
     m = nv * p
-    bounds = uniform_row_blocks(m, world)  # every view carries ~the same nnz: equal ray counts balance nnz
-    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    dA = ct_projector_rows(N, angles, p, geom, lo, hi, ctx=ctx)
-    dB = ct_backprojector_cols(N, angles, p, geom, lo, hi, ctx=ctx)
+    # rank r owns the views r, r+P, r+2P, ... (whole detector rows of the sinogram): every rank sees the
+    # same mix of ray directions, so the gather-bound projector product takes the same time on every rank
+    # (contiguous view blocks left ranks waiting ~10 % of the step at 2048^2) and every view carries the
+    # same number of non-zeros, so the blocks are nnz balanced
+    mine = np.arange(rank, nv, world)
+    dA = ct_projector(N, angles[mine], p, geom, ctx=ctx)
+    dB = ct_backprojector(N, angles[mine], p, geom, ctx=ctx)
     x_true = shepp_logan(N)
     b_exact = dA.matvec(x_true)
     rng = np.random.default_rng(0)
@@ -114,7 +116,8 @@ def build_workload(hg, ctx, name, rank=0, world=1, dist=None, order="natural"):
         t = torch.tensor([nb2], device="cuda", dtype=torch.float64)
         dist.all_reduce(t)
         nb2 = float(t.item())
-    b = b_exact + NOISE * math.sqrt(nb2) * e[lo:hi] / np.linalg.norm(e)  # run_2D_phantom.m:18-19
+    e_mine = e.reshape(nv, p)[mine].ravel()
+    b = b_exact + NOISE * math.sqrt(nb2) * e_mine / np.linalg.norm(e)  # run_2D_phantom.m:18-19
     if order.startswith("tile"):
         # n-space in tile x tile pixel blocks (hg_matrix_permute): A(:,q), B(q,:), x_true(q)
         from hybrid_gmres_b200.ct import tile_permutation
@@ -184,7 +187,13 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    stream = torch.cuda.current_stream().cuda_stream
+    # The library launches on the stream it is given; torch's events only see torch's current stream.  The
+    # legacy default stream has handle 0 (the library would then create its own non-blocking stream, which
+    # events on the default stream do not wait for), so make an explicit stream current and hand it over.
+    bench_stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(bench_stream)
+    stream = bench_stream.cuda_stream
+    assert stream != 0
     ctx = hg.Context(local_rank, stream=stream)
     if args.impl == "reference":
         dA, dB, b, x_true, maxit = build_workload(hg, ctx, args.workload)
@@ -240,7 +249,7 @@ def main():
         peer = comm.transport.startswith("peer")
         config["transport"] = comm.transport
         config["parallelism"] = (
-            f"A row-sharded / B column-sharded x{world}; per step: reduce-scatter pulled over NVLink peer memory by "
+            f"A row-sharded by whole views (rank r: views r, r+{world}, ...) / B column-sharded x{world}; per step: reduce-scatter pulled over NVLink peer memory by "
             "the first CGS2 multi-dot, 3 one-shot all-reduces inside the second-stage reductions, all-gather "
             "pushed by the normalisation kernel (no NCCL call on the step)" if peer else
             f"A row-sharded / B column-sharded x{world}, NCCL reduce-scatter + all-gather + 3 all-reduce per step")

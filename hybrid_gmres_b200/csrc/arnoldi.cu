@@ -263,11 +263,14 @@ extern "C" int hg_arnoldi_get_q(hg_arnoldi* a, int j, double* q) {
 
 extern "C" int hg_arnoldi_step_bytes(hg_arnoldi* a, int k, double* bytes) {
     HG_REQUIRE(a && bytes, "hg_arnoldi_step_bytes: NULL");
-    // S(k) = 12(nnzA+nnzB) + pw(m+n+2) + 16 m + 88 n + 32 k n  (n-space;
-    // m-space swaps the vector terms), pw = 8.
+    // S(k) = matrix streams + 16 m + 88 n + CGS2(k) (n-space; m-space swaps the vector
+    // terms).  Matrix streams: (8 + iw) bytes per entry + pointers in the form each matrix runs with
+    // (iw = 4, or 2 + base words for the sliced form with 16-bit offsets).  CGS2(k) = 32 k n with
+    // separate update / multi-dot kernels, 24 k n when the middle stage is the one-pass staged kernel.
     const double nq = (double)a->nq, nt = (double)a->nt;
-    *bytes = 12.0 * ((double)a->A->nnz + (double)a->B->nnz) + 8.0 * (nq + nt + 2.0) + 16.0 * nt +
-             88.0 * nq + 32.0 * (double)k * nq;
+    const bool one_pass = hg_cgs_fused_mode() == 2 && hg_cgs_staged_nparts(a->ctx, a->nq, k) > 0;
+    *bytes = hg_spmv_stream_bytes(a->A) + hg_spmv_stream_bytes(a->B) + 16.0 * nt + 88.0 * nq +
+             (one_pass ? 24.0 : 32.0) * (double)k * nq;
     return HG_OK;
 }
 

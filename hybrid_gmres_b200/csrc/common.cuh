@@ -166,6 +166,8 @@ struct hg_spmv_epilogue {
 int hg_k_spmv(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
               const hg_spmv_epilogue& ep, int* nparts);
 
+double hg_spmv_stream_bytes(const hg_matrix* m);  // (8 + index bytes) per entry + pointers, as stored
+
 // partials[j*nslabs + slab] = sum over slab rows V[r,j]*w[r];  returns nslabs
 int hg_k_multidot(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* w,
                   double* partials, int* nslabs);

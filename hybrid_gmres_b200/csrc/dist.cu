@@ -420,10 +420,11 @@ extern "C" int hg_darnoldi_get_q(hg_darnoldi* a, int j, double* q_slice, int64_t
 
 extern "C" int hg_darnoldi_step_bytes(hg_darnoldi* a, int k, double* bytes) {
     HG_REQUIRE(a && bytes, "hg_darnoldi_step_bytes: NULL");
-    // this rank's share of S(k) plus the replicated q / partial w vectors
+    // this rank's share of S(k) (hg_arnoldi_step_bytes) plus the replicated q / partial w vectors
     const double np = (double)a->n_p, mp = (double)a->m_p, n = (double)a->n_pad;
-    *bytes = 12.0 * ((double)a->A->nnz + (double)a->B->nnz) + 8.0 * (mp + n + 2.0) + 16.0 * mp + 16.0 * n +
-             72.0 * np + 32.0 * (double)k * np;
+    const bool one_pass = a->peer && hg_cgs_fused_mode() == 2 && hg_cgs_staged_nparts(a->ctx, a->n_p, k) > 0;
+    *bytes = hg_spmv_stream_bytes(a->A) + hg_spmv_stream_bytes(a->B) + 16.0 * mp + 16.0 * n + 72.0 * np +
+             (one_pass ? 24.0 : 32.0) * (double)k * np;
     return HG_OK;
 }
 

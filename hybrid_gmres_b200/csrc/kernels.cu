@@ -494,6 +494,12 @@ static double spmv_bytes(const hg_matrix* m, const hg_spmv_epilogue& ep, bool st
     return b;
 }
 
+// matrix-stream bytes of one product with m in the form it runs with (values + indices + pointers)
+double hg_spmv_stream_bytes(const hg_matrix* m) {
+    hg_spmv_epilogue ep;
+    return spmv_bytes(m, ep, false) - 8.0 * (double)m->cols;
+}
+
 int hg_k_spmv(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
               const hg_spmv_epilogue& ep, int* nparts) {
     if (nparts) *nparts = 0;
