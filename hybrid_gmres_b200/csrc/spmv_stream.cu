@@ -257,7 +257,7 @@ static int g_cgs_alternate = -1;
 bool hg_cgs_alternate() {
     if (g_cgs_alternate < 0) {
         const char* e = getenv("HG_CGS_ALTERNATE");
-        g_cgs_alternate = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured neutral on B200 (647.5 vs 649.1 it/s)
+        g_cgs_alternate = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured neutral on B200
     }
     return g_cgs_alternate != 0;
 }

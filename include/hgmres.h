@@ -67,12 +67,12 @@ int hg_version(void);
  * row-per-warp CSR SpMV, 2 force the TMA-staged streaming SpMV, 3 force the sliced form.
  * "cgs_fused" / env HG_CGS_FUSED: the first CGS2 update and the second-pass dot products in one pass
  * over the basis (it crosses HBM three times per step instead of four).  2 (default): tiles staged in
- * shared memory by cp.async, persistent CTAs (csrc/cgs_staged.cu; 680 -> 728 it/s on the headline
+ * shared memory by cp.async, persistent CTAs (csrc/cgs_staged.cu; 599 -> 634 it/s on the headline
  * workload); 1: the first attempt that re-reads the tile from L2 (slower than the separate kernels,
  * profiles/r01_cgs_fusion.md); 0: separate update and multi-dot kernels.
  * "cgs_alternate": 0 (default; env HG_CGS_ALTERNATE=1 enables) the CGS2 update kernels walk the rows
  * from the end, so each sweep over the basis starts on the ~100 MB the previous one left in L2
- * (measured neutral on B200: 647.5 vs 649.1 it/s).
+ * (measured neutral on B200).
  * "dist_transport": see hg_comm_transport. */
 int hg_set_option(const char* name, int value);
 
