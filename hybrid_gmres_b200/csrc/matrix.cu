@@ -215,6 +215,12 @@ void hg_matrix_pick_tpr(hg_matrix* m) {
     else if (mean >= 24) tpr = 16;
     else if (mean >= 12) tpr = 8;
     else if (mean >= 6) tpr = 4;
+    static const int forced = [] {
+        const char* e = getenv("HG_TPR");  // experiments: threads per row of the CSR kernel (2..32)
+        const int v = e ? atoi(e) : 0;
+        return (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
+    }();
+    if (forced) tpr = forced;
     m->tpr = tpr;
 }
 
