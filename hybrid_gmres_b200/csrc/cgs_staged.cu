@@ -12,7 +12,9 @@
 //
 // Work split: warp w owns the columns j = w, w+8, ...; lane l owns rows l, l+32, ... of the tile, so
 // every shared-memory read is conflict free and the phase-B sums stay in registers across all tiles
-// of the CTA (one warp reduction per column at the very end).  Reductions are in a fixed order:
+// of the CTA (one warp reduction per column at the very end).  Phase B takes its operands from the
+// registers phase A loaded them into (KEEP), so the tile is read from shared memory once.
+// Reductions are in a fixed order:
 // reruns are bit-identical.
 #include <algorithm>
 
@@ -54,7 +56,7 @@ inline Plan make_plan(int k, int NP) {
 
 // CPW: columns per warp (k <= 16*CPW); NP: row pairs per lane (tile rows TR = 64*NP; lane l owns rows
 // 64p + 2l, 64p + 2l + 1: one 16-byte shared-memory load per column and pair)
-template <int CPW, int NP>
+template <int CPW, int NP, bool KEEP>
 __global__ void __launch_bounds__(kThreads, 1)
 cgs_mid_staged_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
                       const double* __restrict__ h, const double* __restrict__ w0,
@@ -117,6 +119,7 @@ cgs_mid_staged_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k
         double2 pa[NP];
 #pragma unroll
         for (int p = 0; p < NP; ++p) pa[p] = make_double2(0.0, 0.0);
+        double2 keep[KEEP ? CPW : 1][KEEP ? NP : 1];  // KEEP: phase B re-uses the operands from registers
 #pragma unroll
         for (int c = 0; c < CPW; ++c) {
             const int j = warp + kWarps * c;
@@ -126,6 +129,7 @@ cgs_mid_staged_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k
 #pragma unroll
                 for (int p = 0; p < NP; ++p) {
                     const double2 v = col[32 * p];
+                    if (KEEP) keep[KEEP ? c : 0][KEEP ? p : 0] = v;
                     pa[p].x = fma(hj, v.x, pa[p].x);
                     pa[p].y = fma(hj, v.y, pa[p].y);
                 }
@@ -158,7 +162,7 @@ cgs_mid_staged_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k
                 const double2* col = reinterpret_cast<const double2*>(sv + (size_t)j * TR) + lane;
 #pragma unroll
                 for (int p = 0; p < NP; ++p) {
-                    const double2 v = col[32 * p];
+                    const double2 v = KEEP ? keep[KEEP ? c : 0][KEEP ? p : 0] : col[32 * p];
                     // a pair straddling n: its first row is real, its second is padding
                     const bool first = r0 + 64 * p + 2 * lane < n;
                     accB[c] = fma(first ? v.x : 0.0, wv[p].x, accB[c]);
@@ -180,18 +184,18 @@ cgs_mid_staged_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k
     }
 }
 
-template <int CPW, int NP>
+template <int CPW, int NP, bool KEEP>
 int launch(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* h, const double* w0,
            double* w1, double* partials, int grid) {
     const Plan p = make_plan(k, NP);
     const int ntiles = (int)((n + p.TR - 1) / p.TR);
     static bool attr_set = false;
     if (!attr_set) {
-        HG_CUDA(cudaFuncSetAttribute(cgs_mid_staged_kernel<CPW, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        HG_CUDA(cudaFuncSetAttribute(cgs_mid_staged_kernel<CPW, NP, KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024));
         attr_set = true;
     }
-    cgs_mid_staged_kernel<CPW, NP><<<grid, kThreads, p.total, ctx->stream>>>(V, ld, n, k, h, w0, w1, partials, ntiles);
+    cgs_mid_staged_kernel<CPW, NP, KEEP><<<grid, kThreads, p.total, ctx->stream>>>(V, ld, n, k, h, w0, w1, partials, ntiles);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }
@@ -212,7 +216,7 @@ int hg_k_cgs_mid_staged(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int
     if (nparts) *nparts = grid;
     // algorithmic bytes: V once, w0 in, w1 out
     hg_launch_scope scope(ctx, HG_K_LINCOMB, 8.0 * (double)n * (double)k + 16.0 * (double)n);
-    if (k <= 40) return launch<3, 4>(ctx, V, ld, n, k, h, w0, w1, partials, grid);   // 256-row tiles
-    if (k <= 88) return launch<6, 2>(ctx, V, ld, n, k, h, w0, w1, partials, grid);   // 128-row tiles
-    return launch<13, 1>(ctx, V, ld, n, k, h, w0, w1, partials, grid);               // 64-row tiles
+    if (k <= 40) return launch<3, 4, true>(ctx, V, ld, n, k, h, w0, w1, partials, grid);   // 256-row tiles
+    if (k <= 88) return launch<6, 2, true>(ctx, V, ld, n, k, h, w0, w1, partials, grid);   // 128-row tiles
+    return launch<13, 1, true>(ctx, V, ld, n, k, h, w0, w1, partials, grid);               // 64-row tiles
 }
