@@ -110,3 +110,44 @@ def test_backprojector_row_sums_count_views(hg, ctx, N, nviews):
     assert np.linalg.norm(yq - yu[q]) <= 1e-12 * np.linalg.norm(yu)
     Bq.close()
     ctx.trim()
+
+
+def test_config3_512_solver_equivalences(hg, ctx):
+    """BASELINE configs[2] at its real size (512^2, the run_equivalence_plots shape with the matched
+    B = A'): the relations the reference's figure titles state (run_equivalence_plots.m:33,44), between
+    solvers that share no code path beyond the kernels — BA-GMRES == LSMR and AB-GMRES == LSQR on the
+    first iterations — and the identity found in the survey (App. A): RTP hybrid AB-GMRES with matched B
+    is hybrid LSQR.  60 M non-zeros per matrix; A' is built by the device transposition."""
+    from hybrid_gmres_b200.ct import ct_projector, shepp_logan
+    N = 512
+    angles = np.arange(180) * 1.0
+    p = int(round(math.sqrt(2.0) * N))
+    A = ct_projector(N, angles, p, "parallel", ctx=ctx)
+    At = A.transpose()
+    x_true = shepp_logan(N)
+    b = A.matvec(x_true)
+    e = np.random.default_rng(0).standard_normal(b.shape[0])
+    b = b + 0.01 * np.linalg.norm(b) * e / np.linalg.norm(e)
+
+    def X(f, *a, **kw):
+        ex = {}
+        f(*a, ctx=ctx, extras=ex, **kw)
+        return ex["X"]
+
+    def rel(P, Q):
+        return np.array([np.linalg.norm(P[:, i] - Q[:, i]) / np.linalg.norm(Q[:, i]) for i in range(min(P.shape[1], Q.shape[1]))])
+
+    K = 4
+    ba, lsmr = X(hg.BAgmres_nonhybrid_bounds, A, At, b, x_true, 0.0, K), X(hg.lsmr_solver, A, b, x_true, 0.0, K, At=At)
+    ab, lsqr = X(hg.ABgmres_nonhybrid_bounds, A, At, b, x_true, 0.0, K), X(hg.lsqr_solver, A, b, x_true, 0.0, K, At=At)
+    assert np.max(rel(ba, lsmr)) < 1e-8, rel(ba, lsmr)
+    assert np.max(rel(ab, lsqr)) < 1e-8, rel(ab, lsqr)
+    rtp = X(hg.hybrid_ab_gmres_rtp, A, At, b, x_true, 0.0, K, 1e-2)
+    hlsqr = X(hg.hybrid_lsqr_solver, A, b, x_true, 0.0, K, 1e-2, At=At)
+    assert np.max(rel(rtp, hlsqr)) < 1e-8, rel(rtp, hlsqr)
+    ptr = X(hg.ABgmres_hybrid_bounds, A, At, b, x_true, 0.0, K, 1e-2)
+    # PTR != RTP (run_ptr_rtp_comparison.m:29,39): small here (lambda = 1e-2 is far below the large singular
+    # values of a CT operator) but well above the level at which the equivalent pairs agree
+    assert np.min(rel(ptr, rtp)[1:]) > 20 * max(np.max(rel(rtp, hlsqr)), 1e-9)
+    A.close(), At.close()
+    ctx.trim()
