@@ -196,3 +196,30 @@ def test_gcv_surface_host_matches_oracle():
         assert surf.shape == surf_o.shape
         assert np.allclose(surf, surf_o, rtol=1e-6, atol=0)
         assert np.array_equal(path, path_o)
+
+
+def test_tile_permutation_keeps_tiles_contiguous():
+    """ct.tile_permutation: perm[new] = old column-major pixel index; every run of tile*tile new
+    indices is one tile x tile block of the image (one 128-byte line for tile = 4)."""
+    from hybrid_gmres_b200.ct import tile_permutation
+    for N, tile in ((8, 4), (16, 4), (16, 8), (12, 4)):
+        q = tile_permutation(N, tile)
+        assert q.dtype == np.int32 and sorted(q.tolist()) == list(range(N * N))
+        for t in range(N * N // (tile * tile)):
+            old = q[t * tile * tile:(t + 1) * tile * tile]
+            rows, cols = old % N, old // N  # column-major: index = row + N*col
+            assert rows.max() - rows.min() == tile - 1 and cols.max() - cols.min() == tile - 1
+            assert rows.min() % tile == 0 and cols.min() % tile == 0
+    with pytest.raises(ValueError):
+        tile_permutation(10, 4)
+
+
+def test_bench_view_interleave_covers_every_view_once():
+    """bench.build_workload gives rank r the views r, r+P, ...: a partition of the views whose parts
+    differ by at most one view (nnz balance) and share the same mix of directions."""
+    for nv, P in ((180, 1), (180, 2), (180, 8), (3600, 8), (181, 4)):
+        parts = [np.arange(r, nv, P) for r in range(P)]
+        allv = np.sort(np.concatenate(parts))
+        assert np.array_equal(allv, np.arange(nv))
+        sizes = [len(p) for p in parts]
+        assert max(sizes) - min(sizes) <= 1
