@@ -173,7 +173,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    K, W = args.steps, max(args.warmup, 0)
+    K, W = max(args.steps, 1), max(args.warmup, 3)  # never fewer than 3 warm-up cycles (reported as run)
 
     if args.impl == "reference" and rank != 0:
         return 0
