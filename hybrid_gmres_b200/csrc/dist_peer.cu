@@ -388,8 +388,9 @@ static bool ensure_ws(hg_comm* c, size_t bytes) {
     } else if (cudaStreamSynchronize(st) != cudaSuccess) {
         ok = 0.0;
     }
-    if (ok == 0.0) {
+    if (ok == 0.0) {  // the same verdict on every rank (all-reduced above)
         close_peers(c);
+        if (P > 1) hg_nccl_barrier(c, st);  // nobody frees memory a peer still has mapped
         if (c->ws) cudaFree(c->ws);
         c->ws = nullptr;
         c->ws_bytes = 0;
