@@ -20,7 +20,7 @@ the outputs as ``tests/golden/ref_*.npz``.  ``tests/test_reference_golden.py`` h
 restatement to those outputs (same stopping iterations and history lengths, H / iterates /
 histories <= 1e-10 on the CT cases, the `==0` breakdown epilogue exactly) and re-executes the
 reference on every CPU run in the build container to prove the fixtures' provenance.
-What remains unpinned, and is stated as such: MATLAB's BUILT-INS (``*``, ``norm``, ``\``, ``svd``,
+What remains unpinned, and is stated as such: MATLAB's BUILT-INS (``*``, ``norm``, ``mldivide``, ``svd``,
 ``eig``, ``fminbnd``) are NumPy/SciPy/LAPACK here, chosen after MATLAB's documented algorithms, so
 rounding-level differences against MathWorks' kernels are possible; the un-vendored third-party
 generators (``shaw``/``heat``/``deriv2``, ``PRtomo_mismatched``) are restated from their published
