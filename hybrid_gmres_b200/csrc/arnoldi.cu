@@ -9,6 +9,15 @@
 
 int hg_multidot_nslabs(const hg_ctx* ctx, int64_t n);
 
+// wall-clock breakdown of the last whole-solver call on this thread (hg_last_solve_stats)
+thread_local double g_solve_stats[8] = {0};
+
+extern "C" int hg_last_solve_stats(double* out, int n) {
+    HG_REQUIRE(out && n >= 0, "hg_last_solve_stats: bad argument");
+    for (int i = 0; i < n; ++i) out[i] = i < 8 ? g_solve_stats[i] : 0.0;
+    return HG_OK;
+}
+
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 struct hg_arnoldi {
@@ -96,7 +105,7 @@ extern "C" int hg_arnoldi_create(hg_ctx* ctx, const hg_matrix* A, const hg_matri
     const int nslabs = hg_multidot_nslabs(ctx, std::max(a->nq, a->nt));
     const size_t npart = (size_t)(kmax + 2) *
                          (size_t)(std::max(nslabs, hg_update_dot_ntiles(std::max(a->nq, a->nt))) + 1);
-    const size_t nstat = (size_t)std::max(a->nq, a->nt) / 8 + 1024;
+    const size_t nstat = hg_stat_capacity(ctx, std::max(a->nq, a->nt));
     cudaError_t e = cudaSuccess;
     auto alloc = [&](double** p, size_t n) {
         if (e == cudaSuccess) e = hg_dmalloc(ctx, p, std::max<size_t>(n, 1) * sizeof(double));
@@ -305,6 +314,21 @@ struct PinBuf {
     }
 };
 
+struct EventRing {
+    std::vector<cudaEvent_t> e;
+    ~EventRing() {
+        for (cudaEvent_t x : e) cudaEventDestroy(x);
+    }
+    int create(int n) {
+        for (int i = 0; i < n; ++i) {
+            cudaEvent_t x;
+            HG_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+            e.push_back(x);
+        }
+        return HG_OK;
+    }
+};
+
 struct ArnoldiHolder {
     hg_arnoldi* a = nullptr;
     ~ArnoldiHolder() { hg_arnoldi_destroy(a); }
@@ -335,19 +359,27 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     hg_arnoldi* a = holder.a;
     const double t_created = now();
     hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
-    DBuf d_x, d_xt, d_y, d_g, stat_e, stat_r;
+    // The loop is software pipelined (see below): iterates alternate between two buffers, and every
+    // host-visible result of an iteration has RING slots so that a slot is rewritten only after the
+    // host has consumed it.
+    constexpr int RING = 4;
+    DBuf d_x[2], d_xt, d_y, d_g, stat_e, stat_r;
     PinBuf h_y, h_g, h_s;
-    HG_TRY(d_x.alloc((size_t)n));
+    EventRing ev;
+    HG_TRY(ev.create(RING));
+    HG_TRY(d_x[0].alloc((size_t)n));
+    HG_TRY(d_x[1].alloc((size_t)n));
     HG_TRY(d_xt.alloc((size_t)n));
     HG_TRY(d_y.alloc((size_t)maxit + 1));
     HG_TRY(d_g.alloc((size_t)maxit + 2));
-    HG_TRY(stat_e.alloc((size_t)std::max(n, m) / 8 + 1024));
-    HG_TRY(stat_r.alloc((size_t)std::max(n, m) / 8 + 1024));
-    HG_TRY(h_y.alloc((size_t)maxit + 1));
-    HG_TRY(h_g.alloc((size_t)maxit + 2));
-    HG_TRY(h_s.alloc(8));
+    HG_TRY(stat_e.alloc(hg_stat_capacity(ctx, std::max(n, m))));
+    HG_TRY(stat_r.alloc(hg_stat_capacity(ctx, std::max(n, m))));
+    HG_TRY(h_y.alloc((size_t)RING * (maxit + 1)));
+    HG_TRY(h_g.alloc((size_t)RING * (maxit + 2)));
+    HG_TRY(h_s.alloc((size_t)RING * 2));
     const double t_bufs = now();
-    HG_CUDA(cudaMemsetAsync(d_x.p, 0, (size_t)n * 8, ctx->stream));
+    HG_CUDA(cudaMemsetAsync(d_x[0].p, 0, (size_t)n * 8, ctx->stream));
+    HG_CUDA(cudaMemsetAsync(d_x[1].p, 0, (size_t)n * 8, ctx->stream));
     HG_CUDA(cudaMemcpyAsync(d_xt.p, x_true, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     HG_TRY(hg_arnoldi_set_rhs(a, b));
     double nb2 = 0, nx2 = 0;
@@ -374,50 +406,98 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
         Gfull.assign((size_t)maxit * maxit, 0.0);
         rhs.assign(maxit, 0.0);
     }
-    bool have_x = (kind == RTP_BA);  // BA initialises x = zeros (hybrid_ba_gmres_rtp.m:4)
-    int k = 0;
     const int ldh = a->ldh();
-    for (k = 1; k <= maxit; ++k) {
+
+    // ---- software-pipelined loop --------------------------------------------------------------
+    // Arnoldi step k+1 does not depend on y_k, so it is queued BEFORE the host looks at step k:
+    //   stream:  step 1 | step 2 | iterate 1 | step 3 | iterate 2 | ...
+    //   host  :  waits for "iterate k-1 done" (which implies step k done), solves the projected
+    //            problem of step k while the device runs step k+1, queues iterate k behind it.
+    // The reference's control flow is kept exactly: the stop rule of iteration k-1 (:38 / :35) is
+    // applied before anything of iteration k is looked at, the `== 0` breakdown of step k (:25)
+    // leaves before x / histories of iteration k exist; at most one queued step + one iterate are
+    // discarded when the loop ends early.
+    int enq = 0;         // Arnoldi steps queued so far
+    int last_x = 0;      // last iteration whose iterate exists (0: none; BA then returns its zeros, :4)
+    auto queue_step = [&](int kk) -> int {
         HG_TRY(hg_arnoldi_steps(a, 1));
         if (kind == RTP_AB) {
             // Gram column of W = A*Q_k against [b, W]: one stream over the cached columns
             // replaces `AQk = A*Qk; AQk'*AQk; AQk'*b` (hybrid_ab_gmres_rtp.m:31-32)
             int ns = 0;
-            HG_TRY(hg_k_multidot(ctx, a->T, a->ldt, m, k + 1, a->T + (size_t)k * a->ldt, a->partials, &ns));
-            HG_TRY(hg_k_reduce(ctx, a->partials, ns, k + 1, d_g.p, false, nullptr, false));
-            HG_CUDA(cudaMemcpyAsync(h_g.p, d_g.p, (size_t)(k + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            HG_TRY(hg_k_multidot(ctx, a->T, a->ldt, m, kk + 1, a->T + (size_t)kk * a->ldt, a->partials, &ns));
+            HG_TRY(hg_k_reduce(ctx, a->partials, ns, kk + 1, d_g.p, false, nullptr, false));
+            HG_CUDA(cudaMemcpyAsync(h_g.p + (size_t)(kk % RING) * (maxit + 2), d_g.p, (size_t)(kk + 1) * 8,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
         }
-        double tw = now();
-        HG_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (kk == 1) HG_CUDA(cudaEventRecord(ev.e[0], ctx->stream));
+        return HG_OK;
+    };
+    auto finish_iterate = [&](int j, bool* stop) -> int {  // histories of iteration j, stop rule
+        const double tw = now();
+        HG_CUDA(cudaEventSynchronize(ev.e[j % RING]));
         t_wait += now() - tw;
+        const double* hs = h_s.p + (size_t)(j % RING) * 2;
+        residual_norm[j - 1] = hs[1] / norm_b;
+        error_norm[j - 1] = hs[0] / norm_xt;
+        last_x = j;
+        *stop = residual_norm[j - 1] <= tol;  // :38 / :35
+        return HG_OK;
+    };
+    int k = 0;
+    bool ended_early = false;
+    for (k = 1; k <= maxit; ++k) {
+        while (enq < std::min(k + 1, maxit)) {
+            ++enq;
+            HG_TRY(queue_step(enq));
+        }
+        if (k == 1) {
+            const double tw = now();
+            HG_CUDA(cudaEventSynchronize(ev.e[0]));
+            t_wait += now() - tw;
+        } else {
+            bool stop = false;
+            HG_TRY(finish_iterate(k - 1, &stop));
+            if (stop) {
+                k = k - 1;
+                ended_early = true;
+                break;
+            }
+        }
         const double th = now();
         const double* hcol = a->h_H + (size_t)(k - 1) * ldh;
-        if (hcol[k] == 0.0) break;  // :25 — leaves before x / histories are touched
+        if (hcol[k] == 0.0) {  // :25 — leaves before x / histories are touched
+            ended_early = true;
+            break;
+        }
+        double* yk = h_y.p + (size_t)(k % RING) * (maxit + 1);
         if (kind == RTP_BA) {
             ls.add_column(hcol);  // yk = H(1:k+1,1:k) \ [beta;0]   (hybrid_ba_gmres_rtp.m:28-29)
-            ls.solve(h_y.p);
+            ls.solve(yk);
         } else {
-            rhs[k - 1] = h_g.p[0];
+            const double* g = h_g.p + (size_t)(k % RING) * (maxit + 2);
+            rhs[k - 1] = g[0];
             for (int j = 0; j < k; ++j) {
-                Gfull[(size_t)(k - 1) * maxit + j] = h_g.p[1 + j];
-                Gfull[(size_t)j * maxit + (k - 1)] = h_g.p[1 + j];
+                Gfull[(size_t)(k - 1) * maxit + j] = g[1 + j];
+                Gfull[(size_t)j * maxit + (k - 1)] = g[1 + j];
             }
-            if (chol_ok) chol_ok = chol.add_row(h_g.p + 1);
+            if (chol_ok) chol_ok = chol.add_row(g + 1);
             if (chol_ok) {
-                chol.solve(rhs.data(), h_y.p);
+                chol.solve(rhs.data(), yk);
             } else {  // mldivide's non-SPD path
                 std::vector<double> M((size_t)k * k);
                 for (int j = 0; j < k; ++j)
                     for (int i2 = 0; i2 < k; ++i2)
                         M[(size_t)j * k + i2] = Gfull[(size_t)j * maxit + i2] + (i2 == j ? lambda : 0.0);
-                hgd::solve_square(k, M.data(), k, rhs.data(), h_y.p);
+                hgd::solve_square(k, M.data(), k, rhs.data(), yk);
             }
         }
         t_host += now() - th;
-        HG_CUDA(cudaMemcpyAsync(d_y.p, h_y.p, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+        HG_CUDA(cudaMemcpyAsync(d_y.p, yk, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
         // x = Q(:,1:k)*yk fused with ||x - x_true||^2          (:33,36 / :30,33)
+        double* xk = d_x[k & 1].p;
         int np_e = 0, np_r = 0;
-        HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n, k, d_y.p, 1.0, nullptr, d_x.p, d_xt.p, stat_e.p, &np_e));
+        HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n, k, d_y.p, 1.0, nullptr, xk, d_xt.p, stat_e.p, &np_e));
         if (residual_mode == 0) {
             // ||b - A*x|| with A*x = (A*Q_k) yk from the cached columns
             HG_TRY(hg_k_lincomb(ctx, a->T + a->ldt, a->ldt, m, k, d_y.p, -1.0, a->d_b, nullptr, nullptr,
@@ -428,33 +508,45 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
             ep.z1 = a->d_b;
             ep.g1 = 1.0;
             ep.stat = stat_r.p;
-            HG_TRY(hg_k_spmv(ctx, A, d_x.p, nullptr, ep, &np_r));
+            HG_TRY(hg_k_spmv(ctx, A, xk, nullptr, ep, &np_r));
         }
         HG_TRY(hg_k_reduce(ctx, stat_e.p, np_e, 1, ctx->d_scalars + 1, false, nullptr, true));
         HG_TRY(hg_k_reduce(ctx, stat_r.p, np_r, 1, ctx->d_scalars + 2, false, nullptr, true));
-        HG_CUDA(cudaMemcpyAsync(h_s.p, ctx->d_scalars + 1, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        HG_CUDA(cudaMemcpyAsync(h_s.p + (size_t)(k % RING) * 2, ctx->d_scalars + 1, 16, cudaMemcpyDeviceToHost,
+                                ctx->stream));
         if (extras && extras->X_hist)
-            HG_CUDA(cudaMemcpyAsync(extras->X_hist + (size_t)(k - 1) * n, d_x.p, (size_t)n * 8,
+            HG_CUDA(cudaMemcpyAsync(extras->X_hist + (size_t)(k - 1) * n, xk, (size_t)n * 8,
                                     cudaMemcpyDeviceToHost, ctx->stream));
-        tw = now();
-        HG_CUDA(cudaStreamSynchronize(ctx->stream));
-        t_wait += now() - tw;
-        have_x = true;
-        residual_norm[k - 1] = h_s.p[1] / norm_b;
-        error_norm[k - 1] = h_s.p[0] / norm_xt;
-        if (residual_norm[k - 1] <= tol) break;  // :38 / :35
+        HG_CUDA(cudaEventRecord(ev.e[k % RING], ctx->stream));
     }
-    if (k > maxit) k = maxit;  // MATLAB leaves k at its last value
+    if (!ended_early) {  // MATLAB leaves k at its last value
+        k = maxit;
+        bool stop = false;
+        HG_TRY(finish_iterate(maxit, &stop));
+    }
     *niters = k;
-    HG_CUDA(cudaMemcpyAsync(x, d_x.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const bool have_x = (kind == RTP_BA) || last_x > 0;  // BA initialises x = zeros (hybrid_ba_gmres_rtp.m:4)
+    const double t_loop_end = now();
+    HG_CUDA(cudaMemcpyAsync(x, d_x[last_x & 1].p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(ctx->stream));  // also drains a discarded speculative step
+    g_solve_stats[0] = t_setup - t_begin;
+    g_solve_stats[1] = t_loop_end - t_setup;
+    g_solve_stats[2] = t_host;
+    g_solve_stats[3] = t_wait;
+    g_solve_stats[4] = now() - t_loop_end;
+    g_solve_stats[5] = (double)k;
     if (trace)
         fprintf(stderr, "[hg trace] rtp %s: setup %.1f ms, loop %.1f ms (host solve %.1f, gpu wait %.1f), k=%d\n",
                 kind == RTP_AB ? "AB" : "BA", t_setup - t_begin, now() - t_setup, t_host, t_wait, k);
     if (x_valid) *x_valid = have_x ? 1 : 0;
     if (extras) {
         if (extras->beta) *extras->beta = beta;
-        if (extras->H) memcpy(extras->H, a->h_H, (size_t)ldh * maxit * 8);
+        if (extras->H) {  // columns the reference never reached stay zero (a discarded speculative step wrote one)
+            memset(extras->H, 0, (size_t)ldh * maxit * 8);
+            memcpy(extras->H, a->h_H, (size_t)ldh * k * 8);
+        }
+        if (extras->X_hist && last_x < maxit)  // the discarded speculative iterate, if any
+            memset(extras->X_hist + (size_t)last_x * n, 0, (size_t)(maxit - last_x) * n * 8);
     }
     return HG_OK;
 }
@@ -643,8 +735,8 @@ extern "C" int hg_gmres_ptr(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* 
     HG_TRY(d_xt.alloc((size_t)n));
     HG_TRY(d_y.alloc((size_t)maxit + 1));
     HG_TRY(d_z.alloc((size_t)m));
-    HG_TRY(stat_e.alloc((size_t)std::max(n, m) / 8 + 1024));
-    HG_TRY(stat_r.alloc((size_t)std::max(n, m) / 8 + 1024));
+    HG_TRY(stat_e.alloc(hg_stat_capacity(ctx, std::max(n, m))));
+    HG_TRY(stat_r.alloc(hg_stat_capacity(ctx, std::max(n, m))));
     HG_TRY(h_y.alloc((size_t)maxit + 1));
     HG_TRY(h_s.alloc(8));
     HG_CUDA(cudaMemsetAsync(d_x.p, 0, (size_t)n * 8, ctx->stream));

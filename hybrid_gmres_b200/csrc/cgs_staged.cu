@@ -18,6 +18,8 @@
 // reruns are bit-identical.
 #include <algorithm>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace {
@@ -189,11 +191,13 @@ int launch(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const dou
            double* w1, double* partials, int grid) {
     const Plan p = make_plan(k, NP);
     const int ntiles = (int)((n + p.TR - 1) / p.TR);
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in is per device (and per template instance): one bit per device ordinal
+    static std::atomic<unsigned long long> attr_set{0};
+    const unsigned long long dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_set.load(std::memory_order_relaxed) & dev_bit)) {
         HG_CUDA(cudaFuncSetAttribute(cgs_mid_staged_kernel<CPW, NP, KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024));
-        attr_set = true;
+        attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
     cgs_mid_staged_kernel<CPW, NP, KEEP><<<grid, kThreads, p.total, ctx->stream>>>(V, ld, n, k, h, w0, w1, partials, ntiles);
     HG_CUDA(cudaGetLastError());

@@ -133,6 +133,12 @@ struct hg_matrix {
 constexpr int kNnzPad = 16;
 
 int hg_ensure_partials(hg_ctx* ctx, size_t ndoubles);
+// doubles a per-block `stat` partial buffer needs for a vector / SpMV of `rows` rows: the block kernels
+// write at most rows/8 + 1024 partials, the streaming SpMV one per work unit (sm_count * 8)
+inline size_t hg_stat_capacity(const hg_ctx* ctx, int64_t rows) {
+    const size_t a = (size_t)(rows > 0 ? rows : 0) / 8 + 1024, b = (size_t)ctx->sm_count * 16 + 64;
+    return a > b ? a : b;
+}
 int hg_matrix_alloc(hg_ctx* ctx, int64_t rows, int64_t cols, int64_t nnz, hg_matrix** out);
 void hg_matrix_pick_tpr(hg_matrix* m);
 
@@ -221,7 +227,7 @@ int hg_norm2_sync(hg_ctx* ctx, const double* x, int64_t n, double* out);
 // reduce `np` partials at ctx->d_partials into d_scalars[slot] (optionally sqrt)
 int hg_reduce_to_scalar(hg_ctx* ctx, int np, int slot, bool do_sqrt);
 
-// TMA-staged fused CGS2 middle stage (cgs_staged.cu): w1 = w0 - V h and partials = V^T w1 in one pass
+// shared-memory-staged (cp.async) fused CGS2 middle stage (cgs_staged.cu): w1 = w0 - V h and partials = V^T w1 in one pass
 // over V.  hg_cgs_staged_nparts: partials per column the kernel writes, 0 when (n, k) is out of range.
 int hg_cgs_staged_nparts(const hg_ctx* ctx, int64_t n, int k);
 int hg_k_cgs_mid_staged(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* h,

@@ -179,16 +179,24 @@ extern "C" int hg_ctx_create(int device, void* stream, hg_ctx** out) {
     }
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    cudaError_t ce = cudaSuccess;
     if (stream) {
         c->stream = (cudaStream_t)stream;
         c->own_stream = false;
     } else {
-        HG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        c->own_stream = true;
+        ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        c->own_stream = ce == cudaSuccess;
     }
-    HG_CUDA(cudaMalloc(&c->d_scalars, 64 * sizeof(double)));
-    HG_CUDA(cudaMemsetAsync(c->d_scalars, 0, 64 * sizeof(double), c->stream));
-    HG_CUDA(cudaMallocHost(&c->h_scalars, 64 * sizeof(double)));
+    if (ce == cudaSuccess) ce = cudaMalloc(&c->d_scalars, 64 * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(c->d_scalars, 0, 64 * sizeof(double), c->stream);
+    if (ce == cudaSuccess) ce = cudaMallocHost(&c->h_scalars, 64 * sizeof(double));
+    if (ce != cudaSuccess) {  // release what was created: no leak on the error path
+        hg_set_error("hg_ctx_create: %s", cudaGetErrorString(ce));
+        if (c->d_scalars) cudaFree(c->d_scalars);
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return HG_ERR_CUDA;
+    }
     *out = c;
     return HG_OK;
 }

@@ -483,13 +483,30 @@ extern "C" int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg
     const int64_t row0 = (int64_t)comm->rank * n_p;
     const int64_t nloc = std::max<int64_t>(0, std::min(n, row0 + n_p) - row0);
     hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
-    DBufD d_x, d_xt, d_y, d_g, stat_e, stat_r, d_xfull;
+    // software-pipelined like the single-GPU solver (arnoldi.cu: rtp_solver): step k+1 is queued before the
+    // host looks at step k; every rank takes the same decisions (the histories are bit-identical on all
+    // ranks), so all ranks queue the same kernel sequence.
+    constexpr int RING = 4;
+    DBufD d_x[2], d_xt, d_y, d_g, stat_e, stat_r, d_xfull;
     PinD h_y, h_g, h_s;
-    HG_TRY(d_x.alloc((size_t)n_p)); HG_TRY(d_xt.alloc((size_t)n_p)); HG_TRY(d_y.alloc((size_t)maxit + 1));
-    HG_TRY(d_g.alloc((size_t)maxit + 2)); HG_TRY(stat_e.alloc((size_t)std::max(n_p, m_p) / 8 + 2048));
-    HG_TRY(stat_r.alloc((size_t)std::max(n_p, m_p) / 8 + 2048)); HG_TRY(d_xfull.alloc((size_t)a->n_pad));
-    HG_TRY(h_y.alloc((size_t)maxit + 1)); HG_TRY(h_g.alloc((size_t)maxit + 2)); HG_TRY(h_s.alloc(8));
-    HG_CUDA(cudaMemsetAsync(d_x.p, 0, (size_t)n_p * 8, st));
+    std::vector<cudaEvent_t> ev(RING, nullptr);
+    struct EvGuard {
+        std::vector<cudaEvent_t>& e;
+        ~EvGuard() {
+            for (cudaEvent_t x : e)
+                if (x) cudaEventDestroy(x);
+        }
+    } ev_guard{ev};
+    for (int i = 0; i < RING; ++i) HG_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    HG_TRY(d_x[0].alloc((size_t)n_p)); HG_TRY(d_x[1].alloc((size_t)n_p)); HG_TRY(d_xt.alloc((size_t)n_p));
+    HG_TRY(d_y.alloc((size_t)maxit + 1));
+    HG_TRY(d_g.alloc((size_t)maxit + 2)); HG_TRY(stat_e.alloc(hg_stat_capacity(ctx, std::max(n_p, m_p)) + 1024));
+    HG_TRY(stat_r.alloc(hg_stat_capacity(ctx, std::max(n_p, m_p)) + 1024)); HG_TRY(d_xfull.alloc((size_t)a->n_pad));
+    HG_TRY(h_y.alloc((size_t)RING * (maxit + 1))); HG_TRY(h_g.alloc((size_t)RING * (maxit + 2)));
+    HG_TRY(h_s.alloc((size_t)RING * 2 + 4));
+    double* h_norms = h_s.p + (size_t)RING * 2;
+    HG_CUDA(cudaMemsetAsync(d_x[0].p, 0, (size_t)n_p * 8, st));
+    HG_CUDA(cudaMemsetAsync(d_x[1].p, 0, (size_t)n_p * 8, st));
     HG_CUDA(cudaMemsetAsync(d_xt.p, 0, (size_t)n_p * 8, st));
     if (nloc > 0)
         HG_CUDA(cudaMemcpyAsync(d_xt.p, x_true + row0, (size_t)nloc * 8, cudaMemcpyHostToDevice, st));
@@ -501,10 +518,10 @@ extern "C" int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg
     HG_TRY(hg_k_sumsq(ctx, d_xt.p, n_p, stat_r.p, &np));
     HG_TRY(hg_k_reduce(ctx, stat_r.p, np, 1, ctx->d_scalars + 4, false, nullptr, false));
     HG_NCCL(g_nccl.AllReduce(ctx->d_scalars + 3, ctx->d_scalars + 3, 2, ncclDouble, ncclSum, comm->comm, st));
-    HG_CUDA(cudaMemcpyAsync(h_s.p + 2, ctx->d_scalars + 3, 16, cudaMemcpyDeviceToHost, st));
+    HG_CUDA(cudaMemcpyAsync(h_norms, ctx->d_scalars + 3, 16, cudaMemcpyDeviceToHost, st));
     HG_TRY(hg_darnoldi_reset(a, lambda));
     HG_CUDA(cudaStreamSynchronize(st));
-    const double norm_b = std::sqrt(h_s.p[2]), norm_xt = std::sqrt(h_s.p[3]);
+    const double norm_b = std::sqrt(h_norms[0]), norm_xt = std::sqrt(h_norms[1]);
     const double beta = a->h_beta[0];
     for (int i = 0; i < maxit; ++i) error_norm[i] = residual_norm[i] = 0.0;
     hgd::HessenbergLS ls;
@@ -517,47 +534,83 @@ extern "C" int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg
         Gfull.assign((size_t)maxit * maxit, 0.0);
         rhs.assign(maxit, 0.0);
     }
-    bool have_x = (kind == 1);
     const int ldh = a->ldh();
-    int k;
-    for (k = 1; k <= maxit; ++k) {
+    int enq = 0, last_x = 0;
+    auto queue_step = [&](int kk) -> int {
         HG_TRY(hg_darnoldi_steps(a, 1));
         if (kind == 0) {
             int ns = 0;
-            HG_TRY(hg_k_multidot(ctx, a->T, a->ldt, m_p, k + 1, a->T + (size_t)k * a->ldt, a->partials, &ns));
+            HG_TRY(hg_k_multidot(ctx, a->T, a->ldt, m_p, kk + 1, a->T + (size_t)kk * a->ldt, a->partials, &ns));
             if (a->peer) {
-                HG_TRY(hg_k_reduce_allreduce(comm, a->partials, ns, k + 1, d_g.p, nullptr, false, false));
+                HG_TRY(hg_k_reduce_allreduce(comm, a->partials, ns, kk + 1, d_g.p, nullptr, false, false));
             } else {
-                HG_TRY(hg_k_reduce(ctx, a->partials, ns, k + 1, d_g.p, false, nullptr, false));
-                HG_NCCL(g_nccl.AllReduce(d_g.p, d_g.p, (size_t)(k + 1), ncclDouble, ncclSum, comm->comm, st));
+                HG_TRY(hg_k_reduce(ctx, a->partials, ns, kk + 1, d_g.p, false, nullptr, false));
+                HG_NCCL(g_nccl.AllReduce(d_g.p, d_g.p, (size_t)(kk + 1), ncclDouble, ncclSum, comm->comm, st));
             }
-            HG_CUDA(cudaMemcpyAsync(h_g.p, d_g.p, (size_t)(k + 1) * 8, cudaMemcpyDeviceToHost, st));
+            HG_CUDA(cudaMemcpyAsync(h_g.p + (size_t)(kk % RING) * (maxit + 2), d_g.p, (size_t)(kk + 1) * 8,
+                                    cudaMemcpyDeviceToHost, st));
         }
-        HG_CUDA(cudaStreamSynchronize(st));
+        if (kk == 1) HG_CUDA(cudaEventRecord(ev[0], st));
+        return HG_OK;
+    };
+    auto finish_iterate = [&](int j, bool* stop) -> int {
+        HG_CUDA(cudaEventSynchronize(ev[j % RING]));
+        if (a->peer) HG_TRY(hg_peer_check(comm));  // a lost rank ends the solve here, not after maxit time-outs
+        const double* hs = h_s.p + (size_t)(j % RING) * 2;
+        error_norm[j - 1] = std::sqrt(hs[0]) / norm_xt;
+        residual_norm[j - 1] = std::sqrt(hs[1]) / norm_b;
+        last_x = j;
+        *stop = residual_norm[j - 1] <= tol;
+        return HG_OK;
+    };
+    int k;
+    bool ended_early = false;
+    for (k = 1; k <= maxit; ++k) {
+        while (enq < std::min(k + 1, maxit)) {
+            ++enq;
+            HG_TRY(queue_step(enq));
+        }
+        if (k == 1) {
+            HG_CUDA(cudaEventSynchronize(ev[0]));
+        } else {
+            bool stop = false;
+            HG_TRY(finish_iterate(k - 1, &stop));
+            if (stop) {
+                k = k - 1;
+                ended_early = true;
+                break;
+            }
+        }
         const double* hcol = a->h_H + (size_t)(k - 1) * ldh;
-        if (hcol[k] == 0.0) break;
+        if (hcol[k] == 0.0) {
+            ended_early = true;
+            break;
+        }
+        double* yk = h_y.p + (size_t)(k % RING) * (maxit + 1);
         if (kind == 1) {
             ls.add_column(hcol);
-            ls.solve(h_y.p);
+            ls.solve(yk);
         } else {
-            rhs[k - 1] = h_g.p[0];
+            const double* g = h_g.p + (size_t)(k % RING) * (maxit + 2);
+            rhs[k - 1] = g[0];
             for (int j = 0; j < k; ++j) {
-                Gfull[(size_t)(k - 1) * maxit + j] = h_g.p[1 + j];
-                Gfull[(size_t)j * maxit + (k - 1)] = h_g.p[1 + j];
+                Gfull[(size_t)(k - 1) * maxit + j] = g[1 + j];
+                Gfull[(size_t)j * maxit + (k - 1)] = g[1 + j];
             }
-            if (chol_ok) chol_ok = chol.add_row(h_g.p + 1);
-            if (chol_ok) chol.solve(rhs.data(), h_y.p);
+            if (chol_ok) chol_ok = chol.add_row(g + 1);
+            if (chol_ok) chol.solve(rhs.data(), yk);
             else {
                 std::vector<double> M((size_t)k * k);
                 for (int j = 0; j < k; ++j)
                     for (int i2 = 0; i2 < k; ++i2)
                         M[(size_t)j * k + i2] = Gfull[(size_t)j * maxit + i2] + (i2 == j ? lambda : 0.0);
-                hgd::solve_square(k, M.data(), k, rhs.data(), h_y.p);
+                hgd::solve_square(k, M.data(), k, rhs.data(), yk);
             }
         }
-        HG_CUDA(cudaMemcpyAsync(d_y.p, h_y.p, (size_t)k * 8, cudaMemcpyHostToDevice, st));
+        HG_CUDA(cudaMemcpyAsync(d_y.p, yk, (size_t)k * 8, cudaMemcpyHostToDevice, st));
+        double* xk = d_x[k & 1].p;
         int np_e = 0, np_r = 0;
-        HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n_p, k, d_y.p, 1.0, nullptr, d_x.p, d_xt.p, stat_e.p, &np_e));
+        HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n_p, k, d_y.p, 1.0, nullptr, xk, d_xt.p, stat_e.p, &np_e));
         HG_TRY(hg_k_lincomb(ctx, a->T + a->ldt, a->ldt, m_p, k, d_y.p, -1.0, a->T, nullptr, nullptr, stat_r.p, &np_r));
         if (a->peer) {
             HG_TRY(hg_k_reduce_allreduce(comm, stat_e.p, np_e, 1, ctx->d_scalars + 1, nullptr, false, false));
@@ -567,23 +620,27 @@ extern "C" int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg
             HG_TRY(hg_k_reduce(ctx, stat_r.p, np_r, 1, ctx->d_scalars + 2, false, nullptr, false));
             HG_NCCL(g_nccl.AllReduce(ctx->d_scalars + 1, ctx->d_scalars + 1, 2, ncclDouble, ncclSum, comm->comm, st));
         }
-        HG_CUDA(cudaMemcpyAsync(h_s.p, ctx->d_scalars + 1, 16, cudaMemcpyDeviceToHost, st));
-        HG_CUDA(cudaStreamSynchronize(st));
-        have_x = true;
-        error_norm[k - 1] = std::sqrt(h_s.p[0]) / norm_xt;
-        residual_norm[k - 1] = std::sqrt(h_s.p[1]) / norm_b;
-        if (residual_norm[k - 1] <= tol) break;
+        HG_CUDA(cudaMemcpyAsync(h_s.p + (size_t)(k % RING) * 2, ctx->d_scalars + 1, 16, cudaMemcpyDeviceToHost, st));
+        HG_CUDA(cudaEventRecord(ev[k % RING], st));
     }
-    if (k > maxit) k = maxit;
+    if (!ended_early) {
+        k = maxit;
+        bool stop = false;
+        HG_TRY(finish_iterate(maxit, &stop));
+    }
     *niters = k;
-    HG_NCCL(g_nccl.AllGather(d_x.p, d_xfull.p, (size_t)n_p, ncclDouble, comm->comm, st));
+    const bool have_x = (kind == 1) || last_x > 0;
+    HG_NCCL(g_nccl.AllGather(d_x[last_x & 1].p, d_xfull.p, (size_t)n_p, ncclDouble, comm->comm, st));
     HG_CUDA(cudaMemcpyAsync(x, d_xfull.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     HG_CUDA(cudaStreamSynchronize(st));
     if (a->peer) HG_TRY(hg_peer_check(comm));
     if (x_valid) *x_valid = have_x ? 1 : 0;
     if (extras) {
         if (extras->beta) *extras->beta = beta;
-        if (extras->H) memcpy(extras->H, a->h_H, (size_t)ldh * maxit * 8);
+        if (extras->H) {
+            memset(extras->H, 0, (size_t)ldh * maxit * 8);
+            memcpy(extras->H, a->h_H, (size_t)ldh * k * 8);
+        }
     }
     return HG_OK;
 }

@@ -232,6 +232,10 @@ reduce_allreduce_kernel(const double* __restrict__ partials, int np, int k, hg_p
                     break;
                 }
             }
+            // acquire side of the exchange: this all-reduce is also the barrier that makes the rows peers
+            // pushed into our replicated vector visible to the kernels that follow, so order every later
+            // read after the observed epochs (the sender fences before its store)
+            __threadfence_system();
             s_part[lane] = ok ? __longlong_as_double((long long)((w0 >> 32) | (w1 & 0xffffffff00000000ull))) : 0.0;
         }
         __syncwarp();

@@ -19,7 +19,22 @@ __global__ void widen_ptr_kernel(const int32_t* __restrict__ in, int64_t* __rest
 __global__ void narrow_idx_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out,
                                   int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (int32_t)in[i];
+    if (i < n) out[i] = (in[i] < 0 || in[i] > 2147483647LL) ? -1 : (int32_t)in[i];  // -1: caught by validate_csr
+}
+
+// Structural validation of caller-supplied CSR arrays: bit 0 rowptr[0] != 0 or rowptr[rows] != nnz,
+// bit 1 a decreasing rowptr, bit 2 a column index outside [0, cols).  One pass, 4 bytes per entry.
+__global__ void validate_csr_kernel(int64_t rows, int64_t cols, int64_t nnz, const int64_t* __restrict__ rowptr,
+                                    const int32_t* __restrict__ colind, unsigned int* __restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int b = 0;
+    if (i == 0 && (rowptr[0] != 0 || rowptr[rows] != nnz)) b |= 1u;
+    if (i < rows && rowptr[i] > rowptr[i + 1]) b |= 2u;
+    if (i < nnz) {
+        const int32_t c = colind[i];
+        if (c < 0 || (int64_t)c >= cols) b |= 4u;
+    }
+    if (b) atomicOr(bad, b);
 }
 
 __global__ void dense_to_csr_kernel(int64_t rows, int64_t cols, const double* __restrict__ a,
@@ -253,14 +268,43 @@ static int upload_ptr(hg_ctx* ctx, const void* ptr, int bits, int64_t count, int
     }
     int32_t* tmp = nullptr;
     HG_CUDA(hg_dmalloc(ctx, &tmp, (size_t)count * 4));
-    HG_CUDA(cudaMemcpyAsync(tmp, ptr, (size_t)count * 4, cudaMemcpyHostToDevice, ctx->stream));
-    {
+    cudaError_t e = cudaMemcpyAsync(tmp, ptr, (size_t)count * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
         hg_launch_scope scope(ctx, HG_K_SETUP, 12.0 * (double)count);
         widen_ptr_kernel<<<(unsigned)cdiv(count, kBlock), kBlock, 0, ctx->stream>>>(tmp, d_out, count);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    hg_dfree(tmp);  // also on the error paths
+    if (e != cudaSuccess) {
+        hg_set_error("matrix upload: %s", cudaGetErrorString(e));
+        return HG_ERR_CUDA;
+    }
+    return HG_OK;
+}
+
+// A malformed input must come back as HG_ERR_INVALID, not as out-of-bounds reads in every SpMV (or
+// out-of-bounds atomics in the transposition).  Runs on the uploaded arrays; synchronises.
+static int validate_csr(hg_ctx* ctx, const hg_matrix* m, const char* who) {
+    unsigned int* d_bad = reinterpret_cast<unsigned int*>(ctx->d_scalars + 48);
+    unsigned int h_bad = 0;
+    HG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), ctx->stream));
+    {
+        const int64_t work = std::max<int64_t>(std::max(m->rows, m->nnz), 1);
+        hg_launch_scope scope(ctx, HG_K_SETUP, 4.0 * (double)m->nnz + 8.0 * (double)m->rows);
+        validate_csr_kernel<<<(unsigned)cdiv(work, kBlock), kBlock, 0, ctx->stream>>>(m->rows, m->cols, m->nnz,
+                                                                                     m->rowptr, m->colind, d_bad);
     }
     HG_CUDA(cudaGetLastError());
+    HG_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     HG_CUDA(cudaStreamSynchronize(ctx->stream));
-    hg_dfree(tmp);
+    if (h_bad) {
+        hg_set_error("%s: malformed sparse input:%s%s%s", who,
+                     (h_bad & 1u) ? " pointer array does not start at 0 / end at nnz;" : "",
+                     (h_bad & 2u) ? " pointer array is not non-decreasing;" : "",
+                     (h_bad & 4u) ? " an index is outside the matrix;" : "");
+        return HG_ERR_INVALID;
+    }
     return HG_OK;
 }
 
@@ -285,6 +329,7 @@ extern "C" int hg_matrix_from_csr(hg_ctx* ctx, int64_t rows, int64_t cols, int64
             st = HG_ERR_CUDA;
         }
     }
+    if (st == HG_OK) st = validate_csr(ctx, m, "hg_matrix_from_csr");
     if (st != HG_OK) {
         hg_matrix_destroy(m);
         return st;
@@ -342,6 +387,7 @@ extern "C" int hg_matrix_from_csc(hg_ctx* ctx, int64_t rows, int64_t cols, int64
             }
         }
         if (tmp) hg_dfree(tmp);
+        if (st == HG_OK) st = validate_csr(ctx, t, "hg_matrix_from_csc");
         if (st != HG_OK) {
             hg_matrix_destroy(t);
             return st;

@@ -18,6 +18,8 @@
 // epilogue vectors (lambda*q, -alpha*u, b) and y are accessed coalesced.
 #include <cstdlib>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace {
@@ -336,11 +338,13 @@ int hg_k_spmv_stream(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y
                                                                               mm->unit_row);
         HG_CUDA(cudaGetLastError());
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in is per device (and per template instance): one bit per device ordinal
+    static std::atomic<unsigned long long> attr_set{0};
+    const unsigned long long dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_set.load(std::memory_order_relaxed) & dev_bit)) {
         HG_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<CW, STAGES>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-        attr_set = true;
+        attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
     if (nparts) *nparts = ep.stat ? n_units : 0;
     double bytes = 12.0 * (double)m->nnz + 8.0 * (double)(m->rows + 1) + 8.0 * (double)m->cols;

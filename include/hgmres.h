@@ -258,6 +258,12 @@ int hg_hybrid_ba_gmres_rtp(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, 
                            double* error_norm, double* residual_norm, int* niters, int* x_valid,
                            const hg_solver_opts* opts, hg_extras* extras);
 
+/* Wall-clock breakdown (milliseconds) of the last hybrid_*_gmres_rtp call made on this thread:
+ * [0] setup (workspace, rhs upload, norms, r0), [1] the iteration loop, of which [2] host projected
+ * solves and [3] host waiting for the device, [4] download of x, [5] iterations.  bench.py reports it
+ * as e2e.breakdown_ms. */
+int hg_last_solve_stats(double* out, int n);
+
 /* Project-then-regularise solvers — the solve path (first four outputs) of
  *   kind 0, hybrid 1: ABgmres_hybrid_bounds.m:11-41      kind 1, hybrid 1: BAgmres_hybrid_bounds.m:11-40
  *   kind 0, hybrid 0: ABgmres_nonhybrid_bounds.m:12-40   kind 1, hybrid 0: BAgmres_nonhybrid_bounds.m:12-39
