@@ -1,10 +1,13 @@
 #!/usr/bin/env python
 """bench.py — Arnoldi iterations/s and HBM roofline on BASELINE.json's headline config.
 
-A "step" is one complete 200-iteration CGS2 Arnoldi cycle of the hybrid AB-/BA-GMRES
-hot path (operator B*(A*q)+lambda*q, two-pass CGS, normalise) on the 1024x1024
-fan-beam phantom problem with an unmatched pixel-driven back-projector (BASELINE.json
-configs[3]); `value` = 200*K / device time.  See DESIGN.md "Measurement".
+A "step" is one complete 200-iteration CGS2 Arnoldi cycle of the hybrid AB-/BA-GMRES hot path (operator
+B*(A*q)+lambda*q, two-pass CGS, normalise) on the 1024x1024 fan-beam phantom problem with an unmatched
+pixel-driven back-projector (BASELINE.json configs[3]); `value` = 200*K / device time.  `e2e` is the full
+hybrid solve through the public API from pinned host CSR.  `parity` compares what was timed with the
+OpenMP C oracle on the same inputs, at every N.  `--impl reference` times the reference's own CPU algorithm
+(oracle/c/hg_oracle.c, all host cores): the same 200-iteration Arnoldi cycle for `value`, the same full
+hybrid solve for `e2e`.  See DESIGN.md "Measurement".
 """
 from __future__ import annotations
 
@@ -34,8 +37,10 @@ WORKLOADS = {
     # BASELINE configs[4]: 2048^2, 3600 views x 2896 detectors (19 G + 30 G non-zeros): 8 GPUs only
     "ct2048_par_3600v_pixelB_k200": dict(N=2048, n_views=3600, geometry="parallel", maxit=200),
 }
+CONFIGS4 = "ct2048_par_3600v_pixelB_k200"
 LAMBDA = 1e-2  # run_2D_phantom.m:8
 NOISE = 0.01   # BASELINE config 1
+PARITY_K = 50  # north star: "over the first 50 iterations"
 
 
 class ClockSampler:
@@ -90,13 +95,26 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_workload(hg, ctx, name, rank=0, world=1, dist=None, order="natural"):
-    """Matrices are generated on the device.  world > 1: this rank's detector rows (whole views) A_p and
-    the matching columns B^p (SURVEY.md §8e); b is the matching part of the sinogram."""
+def geometry_of(name):
     w = WORKLOADS[name]
     N, nv, geom = w["N"], w["n_views"], w["geometry"]
     angles = np.arange(nv) * ((360.0 if geom == "fan" else 180.0) / nv)
     p = int(round(math.sqrt(2.0) * N))
+    return N, nv, geom, angles, p
+
+
+def noisy_rhs(b_exact_mine, nb2, m, mine_rows):
+    """b = b_exact + eta*||b_exact|| e/||e|| (run_2D_phantom.m:18-19), bit-reproducible across hosts and
+    thread counts: NumPy's pairwise sums instead of BLAS dot products."""
+    e = np.random.default_rng(0).standard_normal(m)
+    ne = math.sqrt(float(np.sum(e * e)))
+    return b_exact_mine + NOISE * math.sqrt(nb2) * e[mine_rows] / ne
+
+
+def build_workload(hg, ctx, name, rank=0, world=1, dist=None, order="natural"):
+    """Matrices are generated on the device.  world > 1: this rank's detector rows (whole views) A_p and
+    the matching columns B^p (SURVEY.md §8e); b is the matching part of the sinogram."""
+    N, nv, geom, angles, p = geometry_of(name)
     from hybrid_gmres_b200.ct import ct_backprojector, ct_projector, shepp_logan
     m = nv * p
     # rank r owns the views r, r+P, r+2P, ... (whole detector rows of the sinogram): every rank sees the
@@ -108,16 +126,14 @@ def build_workload(hg, ctx, name, rank=0, world=1, dist=None, order="natural"):
     dB = ct_backprojector(N, angles[mine], p, geom, ctx=ctx)
     x_true = shepp_logan(N)
     b_exact = dA.matvec(x_true)
-    rng = np.random.default_rng(0)
-    e = rng.standard_normal(m)
-    nb2 = float(b_exact @ b_exact)
+    nb2 = float(np.sum(b_exact * b_exact))
     if world > 1:
         import torch
         t = torch.tensor([nb2], device="cuda", dtype=torch.float64)
         dist.all_reduce(t)
         nb2 = float(t.item())
-    e_mine = e.reshape(nv, p)[mine].ravel()
-    b = b_exact + NOISE * math.sqrt(nb2) * e_mine / np.linalg.norm(e)  # run_2D_phantom.m:18-19
+    rows = (mine[:, None] * p + np.arange(p)[None, :]).ravel()
+    b = noisy_rhs(b_exact, nb2, m, rows)
     if order.startswith("tile"):
         # n-space in tile x tile pixel blocks (hg_matrix_permute): A(:,q), B(q,:), x_true(q)
         from hybrid_gmres_b200.ct import tile_permutation
@@ -129,7 +145,7 @@ def build_workload(hg, ctx, name, rank=0, world=1, dist=None, order="natural"):
         dB.close()
         ctx.trim()
         dA, dB, x_true = dA2, dB2, np.ascontiguousarray(x_true[q])
-    return dA, dB, b, x_true, w["maxit"]
+    return dA, dB, b, x_true, WORKLOADS[name]["maxit"]
 
 
 def host_csr(dM):
@@ -138,120 +154,155 @@ def host_csr(dM):
     return sp.csr_matrix((data, indices, indptr), shape=dM.shape)
 
 
-def cpu_reference_sample(A, B, b, x_true, iters):
-    """The reference's BA-RTP loop (hybrid_ba_gmres_rtp.m restated literally) for `iters`
-    iterations on the host cores: the OpenMP C restatement (all cores) when it has been built,
-    else the NumPy/SciPy one.  Returns (iters/s, seconds, iters, description, threads)."""
+def full_host_problem(hg, ctx, name):
+    """The whole problem in the caller's natural pixel order on the host: (A, B, b, x_true) with A, B CSR.
+    Generated by the device generator; `verify_inputs` checks a sub-block against oracle/ct.py."""
+    dA, dB, b, x_true, maxit = build_workload(hg, ctx, name)
+    A, B = host_csr(dA), host_csr(dB)
+    dA.close()
+    dB.close()
+    ctx.trim()
+    return A, B, b, x_true
+
+
+def verify_inputs(name, A, B, views=(0, 1, 77)):
+    """Rows of A and columns of B for a few views against the NumPy generator of oracle/ct.py (the device
+    generator that produced the inputs repeats its arithmetic bit for bit: tests/test_gpu_ct_generator.py)."""
+    from oracle import ct
+    N, nv, geom, angles, p = geometry_of(name)
+    views = [v for v in views if v < nv]
+    Ao = ct.projector(N, angles[views], p, geom).tocsr()
+    Bo = ct.backprojector_pixel_driven(N, angles[views], p, geom).tocsr()
+    ok = True
+    for i, v in enumerate(views):
+        a_dev, a_or = A[v * p:(v + 1) * p], Ao[i * p:(i + 1) * p]
+        ok = ok and a_dev.nnz == a_or.nnz and np.array_equal(a_dev.indices, a_or.indices) and \
+            np.array_equal(a_dev.data, a_or.data)
+        b_dev, b_or = B[:, v * p:(v + 1) * p].tocsr(), Bo[:, i * p:(i + 1) * p].tocsr()
+        b_dev.sort_indices()
+        b_or.sort_indices()
+        ok = ok and b_dev.nnz == b_or.nnz and np.array_equal(b_dev.indices, b_or.indices) and \
+            np.array_equal(b_dev.data, b_or.data)
+    return {"views_checked": list(views), "bit_identical_to_oracle_ct": bool(ok)}
+
+
+def parity_vs_oracle(A, B, b, x_true, res_dev, H_dev, K=PARITY_K):
+    """What was timed vs oracle/c/hg_oracle.c on the same inputs, first K iterations: the literal MGS
+    algorithm of hybrid_ba_gmres_rtp.m (`vs` reference arithmetic) and its CGS2 variant (`vs` the device
+    algorithm); max relative difference of the residual history and of H column-wise (2-norm per column)."""
     from oracle import cport
-    if cport.available():
-        t0 = time.perf_counter()
-        x, err, res, it = cport.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, iters, LAMBDA)
-        dt = time.perf_counter() - t0
-        th = cport.num_threads()
-        return it / dt, dt, it, f"oracle/c/hg_oracle.c (OpenMP, {th} threads)", th
-    import oracle
+    if not cport.available():
+        return {"vs": "oracle/c", "unavailable": "oracle/_build/libhgoracle.so not built"}
+    threads = cport.use_all_cores()
+    out = {"vs": "oracle/c/hg_oracle.c (hybrid_ba_gmres_rtp.m restated, OpenMP %d threads)" % threads, "k": K}
     t0 = time.perf_counter()
-    x, err, res, it = oracle.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, iters, LAMBDA)
-    dt = time.perf_counter() - t0
-    return it / dt, dt, it, "oracle/solvers.py (SciPy CSR mat-vec single-threaded, BLAS threaded)", 1
+    for orth in ("mgs", "cgs2"):
+        ex = {}
+        _, _, res, it = cport.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, K, LAMBDA, orth, ex)
+        dres = np.abs(res_dev[:K] - res) / res
+        Ho = ex["H"]
+        dH = np.array([np.linalg.norm(H_dev[: j + 2, j] - Ho[: j + 2, j]) / np.linalg.norm(Ho[: j + 2, j])
+                       for j in range(K)])
+        out[f"max_rel_residual_hist_k{K}_vs_{orth}"] = float(dres.max())
+        out[f"max_rel_H_col_k{K}_vs_{orth}"] = float(dH.max())
+        out[f"first_k_above_1e-8_vs_{orth}"] = {"residual": (np.flatnonzero(dres > 1e-8)[:1] + 1).tolist(),
+                                                "H_col": (np.flatnonzero(dH > 1e-8)[:1] + 1).tolist()}
+        if orth == "mgs":
+            res_mgs, H_mgs = res, Ho
+        else:  # how well the problem itself determines these numbers: the oracle against itself
+            out["oracle_mgs_vs_cgs2_residual"] = float(np.max(np.abs(res - res_mgs) / res_mgs))
+            out["oracle_mgs_vs_cgs2_H_col"] = float(max(
+                np.linalg.norm(Ho[: j + 2, j] - H_mgs[: j + 2, j]) / np.linalg.norm(H_mgs[: j + 2, j]) for j in range(K)))
+    out[f"max_rel_residual_hist_k{K}"] = out[f"max_rel_residual_hist_k{K}_vs_mgs"]
+    out[f"max_rel_H_col_k{K}"] = out[f"max_rel_H_col_k{K}_vs_mgs"]
+    out["oracle_seconds"] = round(time.perf_counter() - t0, 1)
+    return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ct1024_fan_180v_pixelB_k200", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-iters", type=int, default=20, help="iterations of the bounded CPU sample")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--nspace-order", default="tile4", choices=["natural", "tile4", "tile8"],
-                    help="pixel order of the n-space on the device (hg_matrix_permute)")
-    args = ap.parse_args()
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    K, W = max(args.steps, 1), max(args.warmup, 3)  # never fewer than 3 warm-up cycles (reported as run)
-
-    if args.impl == "reference" and rank != 0:
-        return 0
-
-    import torch
+# ---------------------------------------------------------------------------------------------- reference arm
+def reference_arm(args, K, W):
+    """The reference's CPU algorithm on this box's host cores (rank 0 only).  `value`: one 200-iteration
+    Arnoldi cycle (operator + MGS + normalise, hybrid_ba_gmres_rtp.m:19-26) reported over K steps of
+    200/K iterations each; `e2e`: one full hybrid_ba_gmres_rtp solve (200 iterations: + projected least
+    squares, iterate, true residual and error histories)."""
     import hybrid_gmres_b200 as hg
+    from oracle import cport
+    cores = len(os.sched_getaffinity(0))
+    threads = cport.use_all_cores() if cport.available() else 1  # torchrun exports OMP_NUM_THREADS=1
+    ctx = hg.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    A, B, b, x_true = full_host_problem(hg, ctx, args.workload)
+    checks = verify_inputs(args.workload, A, B)
+    ctx.close()
+    m, n = A.shape
+    maxit = WORKLOADS[args.workload]["maxit"]
+    if not cport.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_build/libhgoracle.so not built"}))
+        return 0
+    for _ in range(W):  # warm-up: page in the matrices, spin up the thread team
+        cport.hybrid_rtp("ba", A, B, b, x_true, 0.0, 3, LAMBDA, "mgs", solve=False)
+    ex = {}
+    t0 = time.perf_counter()
+    _, _, _, k_done = cport.hybrid_rtp("ba", A, B, b, x_true, 0.0, maxit, LAMBDA, "mgs", ex, solve=False)
+    dt = time.perf_counter() - t0
+    t_iter = ex["t_iter"]
+    edges = [int(round(i * k_done / K)) for i in range(K + 1)]
+    step_ms = [1e3 * ((t_iter[edges[i + 1] - 1] if edges[i + 1] else 0.0) - (t_iter[edges[i] - 1] if edges[i] else 0.0))
+               for i in range(K)]
+    value = k_done / dt
+    t0 = time.perf_counter()
+    x, err, res, it = cport.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, maxit, LAMBDA, "mgs")
+    dt_full = time.perf_counter() - t0
+    config = {"workload": args.workload, "m": m, "n": n, "nnz_A": int(A.nnz), "nnz_B": int(B.nnz), "maxit": maxit,
+              "lambda": LAMBDA, "orth": "mgs (the reference's sweep, hybrid_ba_gmres_rtp.m:20-23)",
+              "B": "pixel-driven (unmatched)", "nspace_order": "natural", "spmv_form": "host CSR, row-parallel OpenMP",
+              "parallelism": f"{threads} OpenMP threads on {cores} host cores",
+              "inputs": "generated by the device generator, downloaded; " + json.dumps(checks)}
+    line = {"impl": "reference", "metric": "arnoldi_iters_per_s", "value": value, "unit": "iter/s",
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "step_ms": [round(v, 1) for v in step_ms],
+            "cpu_baseline": {"value": value, "unit": "iter/s", "cores": threads, "host_cores": cores, "kind": "port",
+                             "sample": f"one {k_done}-iteration Arnoldi cycle of the same workload ({dt:.1f} s; the K "
+                                       f"steps are its {K} consecutive slices) by oracle/c/hg_oracle.c: 2 SpMV + MGS + "
+                                       f"normalise per iteration, OpenMP {threads} threads; e2e = one full "
+                                       f"hybrid_ba_gmres_rtp solve of {it} iterations ({dt_full:.1f} s)"},
+            "e2e": {"value": it / dt_full, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "final_residual": float(res[-1]),
+                    "api": "hybrid_ba_gmres_rtp(A,B,b,x_true,tol,maxit,lambda) restated in C (3 SpMV + MGS + projected "
+                           "LS + iterate + histories per iteration), host CSR in natural order"}}
+    print(json.dumps(line))
+    return 0
 
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1 and args.impl != "reference":
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # The library launches on the stream it is given; torch's events only see torch's current stream.  The
-    # legacy default stream has handle 0 (the library would then create its own non-blocking stream, which
-    # events on the default stream do not wait for), so make an explicit stream current and hand it over.
-    bench_stream = torch.cuda.Stream(device=local_rank)
-    torch.cuda.set_stream(bench_stream)
-    stream = bench_stream.cuda_stream
-    assert stream != 0
-    ctx = hg.Context(local_rank, stream=stream)
-    if args.impl == "reference":
-        dA, dB, b, x_true, maxit = build_workload(hg, ctx, args.workload)
-    else:
-        dA, dB, b, x_true, maxit = build_workload(hg, ctx, args.workload, rank, world, dist, args.nspace_order)
+# ---------------------------------------------------------------------------------------------- B200 arm
+def measure_arnoldi(args, hg, ctx, torch, dist, rank, world, local_rank, workload, K, W, comm=None):
+    """Clean + instrumented timed passes of K Arnoldi cycles on `workload`.  Returns a dict of results and
+    the live objects (matrices, Arnoldi handle) for the legs that follow."""
+    sharded = world > 1
+    dA, dB, b, x_true, maxit = build_workload(hg, ctx, workload, rank, world, dist, args.nspace_order)
     m, n = dA.shape
     nnzA, nnzB = dA.nnz, dB.nnz
     if dist is not None:
         t = torch.tensor([float(m), float(nnzA), float(nnzB)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t)
         m, nnzA, nnzB = (int(v) for v in t.tolist())
-    cores = len(os.sched_getaffinity(0))
-    config = {"workload": args.workload, "m": m, "n": n, "nnz_A": nnzA, "nnz_B": nnzB, "maxit": maxit,
+    config = {"workload": workload, "m": m, "n": n, "nnz_A": nnzA, "nnz_B": nnzB, "maxit": maxit,
               "lambda": LAMBDA, "orth": "cgs2", "B": "pixel-driven (unmatched)",
               "nspace_order": args.nspace_order,
               "spmv_form": {"A": f"{dA.spmv_form}/idx{dA.spmv_index_bits}", "B": f"{dB.spmv_form}/idx{dB.spmv_index_bits}"},
-              "parallelism": (f"A row-sharded / B column-sharded x{world}, NCCL reduce-scatter + all-gather + "
-                              "3 all-reduce per step") if world > 1 else "single",
+              "parallelism": "single",
               "l2": "inputs (A+B = %.1f GB) exceed the 126 MB L2; no flush needed" % ((nnzA + nnzB) * 12 / 1e9)}
-
-    # ------------------------------------------------------------------ reference arm
-    if args.impl == "reference":
-        A, B = host_csr(dA), host_csr(dB)
-        del dA, dB
-        for _ in range(W):
-            cpu_reference_sample(A, B, b, x_true, 2)
-        t0 = time.perf_counter()
-        its = 0
-        for _ in range(K):
-            _, _, it, desc, threads = cpu_reference_sample(A, B, b, x_true, args.cpu_iters)
-            its += it
-        dt = time.perf_counter() - t0
-        val = its / dt
-        line = {"impl": "reference", "metric": "arnoldi_iters_per_s", "value": val, "unit": "iter/s",
-                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": "iter/s", "cores": threads, "host_cores": cores, "kind": "port",
-                                 "sample": f"{args.cpu_iters} full hybrid BA-RTP iterations per step of the same workload "
-                                           f"(hybrid_ba_gmres_rtp.m restated literally: 3 SpMV + MGS + projected LS per "
-                                           f"iteration) by {desc}"},
-                "e2e": {"value": val, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
-
-    # ------------------------------------------------------------------ B200 arm
-    sharded = world > 1
     if sharded:
-        from hybrid_gmres_b200.distributed import Communicator, ShardedArnoldi
-        comm = Communicator(ctx)
+        from hybrid_gmres_b200.distributed import ShardedArnoldi
         ar = ShardedArnoldi(comm, dA, dB, maxit)
         ar.set_rhs(b)
         peer = comm.transport.startswith("peer")
         config["transport"] = comm.transport
         config["parallelism"] = (
-            f"A row-sharded by whole views (rank r: views r, r+{world}, ...) / B column-sharded x{world}; per step: reduce-scatter pulled over NVLink peer memory by "
-            "the first CGS2 multi-dot, 3 one-shot all-reduces inside the second-stage reductions, all-gather "
-            "pushed by the normalisation kernel (no NCCL call on the step)" if peer else
+            f"A row-sharded by whole views (rank r: views r, r+{world}, ...) / B column-sharded x{world}; per step: "
+            "reduce-scatter pulled over NVLink peer memory by the first CGS2 multi-dot, one-shot all-reduces inside "
+            "the second-stage reductions, all-gather pushed by the normalisation kernel (no NCCL call on the step)"
+            if peer else
             f"A row-sharded / B column-sharded x{world}, NCCL reduce-scatter + all-gather + 3 all-reduce per step")
     else:
         ar = hg.Arnoldi(dA, dB, "n", maxit)
@@ -297,16 +348,68 @@ def main():
     # serialise back-to-back kernels a little, so its step time is reported next to the clean one)
     ms, launches, clocks, _ = timed_pass(False)
     ms_instr, _, _, timing = timed_pass(True)
-    total_iters = maxit * K  # one sharded job: the same 200-iteration cycle on N GPUs (strong scaling)
-    value = total_iters / (ms * 1e-3)
+    H_dev, beta_dev, _ = ar.get()
     step_bytes = sum(ar.step_bytes(k) for k in range(1, maxit + 1))
     if sharded:  # whole-job algorithmic bytes = sum over ranks
         t = torch.tensor([step_bytes], device="cuda", dtype=torch.float64)
         dist.all_reduce(t)
         step_bytes = float(t.item())
-        peak_scale = world
-    else:
-        peak_scale = 1
+    return dict(dA=dA, dB=dB, b=b, x_true=x_true, maxit=maxit, ar=ar, config=config, ms=ms, launches=launches,
+                clocks=clocks, ms_instr=ms_instr, timing=timing, step_bytes=step_bytes, m=m, n=n, nnzA=nnzA,
+                nnzB=nnzB, H=H_dev, beta=beta_dev)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ct1024_fan_180v_pixelB_k200", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and parity legs")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs4", action="store_true", help="at --gpus 8: skip the 2048^2 run (BASELINE configs[4])")
+    ap.add_argument("--nspace-order", default="tile4", choices=["natural", "tile4", "tile8"],
+                    help="pixel order of the n-space on the device (hg_matrix_permute)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = max(args.steps, 1), max(args.warmup, 3)  # never fewer than 3 warm-up cycles (reported as run)
+
+    if args.impl == "reference":
+        return reference_arm(args, K, W) if rank == 0 else 0
+
+    import torch
+    import hybrid_gmres_b200 as hg
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # The library launches on the stream it is given; torch's events only see torch's current stream.  The
+    # legacy default stream has handle 0 (the library would then create its own non-blocking stream, which
+    # events on the default stream do not wait for), so make an explicit stream current and hand it over.
+    bench_stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(bench_stream)
+    stream = bench_stream.cuda_stream
+    assert stream != 0
+    ctx = hg.Context(local_rank, stream=stream)
+    cores = len(os.sched_getaffinity(0))
+    sharded = world > 1
+    comm = None
+    if sharded:
+        from hybrid_gmres_b200.distributed import Communicator
+        comm = Communicator(ctx)
+
+    r = measure_arnoldi(args, hg, ctx, torch, dist, rank, world, local_rank, args.workload, K, W, comm)
+    dA, dB, b, x_true, maxit, ar, config = r["dA"], r["dB"], r["b"], r["x_true"], r["maxit"], r["ar"], r["config"]
+    ms, timing = r["ms"], r["timing"]
+    total_iters = maxit * K  # one sharded job: the same 200-iteration cycle on N GPUs (strong scaling)
+    value = total_iters / (ms * 1e-3)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -315,42 +418,54 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     sp_ms, sp_cnt, sp_bytes = timing["spmv"]
-    achieved = (sp_bytes / sp_cnt) / (sp_ms / sp_cnt * 1e-3) / 1e9 if sp_cnt else 0.0
+    # SURVEY §8(d) algorithmic bytes of one SpMV launch: 12 B per non-zero + 8 B row pointers + the vectors; the
+    # dominant kernel pair is the two launches of one step, so "per launch" is their mean
+    alg_bytes = (12.0 * (r["nnzA"] + r["nnzB"]) + 8.0 * (r["m"] + r["n"] + 2) + 16.0 * r["m"] + 24.0 * r["n"]) / 2.0 / world
+    avg_s = sp_ms / sp_cnt * 1e-3 if sp_cnt else float("nan")
+    achieved = alg_bytes / avg_s / 1e9 if sp_cnt else 0.0
+    achieved_stored = (sp_bytes / sp_cnt) / avg_s / 1e9 if sp_cnt else 0.0
     traffic, traffic_src = None, None
-    if args.workload == "ct1024_fan_180v_pixelB_k200":
-        try:  # dram__bytes_read+write per launch from the committed `ncu --set full` capture of this kernel
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_spmv_traffic.json")))
-            traffic, traffic_src = float(tj["mean"]), tj["source"]
-        except Exception:
-            pass
+    if args.workload == "ct1024_fan_180v_pixelB_k200" and not sharded:
+        for fn in ("r02_spmv_traffic.json", "r01_spmv_traffic.json"):
+            try:  # dram__bytes_read+write per launch from the committed `ncu --set full` capture of this kernel
+                tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
+                traffic, traffic_src = float(tj["mean"]), tj["source"]
+                break
+            except Exception:
+                pass
     forms = config.get("spmv_form", {})
     knames = {"csr/idx32": "spmv_csr_kernel<32>", "csr/idx16": "spmv_csr16_kernel", "sell32/idx32": "spmv_sell32_kernel<4>",
               "sell32/idx16": "spmv_sell16_kernel<4>", "stream/idx32": "spmv_stream_kernel"}
     kname = " + ".join(f"{knames.get(forms.get(w), 'spmv')} ({w})" for w in ("A", "B"))
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": traffic_src, "peak_source": peak_src,
+    step_bytes_8d = (12.0 * (r["nnzA"] + r["nnzB"]) + 8.0 * (r["m"] + r["n"] + 2) + 16.0 * r["m"] + 88.0 * r["n"]) * maxit + \
+        32.0 * r["n"] * maxit * (maxit + 1) / 2.0
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "bytes_model": "SURVEY §8(d): 12 B per non-zero + pointers + vectors, mean of the two SpMV launches of a step",
+                "achieved_stored_format": achieved_stored, "frac_stored_format": achieved_stored / peak,
+                "stored_format_note": "bytes of the arrays the kernels really stream (B: 16-bit column offsets, 10.03 B per "
+                                      "non-zero); `traffic` (ncu dram bytes) matches this figure, not the 12 B/nnz one",
                 "launches": sp_cnt, "avg_launch_ms": sp_ms / sp_cnt if sp_cnt else None,
-                "algorithmic_bytes_per_launch": sp_bytes / sp_cnt if sp_cnt else None,
-                "instrumented_ms_per_step": ms_instr / K,
-                "step_algorithmic_GBps": step_bytes * K / (ms * 1e-3) / 1e9,
-                "step_frac": step_bytes * K / (ms * 1e-3) / 1e9 / (peak * peak_scale),
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "stored_bytes_per_launch": sp_bytes / sp_cnt if sp_cnt else None,
+                "instrumented_ms_per_step": r["ms_instr"] / K,
+                "step_GBps_8d": step_bytes_8d * K / (ms * 1e-3) / 1e9,
+                "step_frac_8d": step_bytes_8d * K / (ms * 1e-3) / 1e9 / (peak * world),
+                "step_GBps_stored": r["step_bytes"] * K / (ms * 1e-3) / 1e9,
+                "step_frac": r["step_bytes"] * K / (ms * 1e-3) / 1e9 / (peak * world),
                 "per_class": {k: {"ms": v[0], "launches": v[1],
                                   "GBps": (v[2] / (v[0] * 1e-3) / 1e9) if v[0] > 0 else None}
                               for k, v in timing.items() if v[1]}}
     line = {"metric": "arnoldi_iters_per_s", "value": value, "unit": "iter/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "roofline": roofline,
-            "gpu_launches": launches, "clocks": clocks}
+            "gpu_launches": r["launches"], "clocks": r["clocks"]}
 
     # ------------------------------------------------------------------ e2e through the public API
-    if sharded and not args.no_e2e:
-        # end to end of the sharded public API: every rank uploads its shards (natural pixel order) from
-        # pinned host memory; the sharded hybrid BA-GMRES re-orders the n-space on the device, runs 200
-        # full hybrid iterations (Arnoldi + projected solve + iterate + both histories) and returns x
-        from hybrid_gmres_b200 import distributed as hgd
-        nperm = None
+    nperm = None
+    if not args.no_e2e:
+        # the caller's host data is in the natural (column-major pixel) order; the library applies the tile
+        # order on the device inside the timed call (nperm=) and returns x in the caller's order
         if args.nspace_order.startswith("tile"):
             from hybrid_gmres_b200.ct import tile_permutation
             nperm = tile_permutation(WORKLOADS[args.workload]["N"], int(args.nspace_order[4:]))
@@ -365,61 +480,10 @@ def main():
             xt[nperm] = x_true
             x_true = xt
         A, B = host_csr(dA), host_csr(dB)
-        pinned = []
-        for arr in (A.indptr, A.indices, A.data, B.indptr, B.indices, B.data, b, x_true):
-            try:
-                hg._lib.check(ctx._lib.hg_host_register(arr.ctypes.data, arr.nbytes))
-                pinned.append(arr)
-            except Exception:
-                pass
         ar.close()
         dA.close()
         dB.close()
         del ar, dA, dB
-        hgd.hybrid_ba_gmres_rtp(comm, A, B, b, x_true, 0.0, 3, LAMBDA, nperm=nperm)  # warm-up (buffer cache)
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        Ke = max(1, min(K, 3))
-        its = 0
-        for _ in range(Ke):
-            x, err, res, it = hgd.hybrid_ba_gmres_rtp(comm, A, B, b, x_true, 0.0, maxit, LAMBDA, nperm=nperm)
-            its += it
-        torch.cuda.synchronize()
-        dist.barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        h2d = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes + B.indptr.nbytes + B.indices.nbytes + \
-            B.data.nbytes + b.nbytes + x_true.nbytes
-        tb = torch.tensor([float(h2d)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tb)
-        line["e2e"] = {"value": its / float(t.item()), "unit": "iter/s", "h2d_bytes_per_step": int(tb.item()),
-                       "d2h_bytes_per_step": int(world * (x.nbytes + maxit * (maxit + 3) // 2 * 8 + maxit * 16)),
-                       "steps": Ke, "final_residual": float(res[-1]),
-                       "api": "distributed.hybrid_ba_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lambda): per-rank "
-                              "upload of the shards from pinned host CSR (natural pixel order) + device re-ordering + "
-                              "200 full sharded hybrid iterations + histories per step"}
-        for arr in pinned:
-            ctx._lib.hg_host_unregister(arr.ctypes.data)
-    elif rank == 0 and not args.no_e2e:
-        nperm = None
-        if args.nspace_order.startswith("tile"):
-            # the caller's host data is in the natural (column-major pixel) order; the library applies the
-            # tile order on the device inside the timed call (nperm=) and returns x in the caller's order
-            from hybrid_gmres_b200.ct import tile_permutation
-            nperm = tile_permutation(WORKLOADS[args.workload]["N"], int(args.nspace_order[4:]))
-            qinv = np.empty_like(nperm)
-            qinv[nperm] = np.arange(nperm.shape[0], dtype=nperm.dtype)
-            nA, nB = dA.permute(None, qinv), dB.permute(qinv, None)
-            ar.close()
-            dA.close()
-            dB.close()
-            dA, dB = nA, nB
-            xt = np.empty_like(x_true)
-            xt[nperm] = x_true
-            x_true = xt
-        A, B = host_csr(dA), host_csr(dB)
         pinned = []
         for arr in (A.indptr, A.indices, A.data, B.indptr, B.indices, B.data, b, x_true):
             try:
@@ -427,41 +491,164 @@ def main():
                 pinned.append(arr)
             except Exception as exc:  # pageable upload still works, only slower
                 print(f"[bench] hg_host_register failed for a {arr.nbytes}-byte array: {exc}", file=sys.stderr)
-        ar.close()
-        del ar
+        if sharded:
+            from hybrid_gmres_b200 import distributed as hgd
+
+            def solve(n_it, cache, stats=None, extras=None):
+                return hgd.hybrid_ba_gmres_rtp(comm, A, B, b, x_true, 0.0, n_it, LAMBDA, nperm=nperm, cache=cache,
+                                               stats=stats, extras=extras)
+            api = ("distributed.hybrid_ba_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lambda): per-rank upload of "
+                   "the shards from pinned host CSR (natural pixel order) + device re-ordering + 200 full sharded "
+                   "hybrid iterations + histories per step")
+        else:
+            def solve(n_it, cache, stats=None, extras=None):
+                return hg.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, n_it, LAMBDA, ctx=ctx, nperm=nperm, cache=cache,
+                                              stats=stats, extras=extras)
+            api = ("hybrid_ba_gmres_rtp(A,B,b,x_true,tol,maxit,lambda) with pinned host CSR A, B in the caller's natural "
+                   "pixel order (upload + device re-ordering + 200 full hybrid iterations + histories per step)")
+
+        def sync_all():
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+
+        def max_over_ranks(v):
+            if dist is None:
+                return v
+            t = torch.tensor([v], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        solve(min(maxit, 3), False)  # warm-up (allocator pools)
         Ke = max(1, min(K, 3))
-        hg.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, min(maxit, 3), LAMBDA, ctx=ctx, nperm=nperm)  # warm-up (allocators)
-        torch.cuda.synchronize()
+        # cold: every call uploads A and B from the (pinned) host arrays — the headline e2e
+        sync_all()
+        its, step_s, stats = 0, [], {}
         t0 = time.perf_counter()
-        its = 0
-        step_s = []
-        for _ in range(Ke):
+        for i in range(Ke):
             ts = time.perf_counter()
-            x, err, res, it = hg.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, maxit, LAMBDA, ctx=ctx, nperm=nperm)
+            st = {}
+            x, err, res, it = solve(maxit, False, st)
             its += it
             step_s.append(round(time.perf_counter() - ts, 4))
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+            stats = st
+        sync_all()
+        dt = max_over_ranks(time.perf_counter() - t0)
         h2d = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes + B.indptr.nbytes + B.indices.nbytes + \
             B.data.nbytes + b.nbytes + x_true.nbytes + maxit * (maxit + 1) // 2 * 8
         d2h = x.nbytes + maxit * (maxit + 3) // 2 * 8 + maxit * 16
-        line["e2e"] = {"value": its / dt, "unit": "iter/s", "h2d_bytes_per_step": int(h2d),
-                       "d2h_bytes_per_step": int(d2h), "steps": Ke, "step_s": step_s,
-                       "final_residual": float(res[-1]),
-                       "api": "hybrid_ba_gmres_rtp(A,B,b,x_true,tol,maxit,lambda) with pinned host CSR A, B in the "
-                              "caller's natural pixel order (upload + device re-ordering + 200 full hybrid "
-                              "iterations + histories per step)"}
+        if dist is not None:
+            tb = torch.tensor([float(h2d)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tb)
+            h2d, d2h = int(tb.item()), d2h * world
+        line["e2e"] = {"value": its / dt, "unit": "iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "steps": Ke, "step_s": step_s, "final_residual": float(res[-1]), "api": api,
+                       "breakdown_ms": {k: round(float(v), 2) for k, v in stats.items() if k.endswith("_ms")},
+                       "breakdown_note": "last cold step on rank 0: fingerprint (cache key, unused when cold), upload "
+                                         "(pinned host -> HBM), reorder (device n-space permutation), solve = setup + loop "
+                                         "(host_solve and host_wait are inside loop) + d2h"}
+        # warm: the matrices are resident from the previous call with the same arrays (SURVEY §8b ownership)
+        solve(min(maxit, 3), True)
+        sync_all()
+        stw = {}
         t0 = time.perf_counter()
-        x, err, res, it = hg.hybrid_ab_gmres_rtp(A, B, b, x_true, 0.0, maxit, LAMBDA, ctx=ctx, nperm=nperm)
-        torch.cuda.synchronize()
-        line["e2e"]["hybrid_ab_iters_per_s"] = it / (time.perf_counter() - t0)
+        itw = 0
+        for i in range(Ke):
+            x, err, res_w, it = solve(maxit, True, stw)
+            itw += it
+        sync_all()
+        dtw = max_over_ranks(time.perf_counter() - t0)
+        line["e2e_warm"] = {"value": itw / dtw, "unit": "iter/s", "steps": Ke,
+                            "h2d_bytes_per_step": int((b.nbytes + x_true.nbytes) * (world if sharded else 1)),
+                            "note": "same call, A and B already resident on the device (matrix cache hit keyed on buffer "
+                                    "addresses + dims + nnz + content checksum)",
+                            "breakdown_ms": {k: round(float(v), 2) for k, v in stw.items() if k.endswith("_ms")}}
+        if not sharded:
+            t0 = time.perf_counter()
+            x2, err2, res2, it2 = hg.hybrid_ab_gmres_rtp(A, B, b, x_true, 0.0, maxit, LAMBDA, ctx=ctx, nperm=nperm)
+            torch.cuda.synchronize()
+            line["e2e"]["hybrid_ab_iters_per_s_warm"] = it2 / (time.perf_counter() - t0)
+
+        # ---------------------------------------------------------------- parity of what was timed
         if not args.no_cpu:
-            v, dt, it, desc, threads = cpu_reference_sample(A, B, b, x_true, args.cpu_iters)
-            line["cpu_baseline"] = {"value": v, "unit": "iter/s", "cores": threads, "host_cores": cores, "kind": "port",
-                                    "sample": f"{it} full hybrid BA-RTP iterations of the same workload ({dt:.1f} s) by "
-                                              f"{desc} — compare with e2e (full hybrid iterations), not with value"}
+            ex = {"want_X": False}
+            _, _, res_p, _ = solve(PARITY_K, True, None, ex)
+            # the device Arnoldi handle timed above and the solver must tell the same story
+            hk = min(PARITY_K, maxit)
+            same = float(max(np.linalg.norm(ex["H"][: j + 2, j] - r["H"][: j + 2, j]) / np.linalg.norm(r["H"][: j + 2, j])
+                             for j in range(hk)))
+            if sharded:
+                # rank 0 needs the whole problem for the oracle: generated once more, unsharded
+                if rank == 0:
+                    hg.clear_matrix_cache()
+                    ctx.trim()
+                    Af, Bf, bf, xf = full_host_problem(hg, ctx, args.workload)
+                    par = parity_vs_oracle(Af, Bf, bf, xf, res_p, ex["H"])
+                    del Af, Bf
+                else:
+                    par = None
+                dist.barrier()
+            else:
+                par = parity_vs_oracle(A, B, b, x_true, res_p, ex["H"])
+            if par is not None:
+                par["timed_arnoldi_vs_solver_H_col"] = same
+                par["full_run_final_residual"] = {"device_k%d" % maxit: float(res[-1])}
+                line["parity"] = par
+        if not sharded and not args.no_cpu:
+            from oracle import cport
+            if cport.available():
+                threads = cport.use_all_cores()
+                t0 = time.perf_counter()
+                _, _, _, itc = cport.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, 30, LAMBDA, "mgs")
+                dtc = time.perf_counter() - t0
+                line["cpu_baseline"] = {"value": itc / dtc, "unit": "iter/s", "cores": threads, "host_cores": cores,
+                                        "kind": "port",
+                                        "sample": f"{itc} full hybrid BA-RTP iterations of the same workload ({dtc:.1f} s) by "
+                                                  "oracle/c/hg_oracle.c (hybrid_ba_gmres_rtp.m restated: 3 SpMV + MGS + projected "
+                                                  "LS per iteration) — compare with e2e (full hybrid iterations), not with value; "
+                                                  "`--impl reference` times the full 200-iteration cycle"}
         for arr in pinned:
             ctx._lib.hg_host_unregister(arr.ctypes.data)
+        del A, B
+    else:
+        ar.close()
+        dA.close()
+        dB.close()
+
+    # ------------------------------------------------------------------ BASELINE configs[4] at 8 GPUs
+    if world == 8 and not args.no_configs4 and args.workload != CONFIGS4:
+        try:
+            hg.clear_matrix_cache()
+            ctx.trim()
+            Kc = max(1, min(K, 2))
+            rc = measure_arnoldi(args, hg, ctx, torch, dist, rank, world, local_rank, CONFIGS4, Kc, 3, comm)
+            msc = rc["ms"]
+            arc = rc["ar"]
+            # parity at a size no CPU oracle can hold (600 GB of matrices): what CGS2 must deliver — an orthonormal
+            # basis (Gram matrix of the sharded basis, summed over ranks) and identical H on every rank
+            kq = 41
+            Qs = np.column_stack([arc.q_slice(j)[0] for j in range(kq)])
+            G = torch.from_numpy(Qs.T @ Qs).cuda()
+            dist.all_reduce(G)
+            orth = float((G.cpu() - torch.eye(kq, dtype=torch.float64)).abs().max())
+            Hc = torch.from_numpy(np.ascontiguousarray(rc["H"])).cuda()
+            Hmax, Hmin = Hc.clone(), Hc.clone()
+            dist.all_reduce(Hmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(Hmin, op=dist.ReduceOp.MIN)
+            line["configs4"] = {"workload": CONFIGS4, "value": rc["maxit"] * Kc / (msc * 1e-3), "unit": "iter/s",
+                                "steps": Kc, "warmup": 3, "ms_per_step": msc / Kc,
+                                "step_frac": rc["step_bytes"] * Kc / (msc * 1e-3) / 1e9 / (peak * world),
+                                "nnz_A": rc["nnzA"], "nnz_B": rc["nnzB"], "transport": rc["config"].get("transport"),
+                                "spmv_GBps_per_gpu": (rc["timing"]["spmv"][2] / (rc["timing"]["spmv"][0] * 1e-3) / 1e9)
+                                if rc["timing"]["spmv"][0] > 0 else None,
+                                "parity": {"basis_orthogonality_max_abs_k40": orth,
+                                           "H_identical_on_all_ranks": bool(torch.equal(Hmax, Hmin)),
+                                           "vs": "no CPU oracle fits 2048^2 (600 GB of matrices): CGS2 invariants instead"}}
+            arc.close()
+            rc["dA"].close()
+            rc["dB"].close()
+        except Exception as exc:  # the headline line must survive a failure of the optional leg
+            line["configs4"] = {"workload": CONFIGS4, "error": repr(exc)[:300]}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

@@ -25,12 +25,15 @@ import hybrid_gmres_b200 as hg  # noqa: E402
 from hybrid_gmres_b200.ct import shepp_logan  # noqa: E402
 
 
-def main():
-    N = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-    noise_lvl, maxit, lam, tol = 0.25, 80, 1e-2, 1e-6  # run_2D_phantom.m:5-9
-    ctx = hg.default_context()
-    n_views = 180
-    angles = np.arange(n_views) * 2.0
+def run(N=64, n_views=180, noise_lvl=0.25, maxit=80, lam=1e-2, tol=1e-6, levels=None, ctx=None, verbose=True,
+        k_gcv=20):
+    """The script's computation as a function (tests/test_gpu_example.py compares the returned numbers with
+    the oracle): returns a dict with the problem in host form, the four reconstructions' error histories
+    and the mismatch-sweep table."""
+    say = print if verbose else (lambda *a, **k: None)
+    ctx = ctx or hg.default_context()
+    levels = np.logspace(-4, 0, 10) if levels is None else np.asarray(levels, dtype=float)  # :79
+    angles = np.arange(n_views) * (360.0 / n_views)
     p = int(round(math.sqrt(2.0) * N))
     dA = hg.ct_projector(N, angles, p, "fan", ctx=ctx)
     x_true = shepp_logan(N)
@@ -39,11 +42,14 @@ def main():
     e = rng.standard_normal(b_exact.shape)
     b_noise = b_exact + e / np.linalg.norm(e) * noise_lvl * np.linalg.norm(b_exact)  # :18-20
     sino = b_noise.reshape(p, n_views, order="F")  # :25-26
-    print(f"N={N}: A {dA.shape}, nnz {dA.nnz}; sinogram {sino.shape}, noise {noise_lvl:.0%}")
+    say(f"N={N}: A {dA.shape}, nnz {dA.nnz}; sinogram {sino.shape}, noise {noise_lvl:.0%}")
 
     dAt = dA.transpose()  # matched back-projector B = A'
     indptr, indices, data = dAt.download()
-    print("\nReconstructions with matched B = A' (final relative error, iterations):")
+    out = {"A": sp.csr_matrix(tuple(reversed(dA.download())), shape=dA.shape),
+           "At": sp.csr_matrix((data, indices, indptr), shape=dAt.shape), "b": b_noise, "x_true": x_true,
+           "sinogram": sino, "recon": {}, "sweep": [], "levels": levels, "E": []}
+    say("\nReconstructions with matched B = A' (final relative error, iterations):")
     for name, f, args in (("non-hybrid AB-GMRES", hg.ABgmres_nonhybrid_bounds, ()),
                           ("non-hybrid BA-GMRES", hg.BAgmres_nonhybrid_bounds, ()),
                           ("hybrid AB-GMRES (PTR)", hg.ABgmres_hybrid_bounds, (lam,)),
@@ -51,11 +57,12 @@ def main():
                           ("hybrid AB-GMRES (RTP)", hg.hybrid_ab_gmres_rtp, (lam,)),
                           ("hybrid BA-GMRES (RTP)", hg.hybrid_ba_gmres_rtp, (lam,))):
         x, err, res, it = f(dA, dAt, b_noise, x_true, tol, maxit, *args, ctx=ctx)
-        print(f"  {name:24s} err {err[-1]:.4f}  min err {err.min():.4f} at k={int(err.argmin()) + 1:3d}  iters {it}")
+        out["recon"][name] = (err, it)
+        say(f"  {name:24s} err {err[-1]:.4f}  min err {err.min():.4f} at k={int(err.argmin()) + 1:3d}  iters {it}")
 
-    print("\nRobustness to mismatch, B = A' + c*E (final relative error):")
-    print("      c        nonhy-AB  nonhy-BA  hybrid-AB  hybrid-BA  GCV lambda(ba)")
-    for c in np.logspace(-4, 0, 10):  # :79
+    say("\nRobustness to mismatch, B = A' + c*E (final relative error):")
+    say("      c        nonhy-AB  nonhy-BA  hybrid-AB  hybrid-BA  GCV lambda(ba)")
+    for c in levels:
         E = rng.standard_normal(data.shape[0])
         E = E / np.linalg.norm(E) * c  # :88 (Frobenius norm c, on the pattern of A')
         dB = hg.DeviceMatrix.from_csr(indptr, indices, data + E, dAt.shape, ctx)
@@ -63,10 +70,18 @@ def main():
         for f, args in ((hg.ABgmres_nonhybrid_bounds, ()), (hg.BAgmres_nonhybrid_bounds, ()),
                         (hg.ABgmres_hybrid_bounds, (lam,)), (hg.BAgmres_hybrid_bounds, (lam,))):
             x, err, res, it = f(dA, dB, b_noise, x_true, tol, maxit, *args, ctx=ctx)
-            row.append(err[-1])
-        lam_gcv, _, _ = hg.fminbnd_gcv(dA, dB, b_noise, dA.shape[0], 20, "ba", 1e-9, 1e-1, 1e-8, ctx=ctx)
-        print(f"  {c:9.2e}   {row[0]:8.4f}  {row[1]:8.4f}  {row[2]:9.4f}  {row[3]:9.4f}  {lam_gcv:.3e}")
+            row.append(err[-1])  # :97-100
+        lam_gcv, fval, _ = hg.fminbnd_gcv(dA, dB, b_noise, dA.shape[0], k_gcv, "ba", 1e-9, 1e-1, 1e-8, ctx=ctx)
+        say(f"  {c:9.2e}   {row[0]:8.4f}  {row[1]:8.4f}  {row[2]:9.4f}  {row[3]:9.4f}  {lam_gcv:.3e}")
+        out["sweep"].append(row + [lam_gcv, fval])
+        out["E"].append(E)
         dB.close()
+    out["sweep"] = np.array(out["sweep"])
+    return out
+
+
+def main():
+    run(int(sys.argv[1]) if len(sys.argv) > 1 else 64)
 
 
 if __name__ == "__main__":

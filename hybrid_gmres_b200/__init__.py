@@ -19,6 +19,7 @@ from .api import (  # noqa: E402,F401
     DeviceMatrix,
     GcvProblem,
     KERNEL_CLASSES,
+    clear_matrix_cache,
     default_context,
     fminbnd_gcv,
     gcv_function,
@@ -29,6 +30,7 @@ from .api import (  # noqa: E402,F401
     hybrid_lsqr_solver,
     lsmr_solver,
     lsqr_solver,
+    matrix_cache_info,
     set_option,
 )
 from .ct import ct_backprojector, ct_projector, ray_tables  # noqa: E402,F401

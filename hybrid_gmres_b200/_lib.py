@@ -95,6 +95,7 @@ PROTOTYPES = {
                                     C.POINTER(HgSolverOpts), C.POINTER(HgExtras)]),
     "hg_hybrid_ba_gmres_rtp": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _d, _vp, _vp, _vp, c_int_p, c_int_p,
                                     C.POINTER(HgSolverOpts), C.POINTER(HgExtras)]),
+    "hg_last_solve_stats": (_i, [_vp, _i]),
     "hg_gmres_ptr": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _d, _i, _d, _vp, _vp, _vp, c_int_p, c_int_p,
                           C.POINTER(HgExtras)]),
     "hg_gcv_prepare": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, c_void_pp]),

@@ -16,11 +16,12 @@ reference's callers pass (SURVEY.md §8b "Input types").
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import os
 import sys
 import time
-import weakref
+import zlib
 
 import numpy as np
 
@@ -31,7 +32,7 @@ __all__ = [
     "Context", "DeviceMatrix", "Arnoldi", "GcvProblem", "default_context",
     "hybrid_ab_gmres_rtp", "hybrid_ba_gmres_rtp", "hybrid_lsqr_solver", "hybrid_lsmr_solver",
     "lsqr_solver", "lsmr_solver", "gcv_function", "gcv_prepare", "fminbnd_gcv",
-    "KERNEL_CLASSES", "set_option",
+    "KERNEL_CLASSES", "set_option", "clear_matrix_cache", "matrix_cache_info",
 ]
 
 _TRACE = os.environ.get("HG_TRACE") is not None
@@ -249,20 +250,155 @@ class DeviceMatrix:
             pass
 
 
-class _Uploaded:
-    """Uploads host matrices for the duration of one solver call."""
+# ---------------------------------------------------------------------------
+# matrix residency across calls (SURVEY.md §8b "Ownership")
+# ---------------------------------------------------------------------------
+# The reference's callers pass the same A / B to many calls in a row (the ~30 gcv_function calls of one
+# fminbnd, the lambda sweeps of analyze_regularization.m:21-33, the solver comparisons of
+# run_equivalence_plots.m:13-22).  Uploaded (and re-ordered) matrices therefore stay on the device, keyed
+# on what identifies the caller's arrays: buffer addresses, shape, nnz and a content checksum — complete
+# for arrays up to 8 MB, a strided 1 MB sample plus head and tail above that (a 7.4 GB pair is not
+# re-read on every call; an in-place edit that touches none of the sampled bytes goes unnoticed — pass
+# ``cache=False`` or call :func:`clear_matrix_cache` after editing a large matrix in place).
+_FULL_HASH_BYTES = 8 << 20
+_SAMPLE_CHUNKS, _SAMPLE_CHUNK_BYTES = 4096, 256
 
-    def __init__(self, ctx, *mats):
+
+def _array_fingerprint(a) -> tuple:
+    a = np.asarray(a)
+    if not a.flags.c_contiguous and not a.flags.f_contiguous:
+        a = np.ascontiguousarray(a)
+    raw = a.reshape(-1, order="A").view(np.uint8)
+    nb = raw.shape[0]
+    if nb <= _FULL_HASH_BYTES:
+        h = zlib.crc32(raw)
+    else:
+        h = zlib.crc32(raw[:65536])
+        h = zlib.crc32(raw[-65536:], h)
+        step = (nb - _SAMPLE_CHUNK_BYTES) // _SAMPLE_CHUNKS
+        starts = (np.arange(_SAMPLE_CHUNKS, dtype=np.int64) * step) & ~np.int64(7)
+        idx = (starts[:, None] + np.arange(_SAMPLE_CHUNK_BYTES, dtype=np.int64)[None, :]).reshape(-1)
+        h = zlib.crc32(raw[idx], h)
+    return (a.__array_interface__["data"][0], a.shape, a.dtype.str, h)
+
+
+def _matrix_fingerprint(M) -> tuple:
+    fmt = getattr(M, "format", None)
+    if fmt in ("csr", "csc"):
+        return (fmt, tuple(M.shape), int(M.nnz), _array_fingerprint(M.indptr), _array_fingerprint(M.indices),
+                _array_fingerprint(M.data))
+    if fmt is not None and hasattr(M, "tocsr"):
+        return None  # other sparse formats are converted on every call: nothing stable to key on
+    return ("dense",) + _array_fingerprint(M)
+
+
+class _MatrixCache:
+    """LRU cache of uploaded (optionally re-ordered) device matrices, bounded by HG_MATRIX_CACHE_GB
+    (default 32 of the 180 GB)."""
+
+    def __init__(self):
+        self.entries = collections.OrderedDict()  # key -> DeviceMatrix
+        self.hits = self.misses = 0
+        self.cap = int(float(os.environ.get("HG_MATRIX_CACHE_GB", "32")) * (1 << 30))
+
+    @staticmethod
+    def _bytes(d):
+        return d.nnz * 12 + (d.shape[0] + 1) * 8
+
+    def get(self, key):
+        d = self.entries.get(key)
+        if d is not None and d._h and d.ctx._h:
+            self.entries.move_to_end(key)
+            self.hits += 1
+            return d
+        if d is not None:
+            del self.entries[key]
+        self.misses += 1
+        return None
+
+    def put(self, key, d):
+        if self.cap <= 0 or self._bytes(d) > self.cap:
+            return False
+        self.entries[key] = d
+        total = sum(self._bytes(v) for v in self.entries.values())
+        while total > self.cap and len(self.entries) > 1:
+            _, old = self.entries.popitem(last=False)
+            total -= self._bytes(old)
+            old.close()
+        return True
+
+    def clear(self):
+        for d in self.entries.values():
+            d.close()
+        self.entries.clear()
+
+
+_matrix_cache = _MatrixCache()
+
+
+def clear_matrix_cache() -> None:
+    """Drop every cached device matrix (and the memoised gcv_function factorisations)."""
+    _matrix_cache.clear()
+    _gcv_cache.clear()
+
+
+def matrix_cache_info() -> dict:
+    return {"entries": len(_matrix_cache.entries), "hits": _matrix_cache.hits, "misses": _matrix_cache.misses,
+            "bytes": sum(_matrix_cache._bytes(v) for v in _matrix_cache.entries.values())}
+
+
+def _resident(ctx, M, role="plain", nperm=None, cache=True, stats=None):
+    """Device matrix for host matrix ``M`` -> (DeviceMatrix, owned).  ``role`` 'A' applies ``nperm`` to the
+    columns (entry order kept), 'B' to the rows; ``owned`` tells the caller to close it after the call."""
+    if M is None:
+        return None, False
+    t0 = time.perf_counter()
+    key = None
+    perm_fp = None if nperm is None else _array_fingerprint(nperm)
+    if isinstance(M, DeviceMatrix):
+        if nperm is None:
+            return M, False
+        base, base_owned = M, False
+    else:
+        fp = _matrix_fingerprint(M) if cache and _matrix_cache.cap > 0 else None
+        if fp is not None:
+            key = (id(ctx), ctx._h.value, fp, role if nperm is not None else "plain", perm_fp)
+            hit = _matrix_cache.get(key)
+            if hit is not None:
+                if stats is not None:
+                    stats["cache_hits"] = stats.get("cache_hits", 0) + 1
+                    stats["fingerprint_ms"] = stats.get("fingerprint_ms", 0.0) + 1e3 * (time.perf_counter() - t0)
+                return hit, False
+        t1 = time.perf_counter()
+        base, base_owned = DeviceMatrix.from_any(M, ctx), True
+        if stats is not None:
+            stats["fingerprint_ms"] = stats.get("fingerprint_ms", 0.0) + 1e3 * (t1 - t0)
+            stats["upload_ms"] = stats.get("upload_ms", 0.0) + 1e3 * (time.perf_counter() - t1)
+    d = base
+    if nperm is not None:
+        t2 = time.perf_counter()
+        d = base.permute(None, nperm, sort=False) if role == "A" else base.permute(nperm, None)
+        if base_owned:
+            base.close()
+        if stats is not None:
+            stats["reorder_ms"] = stats.get("reorder_ms", 0.0) + 1e3 * (time.perf_counter() - t2)
+    if key is not None and _matrix_cache.put(key, d):
+        return d, False
+    return d, (d is not M)
+
+
+class _Uploaded:
+    """Device-resident versions of host matrices for one solver call (cached across calls)."""
+
+    def __init__(self, ctx, *mats, cache=True, stats=None):
         self.ctx = ctx
         self.owned = []
         self.out = []
         for M in mats:
-            if M is None or isinstance(M, DeviceMatrix):
-                self.out.append(M)
-            else:
-                d = DeviceMatrix.from_any(M, ctx)
+            d, owned = _resident(ctx, M, cache=cache, stats=stats)
+            if owned:
                 self.owned.append(d)
-                self.out.append(d)
+            self.out.append(d)
 
     def __enter__(self):
         return self.out
@@ -298,71 +434,86 @@ def _extras(maxit, n, want, want_x=True, aux=False):
     return ex, bufs
 
 
-def _rtp(fn_name, A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm=None):
+def _rtp(fn_name, A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm=None, cache=True,
+         stats=None):
     ctx = _ctx_of(ctx, A, B)
     maxit = int(maxit)
-    t_up = time.perf_counter()
-    with _Uploaded(ctx, A, B) as (dA, dB):
-        if _TRACE:
-            print(f"[hg trace] {fn_name}: upload {1e3 * (time.perf_counter() - t_up):.1f} ms", file=sys.stderr)
+    st = {} if (stats is not None or _TRACE) else None
+    if nperm is not None:
+        # run the n-space of the solve in the caller's cache-friendly order: A(:,q), B(q,:),
+        # x_true(q) — an orthogonal similarity of B*A + lambda*I (hgmres.h: hg_matrix_permute)
+        nperm = np.ascontiguousarray(nperm, dtype=np.int32)
+    dA, ownA = _resident(ctx, A, "A", nperm, cache, st)
+    dB, ownB = _resident(ctx, B, "B", nperm, cache, st)
+    try:
         m, n = dA.shape
         b = _vec(b, m, "b")
         x_true = _vec(x_true, n, "x_true")
         if nperm is not None:
-            # run the n-space of the solve in the caller's cache-friendly order: A(:,q), B(q,:),
-            # x_true(q) — an orthogonal similarity of B*A + lambda*I (hgmres.h: hg_matrix_permute)
-            nperm = np.ascontiguousarray(nperm, dtype=np.int32)
-            t_pm = time.perf_counter()
-            dA, dB = dA.permute(None, nperm, sort=False), dB.permute(nperm, None)
             x_true = np.ascontiguousarray(x_true[nperm])
-            if _TRACE:
-                print(f"[hg trace] {fn_name}: n-space re-ordering {1e3 * (time.perf_counter() - t_pm):.1f} ms",
-                      file=sys.stderr)
         x = np.zeros(n)
         err = np.zeros(maxit)
         res = np.zeros(maxit)
         niters, x_valid = C.c_int(), C.c_int()
         opts = HgSolverOpts()
         opts.residual_mode = int(residual_mode)
-        ex, bufs = _extras(maxit, n, extras is not None)
+        want_x = extras is not None and extras.get("want_X", True)
+        ex, bufs = _extras(maxit, n, extras is not None, want_x=want_x)
         t0 = time.perf_counter()
         check(getattr(ctx._lib, fn_name)(ctx._h, dA._h, dB._h, _ptr(b), _ptr(x_true), float(tol), maxit,
                                          float(lam), _ptr(x), _ptr(err), _ptr(res), C.byref(niters),
                                          C.byref(x_valid), C.byref(opts), C.byref(ex) if ex else None))
-        if _TRACE:
-            print(f"[hg trace] {fn_name}: C call {1e3 * (time.perf_counter() - t0):.1f} ms", file=sys.stderr)
-        if nperm is not None:
+        if st is not None:
+            st["solve_ms"] = 1e3 * (time.perf_counter() - t0)
+            buf = (C.c_double * 8)()
+            check(ctx._lib.hg_last_solve_stats(buf, 8))
+            st.update(setup_ms=buf[0], loop_ms=buf[1], host_solve_ms=buf[2], host_wait_ms=buf[3], d2h_ms=buf[4])
+    finally:
+        if ownA:
             dA.close()
+        if ownB:
             dB.close()
+    if _TRACE:
+        print(f"[hg trace] {fn_name}: " + ", ".join(f"{k} {v:.1f}" if isinstance(v, float) else f"{k} {v}"
+                                                    for k, v in st.items()), file=sys.stderr)
+    if stats is not None:
+        stats.update(st)
     k = niters.value
     if nperm is not None:
         xu = np.empty_like(x)
         xu[nperm] = x
         x = xu
     if extras is not None:
-        X = bufs["X"][:, :k]
-        if nperm is not None:
-            Xu = np.empty_like(X)
-            Xu[nperm, :] = X
-            X = Xu
-        extras.update(H=bufs["H"], beta=float(bufs["beta"][0]), X=X)
+        extras.update(H=bufs["H"], beta=float(bufs["beta"][0]))
+        if want_x:
+            X = bufs["X"][:, :k]
+            if nperm is not None:
+                Xu = np.empty_like(X)
+                Xu[nperm, :] = X
+                X = Xu
+            extras["X"] = X
     return (x if x_valid.value else None), err[:k], res[:k], k
 
 
 def hybrid_ab_gmres_rtp(A, B, b, x_true, tol, maxit, lam, *, ctx=None, residual_mode=0, extras=None,
-                        nperm=None):
+                        nperm=None, cache=True, stats=None):
     """``hybrid_ab_gmres_rtp.m:1`` — same positional arguments and outputs.
     ``x`` is ``None`` exactly when the reference leaves it unassigned (``:25``).
     ``nperm`` (optional, e.g. ``ct.tile_permutation(N)``) runs the solve with the n-space in that
-    order on the device; inputs and outputs stay in the caller's order."""
-    return _rtp("hg_hybrid_ab_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm)
+    order on the device; inputs and outputs stay in the caller's order.  Host matrices stay resident
+    on the device between calls (``cache=False`` uploads afresh; see :func:`clear_matrix_cache`).
+    ``extras`` (dict) receives ``H``, ``beta`` and the iterates ``X`` (skip those with
+    ``extras={"want_X": False}``); ``stats`` (dict) the wall-clock breakdown of the call in ms."""
+    return _rtp("hg_hybrid_ab_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm,
+                cache, stats)
 
 
 def hybrid_ba_gmres_rtp(A, B, b, x_true, tol, maxit, lam, *, ctx=None, residual_mode=0, extras=None,
-                        nperm=None):
-    """``hybrid_ba_gmres_rtp.m:1`` — same positional arguments and outputs (``nperm``: see
+                        nperm=None, cache=True, stats=None):
+    """``hybrid_ba_gmres_rtp.m:1`` — same positional arguments and outputs (keyword arguments: see
     :func:`hybrid_ab_gmres_rtp`)."""
-    return _rtp("hg_hybrid_ba_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm)
+    return _rtp("hg_hybrid_ba_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm,
+                cache, stats)
 
 
 def _gkb(fn_name, A, b, x_true, tol, maxit, lam, ctx, At, extras, five_outputs=False):
@@ -558,29 +709,38 @@ def gcv_prepare(A, B, b, m, k_gcv, gcv_type, *, ctx=None) -> GcvProblem:
     return GcvProblem(h, ctx._lib)
 
 
-_gcv_cache: dict = {}
+_gcv_cache: "collections.OrderedDict" = collections.OrderedDict()
 _GCV_CACHE_MAX = 8
 
 
 def gcv_function(lam, A, B, b, m, k_gcv, gcv_type, *, ctx=None):
     """``gcv_val = gcv_function(lambda,A,B,b,m,k_gcv,gcv_type)`` (``gcv_function.m:1``).
 
-    ``fminbnd`` calls this ~30 times with the same ``(A,B,b,m,k_gcv,gcv_type)``;
-    the device Arnoldi is memoised on the identity of ``A``/``B`` and the bytes
-    of ``b`` so it runs once (the MEX gateway does the same)."""
+    ``fminbnd`` calls this ~30 times with the same ``(A,B,b,m,k_gcv,gcv_type)``; the device Arnoldi
+    (``:4-32``) is memoised on the CONTENT of the inputs — a checksum of A's and B's arrays (complete up
+    to 8 MB per array, sampled above, see ``_array_fingerprint``) and of ``b`` — so it runs once per
+    distinct problem, and a new ``B_pert`` / ``b_noise`` built at a recycled address (the loops of
+    ``plot_error_vs_mismatch_norm.m:30-49``) or an in-place edit is a miss, not a stale hit."""
     b_arr = np.ascontiguousarray(np.asarray(b, dtype=np.float64).reshape(-1))
-    key = (id(A), id(B), hash(b_arr.tobytes()), int(m), int(k_gcv), gcv_type)
-    hit = _gcv_cache.get(key)
-    if hit is not None and hit[1]() is A and hit[2]() is B:
-        return hit[0].eval(lam)
+
+    def fp(M):
+        if isinstance(M, DeviceMatrix):
+            return ("device", id(M), M._h.value if M._h else None)
+        return _matrix_fingerprint(M)
+
+    fa, fb = fp(A), fp(B)
+    key = None
+    if fa is not None and fb is not None:
+        key = (fa, fb, zlib.crc32(b_arr.view(np.uint8)), b_arr.shape[0], int(m), int(k_gcv), gcv_type)
+        hit = _gcv_cache.get(key)
+        if hit is not None:
+            _gcv_cache.move_to_end(key)
+            return hit.eval(lam)
     prob = gcv_prepare(A, B, b_arr, m, k_gcv, gcv_type, ctx=ctx)
-    try:
-        entry = (prob, weakref.ref(A), weakref.ref(B))
-    except TypeError:  # numpy arrays / objects without weakref support: hold a strong ref
-        entry = (prob, (lambda o=A: o), (lambda o=B: o))
-    if len(_gcv_cache) >= _GCV_CACHE_MAX:
-        _gcv_cache.pop(next(iter(_gcv_cache)))
-    _gcv_cache[key] = entry
+    if key is not None:
+        while len(_gcv_cache) >= _GCV_CACHE_MAX:
+            _gcv_cache.popitem(last=False)
+        _gcv_cache[key] = prob
     return prob.eval(lam)
 
 

@@ -4,6 +4,7 @@ all-reduce, all-gather) are issued by ``libhgmres.so`` on its own stream."""
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import numpy as np
 
@@ -98,25 +99,19 @@ class ShardedArnoldi:
             self._h = None
 
 
-def _dist_rtp(kind, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras, nperm=None):
+def _dist_rtp(kind, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras, nperm=None, cache=True, stats=None):
     from ._lib import HgExtras, c_double_p
+    from .api import _resident
     ctx = comm.ctx
     maxit = int(maxit)
     n = A_p.shape[1]
     b_p = _vec(b_p, A_p.shape[0], "b_p")
     x_true = _vec(x_true, n, "x_true")
-    own = []
-    if not isinstance(A_p, DeviceMatrix):
-        A_p = DeviceMatrix.from_any(A_p, ctx)
-        own.append(A_p)
-    if not isinstance(B_p, DeviceMatrix):
-        B_p = DeviceMatrix.from_any(B_p, ctx)
-        own.append(B_p)
     if nperm is not None:  # n-space order of the solve (api._rtp): A_p(:,q), B^p(q,:), x_true(q)
         nperm = np.ascontiguousarray(nperm, dtype=np.int32)
-        A_p, B_p = A_p.permute(None, nperm, sort=False), B_p.permute(nperm, None)
-        own += [A_p, B_p]
         x_true = np.ascontiguousarray(x_true[nperm])
+    dA, ownA = _resident(ctx, A_p, "A", nperm, cache, stats)
+    dB, ownB = _resident(ctx, B_p, "B", nperm, cache, stats)
     x, err, res = np.zeros(n), np.zeros(maxit), np.zeros(maxit)
     niters, x_valid = C.c_int(), C.c_int()
     ex, bufs = None, None
@@ -125,11 +120,18 @@ def _dist_rtp(kind, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras, nperm=
         ex = HgExtras()
         ex.H = bufs["H"].ctypes.data_as(c_double_p)
         ex.beta = bufs["beta"].ctypes.data_as(c_double_p)
-    check(ctx._lib.hg_dist_hybrid_rtp(kind, ctx._h, comm._h, A_p._h, B_p._h, _ptr(b_p), _ptr(x_true), float(tol),
-                                      maxit, float(lam), _ptr(x), _ptr(err), _ptr(res), C.byref(niters),
-                                      C.byref(x_valid), C.byref(ex) if ex else None))
-    for d in own:
-        d.close()
+    try:
+        t0 = time.perf_counter()
+        check(ctx._lib.hg_dist_hybrid_rtp(kind, ctx._h, comm._h, dA._h, dB._h, _ptr(b_p), _ptr(x_true), float(tol),
+                                          maxit, float(lam), _ptr(x), _ptr(err), _ptr(res), C.byref(niters),
+                                          C.byref(x_valid), C.byref(ex) if ex else None))
+        if stats is not None:
+            stats["solve_ms"] = 1e3 * (time.perf_counter() - t0)
+    finally:
+        if ownA:
+            dA.close()
+        if ownB:
+            dB.close()
     k = niters.value
     if nperm is not None:
         xu = np.empty_like(x)
@@ -140,16 +142,19 @@ def _dist_rtp(kind, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras, nperm=
     return (x if x_valid.value else None), err[:k], res[:k], k
 
 
-def hybrid_ab_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lam, *, extras=None, nperm=None):
+def hybrid_ab_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lam, *, extras=None, nperm=None, cache=True,
+                        stats=None):
     """Sharded ``hybrid_ab_gmres_rtp.m``: ``A_p``/``B_p`` are this rank's shards (device matrices, or
-    host matrices uploaded for the call), ``b_p`` its slice of ``b``; returns the reference's four
-    outputs on every rank.  ``nperm``: n-space order on the device, as in the single-GPU solver."""
-    return _dist_rtp(0, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras, nperm)
+    host matrices kept resident on the device between calls), ``b_p`` its slice of ``b``; returns the
+    reference's four outputs on every rank.  ``nperm``: n-space order on the device, as in the single-GPU
+    solver."""
+    return _dist_rtp(0, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras, nperm, cache, stats)
 
 
-def hybrid_ba_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lam, *, extras=None, nperm=None):
+def hybrid_ba_gmres_rtp(comm, A_p, B_p, b_p, x_true, tol, maxit, lam, *, extras=None, nperm=None, cache=True,
+                        stats=None):
     """Sharded ``hybrid_ba_gmres_rtp.m``."""
-    return _dist_rtp(1, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras, nperm)
+    return _dist_rtp(1, comm, A_p, B_p, b_p, x_true, tol, maxit, lam, extras, nperm, cache, stats)
 
 
 def gcv_prepare(comm, A_p, B_p, b_p, m, k_gcv, gcv_type):
@@ -199,6 +204,17 @@ def lsqr_solver(comm, A_p, b_p, x_true, tol, maxit, *, At_p=None):
 
 def lsmr_solver(comm, A_p, b_p, x_true=None, tol=1e-6, maxit=None, *, At_p=None):
     """Sharded ``lsmr_solver.m`` (five outputs)."""
-    if maxit is None:
-        maxit = min(A_p.shape[1], 10 ** 9)
+    if maxit is None:  # lsmr_solver.m:5 — min(m, n) with the GLOBAL row count m = sum of the shards' rows
+        m = A_p.shape[0]
+        try:
+            import torch
+            import torch.distributed as dist
+            if dist.is_initialized() and comm.world > 1:
+                t = torch.tensor([float(m)], dtype=torch.float64,
+                                 device="cuda" if dist.get_backend() == "nccl" else "cpu")
+                dist.all_reduce(t)
+                m = int(t.item())
+        except ImportError:
+            pass
+        maxit = min(m, A_p.shape[1])
     return _dist_gkb(3, comm, A_p, b_p, x_true, tol, maxit, None, At_p)

@@ -575,6 +575,15 @@ class Parser:
             elif tok.val == "." and self.peek(1).kind == "id" and not tok.sp:
                 self.next()
                 a = ("field", a, self.next().val)
+            elif tok.val == "." and self.is_op("(", 1) and not tok.sp:  # dynamic field  s.(expr)
+                self.next()
+                self.next()
+                save_m, self.in_matrix = self.in_matrix, 0
+                save_i, self.in_index = self.in_index, 0
+                e = self.parse_expr()
+                self.expect_op(")")
+                self.in_matrix, self.in_index = save_m, save_i
+                a = ("dynfield", a, e)
             else:
                 break
         return a
@@ -764,6 +773,7 @@ class Interp:
         self.builtins = _make_builtins(self)
         self.calls = []     # trace of user-function calls (name, filename)
         self.last_ws = {}   # function name -> workspace at the end of its last call (H, Q, beta ...)
+        self.out = []       # text written by fprintf / disp
 
     # -- loading ------------------------------------------------------------------
     def load_source(self, src, filename="<string>"):
@@ -1193,11 +1203,12 @@ class Interp:
             return np.array([[float(shp[pos])]])
         if k == "colon":
             return ":"
-        if k == "field":
+        if k in ("field", "dynfield"):
             base = self.eval(node[1], fr)
-            if isinstance(base, dict) and node[2] in base:
-                return base[node[2]]
-            raise MlabError(f"no field {node[2]!r}")
+            name = node[2] if k == "field" else self.eval(node[2], fr)
+            if isinstance(base, dict) and isinstance(name, str) and name in base:
+                return base[name]
+            raise MlabError(f"reference to non-existent field {name!r}")
         raise MlabError(f"cannot evaluate node {k}")
 
     def build_matrix(self, rows, fr):
@@ -1303,6 +1314,8 @@ class Interp:
             sub = self._take(arr, idx)
             return "".join(chr(int(c)) for c in sub.reshape(-1))
         arr = mat(base)
+        if len(arg_nodes) == 1 and arg_nodes[0][0] == "colon":  # x(:) is always a column
+            return dense(arr).reshape(-1, 1, order="F").copy()
         idx = self.eval_indices(arg_nodes, arr, fr)
         return self._take(arr, idx)
 
@@ -1884,8 +1897,77 @@ def _make_builtins(ip: Interp):
     def _noop(args, nargout):
         return ()
 
-    for nm in ("fprintf", "disp", "warning", "tic", "figure", "drawnow", "clc"):
+    for nm in ("warning", "tic", "figure", "drawnow", "clc"):
         B[nm] = _noop
+
+    def _fmt_args(args):
+        out = []
+        for a in args:
+            if isinstance(a, str):
+                out.append(a)
+            else:
+                v = dense(numeric(a)).reshape(-1, order="F")
+                out.extend(float(x) if not float(x).is_integer() else int(x) for x in np.real(v))
+        return out
+
+    @reg("sprintf")
+    def _sprintf(args, nargout):
+        fmt = args[0].replace("\\n", "\n").replace("\\t", "\t")
+        vals = _fmt_args(args[1:])
+        nspec = len(re.findall(r"%(?!%)", fmt))
+        if nspec == 0:
+            return fmt.replace("%%", "%")
+        chunks = []
+        for i in range(0, max(len(vals), 1), nspec):  # MATLAB recycles the format over the arguments
+            part = vals[i:i + nspec]
+            if len(part) < nspec:
+                break
+            part = [float(v) if isinstance(v, int) and re.search(r"%[-+0-9.]*[efg]", fmt) and False else v for v in part]
+            try:
+                chunks.append(fmt % tuple(part))
+            except TypeError:
+                chunks.append(fmt % tuple(float(v) if not isinstance(v, str) else v for v in part))
+        return "".join(chunks)
+
+    @reg("fprintf")
+    def _fprintf(args, nargout):
+        if args and not isinstance(args[0], str):
+            args = args[1:]  # file id
+        ip.out.append(_sprintf(args, 1))
+        return ()
+
+    @reg("disp")
+    def _disp(args, nargout):
+        ip.out.append(str(args[0]) + "\n")
+        return ()
+
+    @reg("load")
+    def _load(args, nargout):
+        import scipy.io as sio
+        raw = sio.loadmat(args[0], squeeze_me=False, struct_as_record=False)
+        out = {}
+        for k, v in raw.items():
+            if k.startswith("__"):
+                continue
+            if sp.issparse(v):
+                out[k] = v.tocsc()
+            elif isinstance(v, np.ndarray) and v.dtype.kind in "US":
+                out[k] = str(v.reshape(-1)[0]) if v.size else ""
+            elif isinstance(v, np.ndarray) and v.dtype.kind in "iufb":
+                out[k] = np.atleast_2d(v).astype(float)
+            else:
+                out[k] = v
+        return out
+
+    @reg("isfield")
+    def _isfield(args, nargout):
+        return np.array([[isinstance(args[0], dict) and isinstance(args[1], str) and args[1] in args[0]]])
+
+    @reg("arrayfun")
+    def _arrayfun(args, nargout):
+        f, x = args[0], dense(numeric(args[1]))
+        vals = [scalar(f.fn([np.array([[v]])], 1)[0]) for v in x.reshape(-1, order="F")]
+        return np.array(vals, dtype=float).reshape(x.shape, order="F")
 
     @reg("toc")
     def _toc(args, nargout):
