@@ -175,7 +175,9 @@ def verify_inputs(name, A, B, views=(0, 1, 77)):
     Bo = ct.backprojector_pixel_driven(N, angles[views], p, geom).tocsr()
     ok = True
     for i, v in enumerate(views):
-        a_dev, a_or = A[v * p:(v + 1) * p], Ao[i * p:(i + 1) * p]
+        a_dev, a_or = A[v * p:(v + 1) * p].copy(), Ao[i * p:(i + 1) * p].copy()
+        a_dev.sort_indices()  # the device generator keeps a ray's entries in traversal order
+        a_or.sort_indices()
         ok = ok and a_dev.nnz == a_or.nnz and np.array_equal(a_dev.indices, a_or.indices) and \
             np.array_equal(a_dev.data, a_or.data)
         b_dev, b_or = B[:, v * p:(v + 1) * p].tocsr(), Bo[:, i * p:(i + 1) * p].tocsr()
@@ -205,11 +207,15 @@ def parity_vs_oracle(A, B, b, x_true, res_dev, H_dev, K=PARITY_K):
                        for j in range(K)])
         out[f"max_rel_residual_hist_k{K}_vs_{orth}"] = float(dres.max())
         out[f"max_rel_H_col_k{K}_vs_{orth}"] = float(dH.max())
+        out[f"max_rel_residual_hist_k20_vs_{orth}"] = float(dres[:20].max())
+        out[f"max_rel_H_col_k20_vs_{orth}"] = float(dH[:20].max())
         out[f"first_k_above_1e-8_vs_{orth}"] = {"residual": (np.flatnonzero(dres > 1e-8)[:1] + 1).tolist(),
                                                 "H_col": (np.flatnonzero(dH > 1e-8)[:1] + 1).tolist()}
         if orth == "mgs":
             res_mgs, H_mgs = res, Ho
         else:  # how well the problem itself determines these numbers: the oracle against itself
+            out["note"] = ("from k ~ 22 on this problem does not determine H / the histories to 1e-8: the oracle's own "
+                           "MGS and CGS2 runs (oracle_mgs_vs_cgs2_*) part by as much as the device parts from either")
             out["oracle_mgs_vs_cgs2_residual"] = float(np.max(np.abs(res - res_mgs) / res_mgs))
             out["oracle_mgs_vs_cgs2_H_col"] = float(max(
                 np.linalg.norm(Ho[: j + 2, j] - H_mgs[: j + 2, j]) / np.linalg.norm(H_mgs[: j + 2, j]) for j in range(K)))
@@ -576,7 +582,7 @@ def main():
             # the device Arnoldi handle timed above and the solver must tell the same story
             hk = min(PARITY_K, maxit)
             same = float(max(np.linalg.norm(ex["H"][: j + 2, j] - r["H"][: j + 2, j]) / np.linalg.norm(r["H"][: j + 2, j])
-                             for j in range(hk)))
+                             for j in range(min(hk, 20))))
             if sharded:
                 # rank 0 needs the whole problem for the oracle: generated once more, unsharded
                 if rank == 0:
@@ -591,7 +597,7 @@ def main():
             else:
                 par = parity_vs_oracle(A, B, b, x_true, res_p, ex["H"])
             if par is not None:
-                par["timed_arnoldi_vs_solver_H_col"] = same
+                par["timed_arnoldi_vs_solver_H_col_k20"] = same  # entry order within the rows differs between the two
                 par["full_run_final_residual"] = {"device_k%d" % maxit: float(res[-1])}
                 line["parity"] = par
         if not sharded and not args.no_cpu:

@@ -26,6 +26,7 @@ from .api import (  # noqa: E402,F401
     gcv_prepare,
     hybrid_ab_gmres_rtp,
     hybrid_ba_gmres_rtp,
+    hybrid_gmres_gcv,
     hybrid_lsmr_solver,
     hybrid_lsqr_solver,
     lsmr_solver,

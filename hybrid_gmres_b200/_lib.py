@@ -83,6 +83,7 @@ PROTOTYPES = {
     "hg_multidot": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp]),
     "hg_lincomb": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _d, _vp, _vp, c_double_p]),
     "hg_cgs_mid": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _vp, _vp]),
+    "hg_cgs2_step": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp, _vp]),
     "hg_arnoldi_create": (_i, [_vp, _vp, _vp, _i, _i, c_void_pp]),
     "hg_arnoldi_destroy": (_i, [_vp]),
     "hg_arnoldi_set_rhs": (_i, [_vp, _vp]),
@@ -98,6 +99,8 @@ PROTOTYPES = {
     "hg_last_solve_stats": (_i, [_vp, _i]),
     "hg_gmres_ptr": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _d, _i, _d, _vp, _vp, _vp, c_int_p, c_int_p,
                           C.POINTER(HgExtras)]),
+    "hg_gmres_ptr_gcv": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _d, _i, _vp, _i, _vp, _vp, _vp, _vp, c_int_p, c_int_p,
+                              C.POINTER(HgExtras)]),
     "hg_gcv_prepare": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, c_void_pp]),
     "hg_gcv_eval": (_i, [_vp, _d, c_double_p]),
     "hg_gcv_get": (_i, [_vp, _vp, c_double_p]),

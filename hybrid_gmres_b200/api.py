@@ -31,7 +31,7 @@ from ._lib import HgExtras, HgSolverOpts, check
 __all__ = [
     "Context", "DeviceMatrix", "Arnoldi", "GcvProblem", "default_context",
     "hybrid_ab_gmres_rtp", "hybrid_ba_gmres_rtp", "hybrid_lsqr_solver", "hybrid_lsmr_solver",
-    "lsqr_solver", "lsmr_solver", "gcv_function", "gcv_prepare", "fminbnd_gcv",
+    "lsqr_solver", "lsmr_solver", "gcv_function", "gcv_prepare", "fminbnd_gcv", "hybrid_gmres_gcv",
     "KERNEL_CLASSES", "set_option", "clear_matrix_cache", "matrix_cache_info",
 ]
 
@@ -257,10 +257,10 @@ class DeviceMatrix:
 # fminbnd, the lambda sweeps of analyze_regularization.m:21-33, the solver comparisons of
 # run_equivalence_plots.m:13-22).  Uploaded (and re-ordered) matrices therefore stay on the device, keyed
 # on what identifies the caller's arrays: buffer addresses, shape, nnz and a content checksum — complete
-# for arrays up to 8 MB, a strided 1 MB sample plus head and tail above that (a 7.4 GB pair is not
+# for arrays up to 1 MB, a strided 1 MB sample plus head and tail above that (a 7.4 GB pair is not
 # re-read on every call; an in-place edit that touches none of the sampled bytes goes unnoticed — pass
 # ``cache=False`` or call :func:`clear_matrix_cache` after editing a large matrix in place).
-_FULL_HASH_BYTES = 8 << 20
+_FULL_HASH_BYTES = 1 << 20
 _SAMPLE_CHUNKS, _SAMPLE_CHUNK_BYTES = 4096, 256
 
 
@@ -718,7 +718,7 @@ def gcv_function(lam, A, B, b, m, k_gcv, gcv_type, *, ctx=None):
 
     ``fminbnd`` calls this ~30 times with the same ``(A,B,b,m,k_gcv,gcv_type)``; the device Arnoldi
     (``:4-32``) is memoised on the CONTENT of the inputs — a checksum of A's and B's arrays (complete up
-    to 8 MB per array, sampled above, see ``_array_fingerprint``) and of ``b`` — so it runs once per
+    to 1 MB per array, sampled above, see ``_array_fingerprint``) and of ``b`` — so it runs once per
     distinct problem, and a new ``B_pert`` / ``b_noise`` built at a recycled address (the loops of
     ``plot_error_vs_mismatch_norm.m:30-49``) or an in-place edit is a miss, not a stale hit."""
     b_arr = np.ascontiguousarray(np.asarray(b, dtype=np.float64).reshape(-1))
@@ -773,6 +773,32 @@ def _ptr_solver(kind, hybrid, A, B, b, x_true, tol, maxit, lam, ctx, extras):
     if extras is not None:
         extras.update(H=bufs["H"], beta=float(bufs["beta"][0]), X=bufs["X"][:, :k])
     return (x if x_valid.value else None), err[:k], res[:k], k
+
+
+def hybrid_gmres_gcv(kind, A, B, b, x_true, tol, maxit, lambda_range, *, ctx=None, extras=None):
+    """Hybrid AB- (``kind='ab'``) / BA-GMRES (``'ba'``) with the regularisation parameter chosen at every
+    iteration: ``lambda_k`` is the grid minimiser of the GCV function of the growing Hessenberg matrix,
+    as ``compute_gcv_surface`` of ``plot_gcv_surface.m:58-122`` computes it, and the iterate is the PTR
+    hybrid one (``ABgmres_hybrid_bounds.m:34-38``) for that ``lambda_k``.  Returns
+    ``(x, error_norm, residual_norm, niters, lambda_path)``."""
+    ctx = _ctx_of(ctx, A, B)
+    maxit = int(maxit)
+    lambdas = np.ascontiguousarray(np.asarray(lambda_range, dtype=np.float64).reshape(-1))
+    with _Uploaded(ctx, A, B) as (dA, dB):
+        m, n = dA.shape
+        b = _vec(b, m, "b")
+        x_true = _vec(x_true, n, "x_true")
+        x, err, res, path = np.zeros(n), np.zeros(maxit), np.zeros(maxit), np.zeros(maxit)
+        niters, x_valid = C.c_int(), C.c_int()
+        ex, bufs = _extras(maxit, n, extras is not None)
+        check(ctx._lib.hg_gmres_ptr_gcv(ctx._h, {"ab": 0, "ba": 1}[kind], dA._h, dB._h, _ptr(b), _ptr(x_true),
+                                        float(tol), maxit, _ptr(lambdas), lambdas.shape[0], _ptr(x), _ptr(err),
+                                        _ptr(res), _ptr(path), C.byref(niters), C.byref(x_valid),
+                                        C.byref(ex) if ex else None))
+    k = niters.value
+    if extras is not None:
+        extras.update(H=bufs["H"], beta=float(bufs["beta"][0]), X=bufs["X"][:, :k])
+    return (x if x_valid.value else None), err[:k], res[:k], k, path[:k]
 
 
 def ABgmres_hybrid_bounds(A, B, b, x_true, tol, maxit, lam, DeltaM=None, *, ctx=None, extras=None):

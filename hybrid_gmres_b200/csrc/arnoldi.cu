@@ -104,7 +104,8 @@ extern "C" int hg_arnoldi_create(hg_ctx* ctx, const hg_matrix* A, const hg_matri
     a->ldt = round_up(std::max<int64_t>(a->nt, 1), 32);
     const int nslabs = hg_multidot_nslabs(ctx, std::max(a->nq, a->nt));
     const size_t npart = (size_t)(kmax + 2) *
-                         (size_t)(std::max(nslabs, hg_update_dot_ntiles(std::max(a->nq, a->nt))) + 1);
+                         (size_t)(std::max(std::max(nslabs, ctx->sm_count),
+                                           hg_update_dot_ntiles(std::max(a->nq, a->nt))) + 1);
     const size_t nstat = hg_stat_capacity(ctx, std::max(a->nq, a->nt));
     cudaError_t e = cudaSuccess;
     auto alloc = [&](double** p, size_t n) {
@@ -205,6 +206,13 @@ static int arnoldi_step(hg_arnoldi* a, int kk) {
     // CGS2: h1 = Q_k' v ; v -= Q_k h1 ; h2 = Q_k' v ; v -= Q_k h2 ; H(1:k,k) = h1 + h2
     // (the reference's MGS sweep, hybrid_ab_gmres_rtp.m:20-23, in its two-pass
     //  classical form mandated by the north star)
+    if (hg_cgs2_step_eligible(ctx, a->nq, kk)) {
+        // small / medium vectors: the whole orthogonalisation, norm and normalisation in one persistent kernel
+        HG_TRY(hg_k_cgs2_step(ctx, a->Q, a->ldq, a->nq, kk, a->w0, a->w1, qnext, Hcol, a->d_hcur, a->partials));
+        HG_CUDA(cudaMemcpyAsync(a->h_H + (size_t)(kk - 1) * a->ldh(), Hcol, (size_t)(kk + 1) * 8,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+        return HG_OK;
+    }
     int ns = 0, np = 0;
     HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->nq, kk, a->w0, a->partials, &ns));
     HG_TRY(hg_k_reduce(ctx, a->partials, ns, kk, Hcol, false, a->d_hcur, false));
@@ -277,7 +285,8 @@ extern "C" int hg_arnoldi_step_bytes(hg_arnoldi* a, int k, double* bytes) {
     // (iw = 4, or 2 + base words for the sliced form with 16-bit offsets).  CGS2(k) = 32 k n with
     // separate update / multi-dot kernels, 24 k n when the middle stage is the one-pass staged kernel.
     const double nq = (double)a->nq, nt = (double)a->nt;
-    const bool one_pass = hg_cgs_fused_mode() == 2 && hg_cgs_staged_nparts(a->ctx, a->nq, k) > 0;
+    const bool one_pass = hg_cgs2_step_eligible(a->ctx, a->nq, k) ||
+                          (hg_cgs_fused_mode() == 2 && hg_cgs_staged_nparts(a->ctx, a->nq, k) > 0);
     *bytes = hg_spmv_stream_bytes(a->A) + hg_spmv_stream_bytes(a->B) + 16.0 * nt + 88.0 * nq +
              (one_pass ? 24.0 : 32.0) * (double)k * nq;
     return HG_OK;
@@ -715,10 +724,13 @@ extern "C" int hg_gcv_destroy(hg_gcv* g) {
 // (BA); projected problem: Tikhonov on H (hybrid) or plain least squares.  The filter-factor
 // bound outputs (phi, dphi; dense eig of A*B / B*A) are out of scope.
 // ===========================================================================
-extern "C" int hg_gmres_ptr(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* A, const hg_matrix* B,
-                            const double* b, const double* x_true, double tol, int maxit, double lambda,
-                            double* x, double* error_norm, double* residual_norm, int* niters, int* x_valid,
-                            hg_extras* extras) {
+// lambdas / nl / lambda_path non-null: the regularisation parameter is chosen at every iteration as the
+// grid minimiser of GCV(lambda, H_k) (compute_gcv_surface + calculate_gcv_from_H, plot_gcv_surface.m:58-122)
+static int ptr_solver(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* A, const hg_matrix* B,
+                      const double* b, const double* x_true, double tol, int maxit, double lambda,
+                      const double* lambdas, int nl, double* lambda_path,
+                      double* x, double* error_norm, double* residual_norm, int* niters, int* x_valid,
+                      hg_extras* extras) {
     HG_REQUIRE(ctx && A && B && b && x_true && x && error_norm && residual_norm && niters,
                "hg_gmres_ptr: NULL argument");
     HG_REQUIRE(kind == 0 || kind == 1, "hg_gmres_ptr: kind must be 0 (AB) or 1 (BA)");
@@ -765,7 +777,35 @@ extern "C" int hg_gmres_ptr(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* 
         const double* H = a->h_H;
         const double* hcol = H + (size_t)(k - 1) * ldh;
         if (hcol[k] == 0.0) break;  // :31
-        if (hybrid) {
+        if (hybrid && nl > 0) {
+            // lambda_k = first grid minimiser of GCV(lambda, H_k)        (plot_gcv_surface.m:92-100, :104-122)
+            std::vector<double> sq((size_t)k * k), sv(k);
+            for (int j = 0; j < k; ++j)
+                for (int i2 = 0; i2 < k; ++i2) sq[(size_t)j * k + i2] = H[(size_t)j * ldh + i2];
+            hgd::singular_values(k, sq.data(), k, sv.data());  // :111
+            const double trace_m = kind == 0 ? (double)m : (double)n;  // op_size, :66,70
+            int best = 0;
+            double vbest = 0.0;
+            for (int i2 = 0; i2 < nl; ++i2) {
+                const double v = hgd::gcv_value(lambdas[i2], H, ldh, k, beta, trace_m, sv.data());
+                if (i2 == 0 || v < vbest) {
+                    vbest = v;
+                    best = i2;
+                }
+            }
+            const double lam_k = lambdas[best];
+            lambda_path[k - 1] = lam_k;
+            // yk = (Hk'*Hk + lambda_k*I) \ (Hk'*tk), from scratch: lambda changes with k
+            std::vector<double> M((size_t)k * k);
+            for (int j = 0; j < k; ++j)
+                for (int i2 = 0; i2 < k; ++i2) {
+                    double acc = 0.0;
+                    for (int t = 0; t <= k; ++t) acc += H[(size_t)i2 * ldh + t] * H[(size_t)j * ldh + t];
+                    M[(size_t)j * k + i2] = acc + (i2 == j ? lam_k : 0.0);
+                }
+            for (int j = 0; j < k; ++j) rhs[j] = beta * H[(size_t)j * ldh];
+            hgd::solve_square(k, M.data(), k, rhs.data(), h_y.p);
+        } else if (hybrid) {
             // yk = (Hk'*Hk + lambda*I) \ (Hk'*tk): Hk'*Hk grows by bordering (column k adds row k+1,
             // which is zero in every earlier column), so the row Cholesky is continued    (:34-36)
             for (int j = 0; j < k; ++j) {
@@ -835,6 +875,24 @@ extern "C" int hg_gmres_ptr(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* 
         if (extras->H) memcpy(extras->H, a->h_H, (size_t)ldh * maxit * 8);
     }
     return HG_OK;
+}
+
+extern "C" int hg_gmres_ptr(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* A, const hg_matrix* B,
+                            const double* b, const double* x_true, double tol, int maxit, double lambda,
+                            double* x, double* error_norm, double* residual_norm, int* niters, int* x_valid,
+                            hg_extras* extras) {
+    return ptr_solver(ctx, kind, hybrid, A, B, b, x_true, tol, maxit, lambda, nullptr, 0, nullptr, x, error_norm,
+                      residual_norm, niters, x_valid, extras);
+}
+
+extern "C" int hg_gmres_ptr_gcv(hg_ctx* ctx, int kind, const hg_matrix* A, const hg_matrix* B, const double* b,
+                                const double* x_true, double tol, int maxit, const double* lambdas, int nl,
+                                double* x, double* error_norm, double* residual_norm, double* lambda_path,
+                                int* niters, int* x_valid, hg_extras* extras) {
+    HG_REQUIRE(lambdas && nl >= 1 && lambda_path, "hg_gmres_ptr_gcv: a lambda grid and lambda_path are required");
+    for (int i = 0; i < maxit; ++i) lambda_path[i] = 0.0;
+    return ptr_solver(ctx, kind, 1, A, B, b, x_true, tol, maxit, 0.0, lambdas, nl, lambda_path, x, error_norm,
+                      residual_norm, niters, x_valid, extras);
 }
 
 // plot_gcv_surface.m:58-102 (compute_gcv_surface) given the Arnoldi factorisation already held by

@@ -130,3 +130,30 @@ extern "C" int hg_cgs_mid(hg_ctx* ctx, int64_t n, int k, const double* V, int64_
     HG_CUDA(cudaStreamSynchronize(ctx->stream));
     return HG_OK;
 }
+
+
+// One whole CGS2 step on host arrays (cgs2_step.cu): hcol[0..k) = h1 + h2, hcol[k] = ||v||, q = v / ||v||.
+extern "C" int hg_cgs2_step(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, const double* w0,
+                            double* hcol, double* q) {
+    HG_REQUIRE(ctx && V && w0 && hcol && q, "hg_cgs2_step: NULL argument");
+    HG_REQUIRE(k >= 1 && n >= 1 && ld >= n, "hg_cgs2_step: bad shape");
+    HG_REQUIRE(hg_cgs2_step_eligible(ctx, n, k), "hg_cgs2_step: (n=%lld, k=%d) is outside the kernel's range",
+               (long long)n, k);
+    HG_CUDA(cudaSetDevice(ctx->device));
+    hg_alloc_scope alloc_scope(ctx);
+    DBuf dV, dw0, dw1, dq, dH, dhc, dp;
+    int64_t ldd = 0;
+    HG_TRY(upload_basis(ctx, n, k, V, ld, dV, &ldd));
+    HG_TRY(dw0.alloc((size_t)ldd));
+    HG_TRY(dw1.alloc((size_t)ldd));
+    HG_TRY(dq.alloc((size_t)ldd));
+    HG_TRY(dH.alloc((size_t)k + 2));
+    HG_TRY(dhc.alloc((size_t)k + 2));
+    HG_TRY(dp.alloc((size_t)(k + 2) * (size_t)(ctx->sm_count + 1)));
+    HG_CUDA(cudaMemcpyAsync(dw0.p, w0, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    HG_TRY(hg_k_cgs2_step(ctx, dV.p, ldd, n, k, dw0.p, dw1.p, dq.p, dH.p, dhc.p, dp.p));
+    HG_CUDA(cudaMemcpyAsync(hcol, dH.p, (size_t)(k + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HG_CUDA(cudaMemcpyAsync(q, dq.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HG_OK;
+}

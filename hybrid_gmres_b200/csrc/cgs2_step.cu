@@ -1,0 +1,387 @@
+// The whole CGS2 orthogonalisation of one Arnoldi step in ONE persistent cooperative kernel:
+//
+//     h1 = V'w0 ; w1 = w0 - V h1 ; h2 = V'w1 ; v = w1 - V h2 ; H(1:k,k) = h1 + h2 ;
+//     H(k+1,k) = ||v|| ; V(:,k+1) = v / H(k+1,k)          (hybrid_ab_gmres_rtp.m:20-26 in its two-pass form)
+//
+// The separate-kernel path launches multi-dot, reduce, staged middle stage, reduce, update, reduce, scale:
+// seven kernels whose boundaries (drain + ramp, ~5 us each) and second-stage reductions cost as much as the
+// data movement once a Krylov vector is a few hundred thousand rows — BASELINE configs[1]/[2] (256^2,
+// 512^2) and every rank's slice of the 1024^2 problem at 4-8 GPUs.  Here one CTA per SM sweeps its row
+// tiles three times (V crosses HBM — or, at these sizes, mostly L2 — three times, as before) with grid-wide
+// barriers in between; every CTA reduces the per-CTA partial sums redundantly in a fixed order, so no
+// second-stage kernel, no host involvement, and bit-identical reruns.
+//
+// Tile pipeline: as in cgs_staged.cu — two shared-memory stages filled by 16-byte cp.async while the 16
+// warps work on the other stage; warp w owns columns j = w, w+16, ...; lane l owns row pairs of the tile.
+#include <cooperative_groups.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct StepPlan {
+    int TR;
+    size_t stage, total;
+};
+inline StepPlan step_plan(int k, int NP) {
+    StepPlan p;
+    p.TR = 64 * NP;
+    p.stage = (size_t)(k + 1) * p.TR * 8;
+    // 2 stages | red[kWarps][TR] | w1 tile [TR] | h[kpad] | scratch[64]
+    p.total = 2 * p.stage + (size_t)(kWarps + 1) * p.TR * 8 + (size_t)((k + 2) / 2 * 2) * 8 + 64 * 8;
+    return p;
+}
+
+struct StepArgs {
+    const double* V;   // basis, column-major, ld
+    int64_t ld, n;
+    int k;             // columns to orthogonalise against
+    const double* w0;  // operator result (n)
+    double* w1;        // scratch (n): w0 - V h1
+    double* qnext;     // V(:,k+1): receives v / ||v||
+    double* Hcol;      // device H column: k + 1 entries
+    double* hcur;      // k entries: last coefficient vector (kept for callers that read it)
+    double* partials;  // (k + 2) * gridDim doubles
+    int ntiles;
+};
+
+// sum over CTAs of partials[j * G + c] for the columns of this warp -> sh[j]; every CTA does the same work
+// in the same order (lane l sums c = l, l+32, ..., then the shuffle tree), so all CTAs hold identical bits.
+// The partials were written by other SMs during this kernel: read through L2 (__ldcg).
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ partials, int G, int ncols, double* sh,
+                                                int warp, int lane) {
+    for (int j = warp; j < ncols; j += kWarps) {
+        const double* p = partials + (size_t)j * G;
+        double s = 0.0;
+        for (int c = lane; c < G; c += 32) s += __ldcg(p + c);
+        s = warp_sum(s);
+        if (lane == 0) sh[j] = s;
+    }
+}
+
+template <int CPW, int NP>
+__global__ void __launch_bounds__(kThreads, 1) cgs2_step_kernel(StepArgs a) {
+    constexpr int TR = 64 * NP;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int k = a.k;
+    const int64_t n = a.n, ld = a.ld;
+    const size_t stage_bytes = (size_t)(k + 1) * TR * 8;
+    double* st0 = reinterpret_cast<double*>(smem);
+    double* red = reinterpret_cast<double*>(smem + 2 * stage_bytes);  // [kWarps][TR]
+    double* w1t = red + kWarps * TR;                                  // [TR]
+    double* sh = w1t + TR;                                            // [k + 1 (+pad)] coefficients
+    double* scratch = sh + (k + 2) / 2 * 2;                           // [64]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = (int)gridDim.x;
+    const int my_tiles = a.ntiles > (int)blockIdx.x ? (a.ntiles - 1 - (int)blockIdx.x) / G + 1 : 0;
+
+    constexpr int CPC = TR / 2;            // 16-byte chunks per column of a tile
+    constexpr int CSTEP = kThreads / CPC;  // columns covered per round of the CTA
+    const int my_off = (threadIdx.x % CPC) * 2;
+    const int my_col0 = threadIdx.x / CPC;
+    // stage tile i of this CTA: k basis columns + one vector (`vec`, "column k" of the stage)
+    auto issue = [&](int i, const double* vec) {
+        if (i < my_tiles) {
+            const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)i * G) * TR;
+            if (my_off < (int)min((int64_t)TR, ld - r0)) {
+                uint32_t dst = smem_u32(st0) + (uint32_t)((i & 1) * stage_bytes) + (uint32_t)(my_col0 * TR + my_off) * 8u;
+                const double* src = a.V + (int64_t)my_col0 * ld + r0 + my_off;
+                int col = my_col0;
+                for (; col < k; col += CSTEP) {
+                    cp_async16(dst, src);
+                    dst += (uint32_t)CSTEP * TR * 8u;
+                    src += (int64_t)CSTEP * ld;
+                }
+                if (col == k) cp_async16(dst, vec + r0 + my_off);
+            }
+        }
+        cp_async_commit();
+    };
+
+    double acc[CPW];
+
+    // ------------------------------------------------------------------ sweep 1: h1 partials = V' w0
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) acc[c] = 0.0;
+    issue(0, a.w0);
+    issue(1, a.w0);
+    for (int i = 0; i < my_tiles; ++i) {
+        const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)i * G) * TR;
+        cp_async_wait_1();
+        __syncthreads();
+        const double* sv = st0 + (size_t)(i & 1) * (stage_bytes / 8);
+        double2 wv[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            wv[p] = reinterpret_cast<const double2*>(sv + (size_t)k * TR)[32 * p + lane];
+            // rows past n hold whatever the padding holds: take them out on both operands
+            if (!(r0 + 64 * p + 2 * lane < n)) wv[p].x = 0.0;
+            if (!(r0 + 64 * p + 2 * lane + 1 < n)) wv[p].y = 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) {
+            const int j = warp + kWarps * c;
+            if (j < k) {
+                const double2* col = reinterpret_cast<const double2*>(sv + (size_t)j * TR) + lane;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const double2 v = col[32 * p];
+                    acc[c] = fma(r0 + 64 * p + 2 * lane < n ? v.x : 0.0, wv[p].x, acc[c]);
+                    acc[c] = fma(r0 + 64 * p + 2 * lane + 1 < n ? v.y : 0.0, wv[p].y, acc[c]);
+                }
+            }
+        }
+        __syncthreads();
+        issue(i + 2, a.w0);
+    }
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+        const int j = warp + kWarps * c;
+        if (j < k) {
+            const double s = warp_sum(acc[c]);
+            if (lane == 0) a.partials[(size_t)j * G + blockIdx.x] = s;
+        }
+    }
+    cp_async_wait_0();
+    grid.sync();
+    reduce_partials(a.partials, G, k, sh, warp, lane);
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int j = threadIdx.x; j < k; j += kThreads) a.Hcol[j] = sh[j];  // h1
+
+    // ------------------------------------------------------------------ sweep 2: w1 = w0 - V h1, h2 partials = V' w1
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) acc[c] = 0.0;
+    issue(0, a.w0);
+    issue(1, a.w0);
+    for (int i = 0; i < my_tiles; ++i) {
+        const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)i * G) * TR;
+        cp_async_wait_1();
+        __syncthreads();
+        const double* sv = st0 + (size_t)(i & 1) * (stage_bytes / 8);
+        double2 pa[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) pa[p] = make_double2(0.0, 0.0);
+        double2 keep[CPW][NP];
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) {
+            const int j = warp + kWarps * c;
+            if (j < k) {
+                const double hj = sh[j];
+                const double2* col = reinterpret_cast<const double2*>(sv + (size_t)j * TR) + lane;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const double2 v = col[32 * p];
+                    keep[c][p] = v;
+                    pa[p].x = fma(hj, v.x, pa[p].x);
+                    pa[p].y = fma(hj, v.y, pa[p].y);
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) reinterpret_cast<double2*>(red + warp * TR)[32 * p + lane] = pa[p];
+        __syncthreads();
+        if (threadIdx.x < TR) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) sum += red[w * TR + threadIdx.x];
+            const int64_t row = r0 + threadIdx.x;
+            double out = 0.0;
+            if (row < n) {
+                out = sv[(size_t)k * TR + threadIdx.x] - sum;
+                a.w1[row] = out;
+            }
+            w1t[threadIdx.x] = out;  // 0 for rows past n: they drop out of the dots
+        }
+        __syncthreads();
+        double2 wv[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) wv[p] = reinterpret_cast<const double2*>(w1t)[32 * p + lane];
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) {
+            const int j = warp + kWarps * c;
+            if (j < k) {
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const double2 v = keep[c][p];
+                    acc[c] = fma(r0 + 64 * p + 2 * lane < n ? v.x : 0.0, wv[p].x, acc[c]);
+                    acc[c] = fma(r0 + 64 * p + 2 * lane + 1 < n ? v.y : 0.0, wv[p].y, acc[c]);
+                }
+            }
+        }
+        __syncthreads();
+        issue(i + 2, a.w0);
+    }
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+        const int j = warp + kWarps * c;
+        if (j < k) {
+            const double s = warp_sum(acc[c]);
+            if (lane == 0) a.partials[(size_t)j * G + blockIdx.x] = s;
+        }
+    }
+    cp_async_wait_0();
+    __threadfence();  // w1 rows of this CTA are re-read below through cp.async (L2)
+    grid.sync();
+    reduce_partials(a.partials, G, k, sh, warp, lane);
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int j = threadIdx.x; j < k; j += kThreads) {
+            a.Hcol[j] = a.Hcol[j] + sh[j];  // H(1:k,k) = h1 + h2
+            a.hcur[j] = sh[j];
+        }
+
+    // ------------------------------------------------------------------ sweep 3: v = w1 - V h2, ||v||^2 partial
+    double nrm_acc = 0.0;
+    issue(0, a.w1);
+    issue(1, a.w1);
+    for (int i = 0; i < my_tiles; ++i) {
+        const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)i * G) * TR;
+        cp_async_wait_1();
+        __syncthreads();
+        const double* sv = st0 + (size_t)(i & 1) * (stage_bytes / 8);
+        double2 pa[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) pa[p] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) {
+            const int j = warp + kWarps * c;
+            if (j < k) {
+                const double hj = sh[j];
+                const double2* col = reinterpret_cast<const double2*>(sv + (size_t)j * TR) + lane;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const double2 v = col[32 * p];
+                    pa[p].x = fma(hj, v.x, pa[p].x);
+                    pa[p].y = fma(hj, v.y, pa[p].y);
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) reinterpret_cast<double2*>(red + warp * TR)[32 * p + lane] = pa[p];
+        __syncthreads();
+        if (threadIdx.x < TR) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) sum += red[w * TR + threadIdx.x];
+            const int64_t row = r0 + threadIdx.x;
+            if (row < n) {
+                const double out = sv[(size_t)k * TR + threadIdx.x] - sum;
+                a.qnext[row] = out;
+                nrm_acc = fma(out, out, nrm_acc);
+            }
+        }
+        __syncthreads();
+        issue(i + 2, a.w1);
+    }
+    cp_async_wait_0();
+    {   // CTA sum of nrm_acc in a fixed order: warp shuffle tree, then warps in order
+        const double s = warp_sum(nrm_acc);
+        if (lane == 0) scratch[warp] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kWarps; ++w) t += scratch[w];
+            a.partials[(size_t)k * G + blockIdx.x] = t;
+        }
+    }
+    __threadfence();
+    grid.sync();
+    if (warp == 0) {
+        const double* p = a.partials + (size_t)k * G;
+        double s = 0.0;
+        for (int c = lane; c < G; c += 32) s += __ldcg(p + c);
+        s = warp_sum(s);
+        if (lane == 0) scratch[32] = sqrt(s);  // H(k+1,k) = norm(v)
+    }
+    __syncthreads();
+    const double nrm = scratch[32];
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.Hcol[k] = nrm;
+    // ------------------------------------------------------------------ sweep 4: V(:,k+1) = v / H(k+1,k)
+    for (int i = 0; i < my_tiles; ++i) {
+        const int64_t row = ((int64_t)blockIdx.x + (int64_t)i * G) * TR + threadIdx.x;
+        if (threadIdx.x < TR && row < n) a.qnext[row] = a.qnext[row] / nrm;  // division, as the reference (:26)
+    }
+}
+
+template <int CPW, int NP>
+int launch_step(hg_ctx* ctx, StepArgs& a) {
+    const StepPlan p = step_plan(a.k, NP);
+    a.ntiles = (int)((a.n + p.TR - 1) / p.TR);
+    static std::atomic<unsigned long long> attr_set{0};
+    const unsigned long long dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_set.load(std::memory_order_relaxed) & dev_bit)) {
+        HG_CUDA(cudaFuncSetAttribute(cgs2_step_kernel<CPW, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
+    }
+    void* params[] = {&a};
+    HG_CUDA(cudaLaunchCooperativeKernel((const void*)cgs2_step_kernel<CPW, NP>, dim3(ctx->sm_count), dim3(kThreads),
+                                        params, p.total, ctx->stream));
+    return HG_OK;
+}
+
+int g_step_max_n = -1;
+
+}  // namespace
+
+// Largest Krylov vector length for which the whole-step kernel is used (option "cgs_step_max_n" / env
+// HG_CGS_STEP_MAX_N; 0 disables).  Above it the separate streaming kernels win: their multi-dot and update
+// sweeps run at 6.5-6.6 TB/s, the staged pipeline of this kernel at ~5.3.
+int64_t hg_cgs2_step_max_n() {
+    if (g_step_max_n < 0) {
+        const char* e = getenv("HG_CGS_STEP_MAX_N");
+        g_step_max_n = e ? atoi(e) : 400000;
+    }
+    return g_step_max_n;
+}
+void hg_cgs2_step_max_n_set(int v) { g_step_max_n = v < 0 ? 0 : v; }
+
+bool hg_cgs2_step_eligible(const hg_ctx* ctx, int64_t n, int k) {
+    (void)ctx;
+    return k >= 1 && k <= 208 && n >= 1 && n <= hg_cgs2_step_max_n();
+}
+
+// partials capacity needed: (k + 2) * sm_count doubles
+int hg_k_cgs2_step(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* w0, double* w1,
+                   double* qnext, double* Hcol, double* hcur, double* partials) {
+    HG_REQUIRE(hg_cgs2_step_eligible(ctx, n, k), "cgs2_step: (n, k) out of range");
+    StepArgs a;
+    a.V = V;
+    a.ld = ld;
+    a.n = n;
+    a.k = k;
+    a.w0 = w0;
+    a.w1 = w1;
+    a.qnext = qnext;
+    a.Hcol = Hcol;
+    a.hcur = hcur;
+    a.partials = partials;
+    a.ntiles = 0;
+    // algorithmic bytes: three sweeps over V_k, w0 twice, w1 out + in, q out + scale
+    hg_launch_scope scope(ctx, HG_K_LINCOMB, 24.0 * (double)n * (double)k + 56.0 * (double)n);
+    if (k <= 16) return launch_step<1, 4>(ctx, a);   // 256-row tiles
+    if (k <= 40) return launch_step<3, 4>(ctx, a);   // 256-row tiles (2 x 84 KB stages)
+    if (k <= 96) return launch_step<6, 2>(ctx, a);   // 128-row tiles
+    return launch_step<13, 1>(ctx, a);               // 64-row tiles
+}

@@ -233,6 +233,13 @@ int hg_cgs_staged_nparts(const hg_ctx* ctx, int64_t n, int k);
 int hg_k_cgs_mid_staged(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* h,
                      const double* w0, double* w1, double* partials, int* nparts);
 
+// whole CGS2 step in one persistent cooperative kernel (cgs2_step.cu): small / medium Krylov vectors
+bool hg_cgs2_step_eligible(const hg_ctx* ctx, int64_t n, int k);
+int64_t hg_cgs2_step_max_n();
+void hg_cgs2_step_max_n_set(int v);
+int hg_k_cgs2_step(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* w0, double* w1,
+                   double* qnext, double* Hcol, double* hcur, double* partials);
+
 // options (spmv_stream.cu)
 bool hg_cgs_fused();      // 1: L2-re-read fused kernel (update_dot_kernel)
 int hg_cgs_fused_mode();  // 0 separate kernels, 1 update_dot_kernel, 2 shared-memory-staged fused kernel

@@ -73,6 +73,9 @@ int hg_version(void);
  * "cgs_alternate": 0 (default; env HG_CGS_ALTERNATE=1 enables) the CGS2 update kernels walk the rows
  * from the end, so each sweep over the basis starts on the ~100 MB the previous one left in L2
  * (measured neutral on B200).
+ * "cgs_step_max_n" / env HG_CGS_STEP_MAX_N (default 400000; 0 disables): Krylov vectors up to this length
+ * run the whole CGS2 step (orthogonalisation, norm, normalisation) in ONE persistent cooperative kernel
+ * (csrc/cgs2_step.cu) instead of seven launches.
  * "dist_transport": see hg_comm_transport. */
 int hg_set_option(const char* name, int value);
 
@@ -179,6 +182,13 @@ int hg_lincomb(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, const
 int hg_cgs_mid(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, const double* h,
                const double* w0, int fused, double* w1, double* d);
 
+/* One whole CGS2 step (two-pass classical Gram-Schmidt, norm, normalisation) of w0 against the k columns of
+ * V in the single persistent cooperative kernel of csrc/cgs2_step.cu: hcol[0..k) = V'w0 + V'(w0 - V V'w0),
+ * hcol[k] = ||v||, q = v / ||v||.  1 <= k <= 208 and n <= option "cgs_step_max_n" (default 400000), else
+ * HG_ERR_INVALID — larger vectors use the separate streaming kernels. */
+int hg_cgs2_step(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, const double* w0, double* hcol,
+                 double* q);
+
 /* ---- Arnoldi on device-resident data (a1-a4, a9 in SURVEY.md §8a) -------- */
 typedef enum hg_space {
     HG_SPACE_N = 0, /* operator B*(A*q) + shift*q, start B*b  (hybrid_*_rtp.m:6-13,
@@ -273,6 +283,17 @@ int hg_last_solve_stats(double* out, int n);
 int hg_gmres_ptr(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* A, const hg_matrix* B, const double* b,
                  const double* x_true, double tol, int maxit, double lambda, double* x, double* error_norm,
                  double* residual_norm, int* niters, int* x_valid, hg_extras* extras);
+
+/* The same hybrid PTR solve with the regularisation parameter chosen AT EVERY ITERATION from the growing
+ * Hessenberg matrix: lambda_k = the first minimiser over `lambdas[0..nl)` of
+ * GCV(lambda, H_k) exactly as compute_gcv_surface / calculate_gcv_from_H evaluate it
+ * (plot_gcv_surface.m:58-122), then y_k = (H_k'H_k + lambda_k I) \ (H_k' beta e1) and x_k as in
+ * AB/BAgmres_hybrid_bounds.m:34-38.  lambda_path (maxit entries) receives lambda_1..lambda_niters.
+ * No device work beyond hg_gmres_ptr's: the choice is made on the host from H. */
+int hg_gmres_ptr_gcv(hg_ctx* ctx, int kind, const hg_matrix* A, const hg_matrix* B, const double* b,
+                     const double* x_true, double tol, int maxit, const double* lambdas, int nl, double* x,
+                     double* error_norm, double* residual_norm, double* lambda_path, int* niters, int* x_valid,
+                     hg_extras* extras);
 
 /* gcv_function(lambda,A,B,b,m,k_gcv,gcv_type): the lambda-independent Arnoldi
  * (gcv_function.m:4-32) runs ONCE in hg_gcv_prepare; hg_gcv_eval is the

@@ -45,4 +45,5 @@ from .ptr import (  # noqa: F401,E402
     ABgmres_nonhybrid_bounds,
     BAgmres_hybrid_bounds,
     BAgmres_nonhybrid_bounds,
+    hybrid_gmres_gcv,
 )

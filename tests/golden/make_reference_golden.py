@@ -138,6 +138,20 @@ def run_case(A, B, b, x_true, tol, maxit, lam, k_gcv, surface_k=None):
             surf, path = ip.call(f, [t, A, B, b, S(surface_k), kr, lam_grid], 2)
             out[f"surface_{t}"] = np.asarray(surf, dtype=float)
             out[f"surface_{t}_path"] = np.asarray(path, dtype=float).reshape(-1)
+            # per-iteration lambda_k hybrid solve: the iterate the reference's own PTR
+            # solver returns after k iterations with lambda = lambda_k of the path above
+            fn = ("AB" if t == "ab" else "BA") + "gmres_hybrid_bounds"
+            Xk, ek, rk = [], [], []
+            for kk in range(1, surface_k + 1):
+                lam_k = float(out[f"surface_{t}_path"][kk - 1])
+                xk, e_, r_, it_ = ip.call(fn, [A, B, b, x_true, S(0.0), S(kk), S(lam_k), DM if t == "ab" else DN], 4)
+                assert int(mlab.scalar(it_)) == kk
+                Xk.append(np.asarray(xk, dtype=float).reshape(-1))
+                ek.append(float(np.asarray(e_).reshape(-1)[-1]))
+                rk.append(float(np.asarray(r_).reshape(-1)[-1]))
+            out[f"lamk_{t}_X"] = np.stack(Xk, axis=1)
+            out[f"lamk_{t}_err"] = np.array(ek)
+            out[f"lamk_{t}_res"] = np.array(rk)
         out["surface_lams"] = lam_grid.reshape(-1)
         out["surface_k"] = surface_k
     out["ref_files_executed"] = np.array(sorted({os.path.basename(f) for _, f in ip.calls}))

@@ -157,3 +157,31 @@ def test_breakdown_epilogue_matches_executed_reference(hg, ctx):
     x, err, res, it = hg.hybrid_ab_gmres_rtp(sp.identity(n, format="csc"), sp.identity(n, format="csr"), e1, xt,
                                              1e-6, 4, 1e-2, ctx=ctx)
     assert x is None and it == 1 and res[0] == 0.0
+
+
+@pytest.mark.parametrize("name", ["ref_ct16_perturbed", "ref_ct20_fan_pixel"])
+@pytest.mark.parametrize("t", ["ab", "ba"])
+def test_lambda_k_hybrid_solve_against_executed_reference(hg, ctx, name, t):
+    """hg_gmres_ptr_gcv (lambda chosen at every iteration from the growing H): the
+    lambda_k path equals the reference's compute_gcv_surface path exactly, the iterates equal what the
+    reference's PTR solver gives with that lambda_k."""
+    A, B, b, x_true, tol, maxit, lam, k_gcv, r = load_ref(name)
+    K = int(r["surface_k"])
+    ex = {}
+    x, err, res, it, path = hg.hybrid_gmres_gcv(t, A, B, b, x_true, 0.0, K, r["surface_lams"], ctx=ctx, extras=ex)
+    assert it == K and np.array_equal(path, r[f"surface_{t}_path"])
+    assert _rel_cols(ex["X"], r[f"lamk_{t}_X"], K) < TOL
+    assert _relmax(err, r[f"lamk_{t}_err"]) < TOL and _relmax(res, r[f"lamk_{t}_res"]) < TOL
+    assert np.linalg.norm(x - r[f"lamk_{t}_X"][:, -1]) <= TOL * np.linalg.norm(x)
+
+
+def test_lambda_k_hybrid_solve_on_ct_problem(hg, ctx, ct48_unmatched):
+    """the same mode on a larger unmatched CT problem against the oracle restatement (oracle/ptr.py)"""
+    import oracle
+    A, B, b, x_true = ct48_unmatched
+    lams = np.logspace(-8, -1, 40)
+    for t in ("ab", "ba"):
+        x, err, res, it, path = hg.hybrid_gmres_gcv(t, A, B, b, x_true, 1e-6, 25, lams, ctx=ctx)
+        xo, erro, reso, ito, patho = oracle.hybrid_gmres_gcv(t, A, B, b, x_true, 1e-6, 25, lams)
+        assert it == ito and np.array_equal(path, patho)
+        assert _relmax(err, erro) < 1e-7 and _relmax(res, reso) < 1e-7

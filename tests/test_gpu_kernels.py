@@ -381,3 +381,67 @@ def test_cgs_staged_stage_against_numpy(hg, ctx, n, k):
     with pytest.raises(hg._lib.HgError):  # outside its range the staged kernel refuses (callers fall back)
         hg._lib.check(lib.hg_cgs_mid(ctx._h, 1000, 8, V.ctypes.data, n, h.ctypes.data, w0.ctypes.data, 1,
                                      np.zeros(1000).ctypes.data, np.zeros(8).ctypes.data))
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (63, 1), (1000, 5), (4097, 16), (20000, 17), (65536, 40), (65537, 41),
+                                 (131072, 96), (131075, 97), (70001, 200), (300000, 208)])
+def test_cgs2_whole_step_kernel_against_numpy(hg, ctx, n, k):
+    """csrc/cgs2_step.cu — the persistent cooperative kernel that does the whole CGS2 step: every template
+    shape (k <= 16 / 40 / 96 / 208), ragged n, more CTAs than tiles.  Against the same algorithm in NumPy
+    (h to 1e-13 of ||w||, the new vector orthogonal to V to 1e-14) and bit-identical on a rerun."""
+    rng = np.random.default_rng(n + k)
+    V, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    V = np.asfortranarray(V)
+    w0 = rng.standard_normal(n) + V @ rng.standard_normal(k) * 3.0
+    lib = ctx._lib
+    outs = []
+    for rep in range(2):
+        hcol, q = np.zeros(k + 1), np.zeros(n)
+        hg._lib.check(lib.hg_cgs2_step(ctx._h, n, k, V.ctypes.data, n, w0.ctypes.data, hcol.ctypes.data, q.ctypes.data))
+        outs.append((hcol, q))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    hcol, q = outs[0]
+    h1 = V.T @ w0
+    w1 = w0 - V @ h1
+    h2 = V.T @ w1
+    v = w1 - V @ h2
+    nw = np.linalg.norm(w0)
+    assert np.max(np.abs(hcol[:k] - (h1 + h2))) < 1e-13 * nw
+    assert abs(hcol[k] - np.linalg.norm(v)) < 1e-13 * nw
+    if np.linalg.norm(v) > 1e-8 * nw:
+        assert np.linalg.norm(q - v / np.linalg.norm(v)) < 1e-12
+        assert np.max(np.abs(V.T @ q)) < 1e-13
+
+
+def test_arnoldi_whole_step_kernel_matches_separate_kernels(hg, ctx):
+    """The Arnoldi handle with the whole-step kernel (default for n <= 400000) against the separate
+    multi-dot / staged / update kernels (cgs_step_max_n = 0) on the 256^2 problem: H column-wise to 1e-9 over
+    the well-determined columns, orthonormal basis, bit-identical reruns."""
+    from hybrid_gmres_b200.ct import ct_backprojector, ct_projector, shepp_logan
+    N, K, lam = 256, 60, 1e-2
+    angles = np.arange(180) * 2.0
+    dA = ct_projector(N, angles, None, "fan", ctx=ctx)
+    dB = ct_backprojector(N, angles, None, "fan", ctx=ctx)
+    b = dA.matvec(shepp_logan(N))
+    res = {}
+    try:
+        for mode in (0, 400000, 400000):
+            hg.set_option("cgs_step_max_n", mode)
+            ar = hg.Arnoldi(dA, dB, "n", K)
+            ar.set_rhs(b)
+            ar.reset(lam)
+            l0 = ctx.launch_count
+            ar.steps(K)
+            H, beta, k = ar.get()
+            res.setdefault(mode, []).append((H, ctx.launch_count - l0))
+            if mode:
+                Q = np.column_stack([ar.q(j) for j in range(K + 1)])
+            ar.close()
+    finally:
+        hg.set_option("cgs_step_max_n", 400000)
+    (H0, l_sep), (H1, l_fused), (H2, _) = res[0][0], res[400000][0], res[400000][1]
+    assert np.array_equal(H1, H2)
+    assert l_fused <= 3 * K + 4 and l_sep > 3 * l_fused  # SpMV A, SpMV B, one CGS2 kernel per step
+    for j in range(20):
+        assert np.linalg.norm(H1[:j + 2, j] - H0[:j + 2, j]) <= 1e-9 * np.linalg.norm(H0[:j + 2, j]), j
+    assert np.max(np.abs(Q.T @ Q - np.eye(K + 1))) < 1e-12

@@ -171,3 +171,19 @@ end
     assert np.array_equal(f, np.array([[1, -2, 3], [1, 9, 3.0]]))
     with pytest.raises(mlab.MlabError):
         ip.load_source("x = [1 2\n")
+
+
+@pytest.mark.parametrize("name", ["ref_ct16_perturbed", "ref_ct20_fan_pixel"])
+@pytest.mark.parametrize("t", ["ab", "ba"])
+def test_oracle_lambda_k_solve_matches_executed_reference(name, t):
+    """Per-iteration lambda_k hybrid solve: lambda_k from the reference's
+    compute_gcv_surface (plot_gcv_surface.m:58-102), the iterate from the reference's own PTR solver run
+    for k iterations with that lambda_k — both executed from the reference source — vs oracle/ptr.py."""
+    A, B, b, x_true, tol, maxit, lam, k_gcv, r = load_ref(name)
+    A, B = _csr(A), _csr(B)
+    K = int(r["surface_k"])
+    x, err, res, it, path = oracle.hybrid_gmres_gcv(t, A, B, b, x_true, 0.0, K, r["surface_lams"], extras=(ex := {}))
+    assert it == K and np.array_equal(path, r[f"surface_{t}_path"])
+    for j in range(K):
+        assert _relnorm(ex["X"][:, j], r[f"lamk_{t}_X"][:, j]) < 1e-9, j
+    assert _rel(err, r[f"lamk_{t}_err"]) < 1e-9 and _rel(res, r[f"lamk_{t}_res"]) < 1e-9
