@@ -505,22 +505,23 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
         HG_CUDA(cudaMemcpyAsync(d_y.p, yk, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
         // x = Q(:,1:k)*yk fused with ||x - x_true||^2          (:33,36 / :30,33)
         double* xk = d_x[k & 1].p;
-        int np_e = 0, np_r = 0;
-        HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n, k, d_y.p, 1.0, nullptr, xk, d_xt.p, stat_e.p, &np_e));
         if (residual_mode == 0) {
-            // ||b - A*x|| with A*x = (A*Q_k) yk from the cached columns
-            HG_TRY(hg_k_lincomb(ctx, a->T + a->ldt, a->ldt, m, k, d_y.p, -1.0, a->d_b, nullptr, nullptr,
-                                stat_r.p, &np_r));
+            // ... and ||b - A*x|| with A*x = (A*Q_k) yk from the cached columns, both norms finished by the
+            // last block of the same launch
+            HG_TRY(hg_k_iterate(ctx, a->Q, a->ldq, n, a->T + a->ldt, a->ldt, m, k, d_y.p, a->d_b, xk, d_xt.p,
+                                stat_e.p, reinterpret_cast<unsigned int*>(ctx->d_scalars + 40), ctx->d_scalars + 1));
         } else {
+            int np_e = 0, np_r = 0;
+            HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n, k, d_y.p, 1.0, nullptr, xk, d_xt.p, stat_e.p, &np_e));
             hg_spmv_epilogue ep;  // literal: norm(b - A*x)       (:35 / :32)
             ep.alpha = -1.0;
             ep.z1 = a->d_b;
             ep.g1 = 1.0;
             ep.stat = stat_r.p;
             HG_TRY(hg_k_spmv(ctx, A, xk, nullptr, ep, &np_r));
+            HG_TRY(hg_k_reduce(ctx, stat_e.p, np_e, 1, ctx->d_scalars + 1, false, nullptr, true));
+            HG_TRY(hg_k_reduce(ctx, stat_r.p, np_r, 1, ctx->d_scalars + 2, false, nullptr, true));
         }
-        HG_TRY(hg_k_reduce(ctx, stat_e.p, np_e, 1, ctx->d_scalars + 1, false, nullptr, true));
-        HG_TRY(hg_k_reduce(ctx, stat_r.p, np_r, 1, ctx->d_scalars + 2, false, nullptr, true));
         HG_CUDA(cudaMemcpyAsync(h_s.p + (size_t)(k % RING) * 2, ctx->d_scalars + 1, 16, cudaMemcpyDeviceToHost,
                                 ctx->stream));
         if (extras && extras->X_hist)

@@ -17,7 +17,7 @@
 
 #include <atomic>
 
-#include "common.cuh"
+#include "dist_internal.h"
 
 namespace cg = cooperative_groups;
 
@@ -52,6 +52,22 @@ inline StepPlan step_plan(int k, int NP) {
     return p;
 }
 
+// Multi-GPU (NVLink peer memory, dist_peer.cu protocol): the same kernel also does the collectives of the
+// sharded step — pulls the reduce-scatter of B^p u_p, exchanges the three coefficient / norm sums as LL
+// words ({half, epoch} pairs, the data carries its flag), pushes the new basis rows into every rank's
+// replicated vector and scales its local copy.  One launch replaces seven kernels + three all-reduce kernels.
+struct StepPeer {
+    hg_peer_tbl t;
+    size_t ypart_off, yflag_off, qfull_off;  // byte offsets inside the symmetric workspace
+    size_t inbox_off[3];
+    unsigned long long y_epoch;
+    unsigned int ar_epoch[3];
+    unsigned long long* err;
+    int64_t row0, n_pad;    // first global row of this rank's slice; length of the replicated vector
+    const double* q_slice;  // local slice of q_k (shift term), or nullptr
+    double shift;
+};
+
 struct StepArgs {
     const double* V;   // basis, column-major, ld
     int64_t ld, n;
@@ -63,7 +79,73 @@ struct StepArgs {
     double* hcur;      // k entries: last coefficient vector (kept for callers that read it)
     double* partials;  // (k + 2) * gridDim doubles
     int ntiles;
+    double* w0w;       // PEER: w0 is produced here (same buffer as w0)
+    StepPeer peer;     // PEER only
 };
+
+constexpr long long kStepSpinLimit = 40000000000LL;  // ~20 s of SM clocks: a lost rank is reported, not a hang
+
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All-reduce of sh[0..ncols) over the ranks.  CTA 0 stores this rank's sums into every rank's inbox (own
+// included); EVERY CTA then polls its rank's inbox and adds the P contributions in rank order, so all CTAs
+// of all ranks end with identical bits.  Inbox entry (j, src) is 16 bytes at ((j * P + src) * 2) words.
+__device__ __forceinline__ void peer_allreduce(const StepPeer& pr, int which, double* sh, int ncols, int warp, int lane) {
+    const int P = pr.t.P;
+    const unsigned int epoch = pr.ar_epoch[which];
+    __syncthreads();  // sh holds the local sums
+    if (blockIdx.x == 0) {
+        __threadfence_system();  // rows this rank pushed to peers are ordered before the words that announce them
+        for (int idx = threadIdx.x; idx < ncols * P; idx += kThreads) {
+            const int j = idx / P, dstp = idx % P;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(sh[j]);
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(pr.t.base[dstp] + pr.inbox_off[which]) +
+                                      ((size_t)j * P + pr.t.rank) * 2;
+            st_relaxed_sys_u64(dst, (bits << 32) | epoch);
+            st_relaxed_sys_u64(dst + 1, (bits & 0xffffffff00000000ull) | epoch);
+        }
+    }
+    __syncthreads();  // CTA 0: everything read from sh before it is overwritten
+    const unsigned long long* inbox = reinterpret_cast<const unsigned long long*>(pr.t.base[pr.t.rank] + pr.inbox_off[which]);
+    for (int j = warp; j < ncols; j += kWarps) {
+        double v = 0.0;
+        if (lane < P) {
+            const unsigned long long* src = inbox + ((size_t)j * P + lane) * 2;
+            const long long t0 = clock64();
+            unsigned long long w0, w1;
+            bool ok = true;
+            for (;;) {
+                w0 = ld_relaxed_sys_u64(src);
+                w1 = ld_relaxed_sys_u64(src + 1);
+                if ((unsigned int)w0 == epoch && (unsigned int)w1 == epoch) break;
+                if (clock64() - t0 > kStepSpinLimit) {
+                    *pr.err = 1ull;
+                    __threadfence_system();
+                    ok = false;
+                    break;
+                }
+            }
+            __threadfence_system();  // acquire: later reads of peer-written rows come after the observed epochs
+            v = ok ? __longlong_as_double((long long)((w0 >> 32) | (w1 & 0xffffffff00000000ull))) : 0.0;
+        }
+        double s = 0.0;
+        for (int r = 0; r < P; ++r) s += __shfl_sync(0xffffffffu, v, r);  // rank order
+        if (lane == 0) sh[j] = s;
+    }
+    __syncthreads();
+}
 
 // sum over CTAs of partials[j * G + c] for the columns of this warp -> sh[j]; every CTA does the same work
 // in the same order (lane l sums c = l, l+32, ..., then the shuffle tree), so all CTAs hold identical bits.
@@ -79,7 +161,7 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
     }
 }
 
-template <int CPW, int NP>
+template <int CPW, int NP, bool PEER>
 __global__ void __launch_bounds__(kThreads, 1) cgs2_step_kernel(StepArgs a) {
     constexpr int TR = 64 * NP;
     cg::grid_group grid = cg::this_grid();
@@ -120,6 +202,49 @@ __global__ void __launch_bounds__(kThreads, 1) cgs2_step_kernel(StepArgs a) {
     };
 
     double acc[CPW];
+
+    if constexpr (PEER) {
+        // ---------------------------------------------------------------- sweep 0: reduce-scatter by pulling
+        // w0[r] = sum_p (B^p u_p)[row0 + r] + shift * q_k[r] on this CTA's tiles, once every rank's SpMV is done
+        const StepPeer& pr = a.peer;
+        if (threadIdx.x < pr.t.P) {
+            const unsigned long long* f = reinterpret_cast<const unsigned long long*>(pr.t.base[pr.t.rank] + pr.yflag_off) + threadIdx.x;
+            const long long t0 = clock64();
+            while (ld_acquire_sys_u64(f) < pr.y_epoch) {
+                if (clock64() - t0 > kStepSpinLimit) {
+                    *pr.err = 1ull;
+                    __threadfence_system();
+                    break;
+                }
+                __nanosleep(32);
+            }
+        }
+        __syncthreads();
+        for (int i = 0; i < my_tiles; ++i) {
+            const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)i * G) * TR;
+            for (int t2 = threadIdx.x; t2 < TR / 2; t2 += kThreads) {
+                const int64_t r = r0 + 2 * t2;  // n (= n_p) is a multiple of 32: pairs never straddle it
+                if (r < n) {
+                    double2 sacc = make_double2(0.0, 0.0);
+#pragma unroll 4
+                    for (int pp = 0; pp < pr.t.P; ++pp) {  // fixed rank order: every rank forms the same bits
+                        const double2 v = __ldcg(reinterpret_cast<const double2*>(
+                            reinterpret_cast<const double*>(pr.t.base[pp] + pr.ypart_off) + pr.row0 + r));
+                        sacc.x += v.x;
+                        sacc.y += v.y;
+                    }
+                    if (pr.shift != 0.0) {
+                        const double2 qv = *reinterpret_cast<const double2*>(pr.q_slice + r);
+                        sacc.x += pr.shift * qv.x;
+                        sacc.y += pr.shift * qv.y;
+                    }
+                    *reinterpret_cast<double2*>(a.w0w + r) = sacc;
+                }
+            }
+        }
+        __threadfence();  // staged below through cp.async (L2)
+        __syncthreads();
+    }
 
     // ------------------------------------------------------------------ sweep 1: h1 partials = V' w0
 #pragma unroll
@@ -166,6 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) cgs2_step_kernel(StepArgs a) {
     cp_async_wait_0();
     grid.sync();
     reduce_partials(a.partials, G, k, sh, warp, lane);
+    if constexpr (PEER) peer_allreduce(a.peer, 0, sh, k, warp, lane);
     __syncthreads();
     if (blockIdx.x == 0)
         for (int j = threadIdx.x; j < k; j += kThreads) a.Hcol[j] = sh[j];  // h1
@@ -245,6 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) cgs2_step_kernel(StepArgs a) {
     __threadfence();  // w1 rows of this CTA are re-read below through cp.async (L2)
     grid.sync();
     reduce_partials(a.partials, G, k, sh, warp, lane);
+    if constexpr (PEER) peer_allreduce(a.peer, 1, sh, k, warp, lane);
     __syncthreads();
     if (blockIdx.x == 0)
         for (int j = threadIdx.x; j < k; j += kThreads) {
@@ -289,6 +416,11 @@ __global__ void __launch_bounds__(kThreads, 1) cgs2_step_kernel(StepArgs a) {
             if (row < n) {
                 const double out = sv[(size_t)k * TR + threadIdx.x] - sum;
                 a.qnext[row] = out;
+                if constexpr (PEER) {  // all-gather by the producer: the row goes into every rank's replicated vector
+#pragma unroll 4
+                    for (int pp = 0; pp < a.peer.t.P; ++pp)
+                        reinterpret_cast<double*>(a.peer.t.base[pp] + a.peer.qfull_off)[a.peer.row0 + row] = out;
+                }
                 nrm_acc = fma(out, out, nrm_acc);
             }
         }
@@ -306,6 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) cgs2_step_kernel(StepArgs a) {
             a.partials[(size_t)k * G + blockIdx.x] = t;
         }
     }
+    if constexpr (PEER) __threadfence_system();  // pushed rows are performed before anything that follows the barrier
     __threadfence();
     grid.sync();
     if (warp == 0) {
@@ -313,30 +446,37 @@ __global__ void __launch_bounds__(kThreads, 1) cgs2_step_kernel(StepArgs a) {
         double s = 0.0;
         for (int c = lane; c < G; c += 32) s += __ldcg(p + c);
         s = warp_sum(s);
-        if (lane == 0) scratch[32] = sqrt(s);  // H(k+1,k) = norm(v)
+        if (lane == 0) scratch[32] = s;
     }
+    // PEER: this exchange is also the barrier that makes every rank's pushed rows visible here
+    if constexpr (PEER) peer_allreduce(a.peer, 2, scratch + 32, 1, warp, lane);
     __syncthreads();
-    const double nrm = scratch[32];
+    const double nrm = sqrt(scratch[32]);  // H(k+1,k) = norm(v)
     if (blockIdx.x == 0 && threadIdx.x == 0) a.Hcol[k] = nrm;
     // ------------------------------------------------------------------ sweep 4: V(:,k+1) = v / H(k+1,k)
     for (int i = 0; i < my_tiles; ++i) {
         const int64_t row = ((int64_t)blockIdx.x + (int64_t)i * G) * TR + threadIdx.x;
         if (threadIdx.x < TR && row < n) a.qnext[row] = a.qnext[row] / nrm;  // division, as the reference (:26)
     }
+    if constexpr (PEER) {  // ... and this rank's copy of the replicated vector (rows from all ranks)
+        double* qf = reinterpret_cast<double*>(a.peer.t.base[a.peer.t.rank] + a.peer.qfull_off);
+        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < a.peer.n_pad; i += (int64_t)G * kThreads)
+            qf[i] = __ldcg(qf + i) / nrm;
+    }
 }
 
-template <int CPW, int NP>
+template <int CPW, int NP, bool PEER>
 int launch_step(hg_ctx* ctx, StepArgs& a) {
     const StepPlan p = step_plan(a.k, NP);
     a.ntiles = (int)((a.n + p.TR - 1) / p.TR);
     static std::atomic<unsigned long long> attr_set{0};
     const unsigned long long dev_bit = 1ull << (ctx->device & 63);
     if (!(attr_set.load(std::memory_order_relaxed) & dev_bit)) {
-        HG_CUDA(cudaFuncSetAttribute(cgs2_step_kernel<CPW, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HG_CUDA(cudaFuncSetAttribute(cgs2_step_kernel<CPW, NP, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
     void* params[] = {&a};
-    HG_CUDA(cudaLaunchCooperativeKernel((const void*)cgs2_step_kernel<CPW, NP>, dim3(ctx->sm_count), dim3(kThreads),
+    HG_CUDA(cudaLaunchCooperativeKernel((const void*)cgs2_step_kernel<CPW, NP, PEER>, dim3(ctx->sm_count), dim3(kThreads),
                                         params, p.total, ctx->stream));
     return HG_OK;
 }
@@ -378,10 +518,57 @@ int hg_k_cgs2_step(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, c
     a.hcur = hcur;
     a.partials = partials;
     a.ntiles = 0;
+    a.w0w = nullptr;
     // algorithmic bytes: three sweeps over V_k, w0 twice, w1 out + in, q out + scale
     hg_launch_scope scope(ctx, HG_K_LINCOMB, 24.0 * (double)n * (double)k + 56.0 * (double)n);
-    if (k <= 16) return launch_step<1, 4>(ctx, a);   // 256-row tiles
-    if (k <= 40) return launch_step<3, 4>(ctx, a);   // 256-row tiles (2 x 84 KB stages)
-    if (k <= 96) return launch_step<6, 2>(ctx, a);   // 128-row tiles
-    return launch_step<13, 1>(ctx, a);               // 64-row tiles
+    if (k <= 16) return launch_step<1, 4, false>(ctx, a);   // 256-row tiles
+    if (k <= 40) return launch_step<3, 4, false>(ctx, a);   // 256-row tiles (2 x 84 KB stages)
+    if (k <= 96) return launch_step<6, 2, false>(ctx, a);   // 128-row tiles
+    return launch_step<13, 1, false>(ctx, a);               // 64-row tiles
+}
+
+// Sharded step over NVLink peer memory: waits for the latest HG_FLAG_Y signal of every rank, then
+// w0 = sum_p ypart_p[slice] + shift * q_slice, the CGS2 step on the local slices with the three sums
+// all-reduced inside the kernel, the un-normalised rows pushed into every rank's replicated vector `buf`,
+// and finally qnext and the local replicated copy divided by H(k+1,k).  Uses three inbox slots.
+int hg_k_cgs2_step_peer(hg_comm* c, const double* V, int64_t ld, int64_t n_p, int k, double* w0, double* w1,
+                        double* qnext, double* Hcol, double* hcur, double* partials, int64_t row0,
+                        const double* q_slice, double shift, int buf) {
+    hg_ctx* ctx = c->ctx;
+    HG_REQUIRE(hg_cgs2_step_eligible(ctx, n_p, k) && k + 1 <= c->lay.kpad, "cgs2_step_peer: (n, k) out of range");
+    StepArgs a;
+    a.V = V;
+    a.ld = ld;
+    a.n = n_p;
+    a.k = k;
+    a.w0 = w0;
+    a.w0w = w0;
+    a.w1 = w1;
+    a.qnext = qnext;
+    a.Hcol = Hcol;
+    a.hcur = hcur;
+    a.partials = partials;
+    a.ntiles = 0;
+    StepPeer& pr = a.peer;
+    pr.t = c->tbl;
+    pr.ypart_off = c->lay.ypart;
+    pr.yflag_off = c->lay.flags + (size_t)HG_FLAG_Y * HG_MAX_PEERS * 8;
+    pr.qfull_off = c->lay.qfull + (size_t)buf * c->lay.n_pad * 8;
+    pr.y_epoch = c->bar_seq[HG_FLAG_Y];
+    for (int i = 0; i < 3; ++i) {
+        const unsigned long long seq = c->bar_seq[HG_FLAG_AR]++;
+        pr.inbox_off[i] = c->lay.inbox + (size_t)(seq % kInboxSlots) * c->nranks * c->lay.kpad * 16;
+        pr.ar_epoch[i] = (unsigned int)(seq % 0xfffffffeull) + 1u;
+    }
+    pr.err = c->d_err;
+    pr.row0 = row0;
+    pr.n_pad = c->lay.n_pad;
+    pr.q_slice = q_slice;
+    pr.shift = q_slice ? shift : 0.0;
+    hg_launch_scope scope(ctx, HG_K_LINCOMB, 24.0 * (double)n_p * (double)k + 8.0 * (double)n_p * (c->nranks + 8) +
+                                                 16.0 * (double)c->lay.n_pad);
+    if (k <= 16) return launch_step<1, 4, true>(ctx, a);
+    if (k <= 40) return launch_step<3, 4, true>(ctx, a);
+    if (k <= 96) return launch_step<6, 2, true>(ctx, a);
+    return launch_step<13, 1, true>(ctx, a);
 }

@@ -190,6 +190,11 @@ int hg_k_lincomb(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, con
                  double s, const double* z, double* out, const double* ref, double* stat,
                  int* nparts);
 
+// iterate + both histories of a hybrid iteration in one launch (kernels.cu: iterate_kernel)
+int hg_k_iterate(hg_ctx* ctx, const double* Q, int64_t ldq, int64_t n, const double* T, int64_t ldt, int64_t m,
+                 int k, const double* y, const double* b, double* x, const double* x_true, double* stat,
+                 unsigned int* ticket, double* out2);
+
 // same, with the result rows also stored to up to 16 further destinations (peer-GPU copies of the
 // vector: the all-gather of the sharded Arnoldi is done by the producing kernel, dist_peer.cu)
 struct hg_out_list {

@@ -85,3 +85,9 @@ int hg_k_reduce_allreduce(hg_comm* c, const double* partials, int np, int k, dou
 int hg_k_scale2(hg_comm* c, double* a, int64_t na, double* b, int64_t nb, const double* d_div);
 // destinations of this rank's rows [row0, row0+n_p) in every rank's replicated vector `buf`
 void hg_peer_push_list(hg_comm* c, int buf, int64_t row0, hg_out_list* out);
+
+// cgs2_step.cu: the whole sharded CGS2 step (pull reduce-scatter, three in-kernel all-reduces, push
+// all-gather, normalisation) in one persistent cooperative kernel
+int hg_k_cgs2_step_peer(hg_comm* c, const double* V, int64_t ld, int64_t n_p, int k, double* w0, double* w1,
+                        double* qnext, double* Hcol, double* hcur, double* partials, int64_t row0,
+                        const double* q_slice, double shift, int buf);

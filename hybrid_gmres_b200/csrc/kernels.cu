@@ -281,6 +281,98 @@ lincomb_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
 
 
 // ---------------------------------------------------------------------------
+// Iterate + both histories of one hybrid iteration in ONE launch (hybrid_ba_gmres_rtp.m:30-33,
+// hybrid_ab_gmres_rtp.m:33-36 with A*x taken from the cached columns T = A*Q_k):
+//   job 0 (blocks [0, g0)):      x = Q y           and  sum (x - x_true)^2
+//   job 1 (blocks [g0, g0+g1)):  r = b - T y (not stored)  and  sum r^2
+// then the LAST block to finish (ticket counter) adds the per-block sums of each job in block order and
+// writes out[0] = ||x - x_true||, out[1] = ||r||: no second-stage kernels, fixed summation order.
+// ---------------------------------------------------------------------------
+struct hg_iter_job {
+    const double* V;    // n x k column-major
+    int64_t ld, n;
+    double s;           // scale of the combination (+1: x = V y, -1: r = z - V y)
+    const double* z;    // added vector or nullptr
+    double* out;        // result or nullptr
+    const double* ref;  // subtracted before squaring, or nullptr
+    int grid;           // blocks of this job
+};
+
+__global__ void __launch_bounds__(kBlock)
+iterate_kernel(hg_iter_job j0, hg_iter_job j1, int k, const double* __restrict__ c, double* __restrict__ stat,
+               unsigned int* __restrict__ ticket, double* __restrict__ out2) {
+    extern __shared__ double sc[];
+    __shared__ bool s_last;
+    const bool second = (int)blockIdx.x >= j0.grid;
+    const hg_iter_job& J = second ? j1 : j0;
+    const int64_t blk = second ? (int64_t)blockIdx.x - j0.grid : blockIdx.x;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) sc[j] = J.s * c[j];
+    __syncthreads();
+    const int64_t r = (blk * kBlock + threadIdx.x) * 2;
+    const int64_t n = J.n, ld = J.ld;
+    double sq = 0.0;
+    if (r + 1 < n) {
+        double ax = 0.0, ay = 0.0;
+        if (J.z) {
+            const double2 zz = *reinterpret_cast<const double2*>(J.z + r);
+            ax = zz.x;
+            ay = zz.y;
+        }
+        const double* p = J.V + r;
+        int j = 0;
+        for (; j + 8 <= k; j += 8) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = ld_stream2(p + (int64_t)(j + u) * ld);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                ax = fma(sc[j + u], v[u].x, ax);
+                ay = fma(sc[j + u], v[u].y, ay);
+            }
+        }
+        for (; j < k; ++j) {
+            const double2 v = ld_stream2(p + (int64_t)j * ld);
+            ax = fma(sc[j], v.x, ax);
+            ay = fma(sc[j], v.y, ay);
+        }
+        if (J.out) *reinterpret_cast<double2*>(J.out + r) = make_double2(ax, ay);
+        double dx = ax, dy = ay;
+        if (J.ref) {
+            const double2 rr = *reinterpret_cast<const double2*>(J.ref + r);
+            dx -= rr.x;
+            dy -= rr.y;
+        }
+        sq = dx * dx + dy * dy;
+    } else if (r < n) {
+        double ax = J.z ? J.z[r] : 0.0;
+        for (int j = 0; j < k; ++j) ax = fma(sc[j], ld_stream(J.V + (int64_t)j * ld + r), ax);
+        if (J.out) J.out[r] = ax;
+        const double dx = J.ref ? ax - J.ref[r] : ax;
+        sq = dx * dx;
+    }
+    const double t = block_sum(sq);
+    if (threadIdx.x == 0) {
+        stat[blockIdx.x] = t;
+        __threadfence();
+        const unsigned int done = atomicAdd(ticket, 1u);
+        s_last = done == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {  // every block's partial is visible (fence before its ticket); sum in block order
+        __threadfence();
+        for (int job = 0; job < 2; ++job) {
+            const int lo = job ? j0.grid : 0, cnt = job ? j1.grid : j0.grid;
+            double v = 0.0;
+            for (int i = threadIdx.x; i < cnt; i += blockDim.x) v += __ldcg(stat + lo + i);
+            v = block_sum(v);
+            if (threadIdx.x == 0) out2[job] = sqrt(v);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch on this stream
+    }
+}
+
+// ---------------------------------------------------------------------------
 // CGS2 middle stage, fused:  w1 = w0 - V h1   and   partials = V^T w1   on a row tile.
 // A CTA owns kTileRows rows.  Phase A streams the tile of V from HBM (warps own columns,
 // lanes own row pairs, per-warp partial sums combined in a fixed order through shared
@@ -598,6 +690,22 @@ int hg_k_lincomb(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, con
                  double s, const double* z, double* out, const double* ref, double* stat,
                  int* nparts) {
     return hg_k_lincomb_push(ctx, V, ld, n, k, c, s, z, out, ref, stat, nparts, nullptr, false);
+}
+
+// x = Q y (+ ||x - x_true||) and ||b - T y|| in one launch; out2[0] = error norm, out2[1] = residual norm
+// (device doubles); stat needs cdiv(n, 512) + cdiv(m, 512) doubles; ticket is a zero-initialised device word.
+int hg_k_iterate(hg_ctx* ctx, const double* Q, int64_t ldq, int64_t n, const double* T, int64_t ldt, int64_t m,
+                 int k, const double* y, const double* b, double* x, const double* x_true, double* stat,
+                 unsigned int* ticket, double* out2) {
+    hg_iter_job j0{Q, ldq, n, 1.0, nullptr, x, x_true, (int)cdiv(n, 2 * kBlock)};
+    hg_iter_job j1{T, ldt, m, -1.0, b, nullptr, nullptr, (int)cdiv(m, 2 * kBlock)};
+    const int grid = j0.grid + j1.grid;
+    if (grid == 0) return HG_OK;
+    hg_launch_scope scope(ctx, HG_K_LINCOMB, 8.0 * (double)k * (double)(n + m) + 24.0 * (double)n + 8.0 * (double)m);
+    const size_t smem = (size_t)(k > 0 ? k : 1) * sizeof(double);
+    iterate_kernel<<<(unsigned)grid, kBlock, smem, ctx->stream>>>(j0, j1, k, y, stat, ticket, out2);
+    HG_CUDA(cudaGetLastError());
+    return HG_OK;
 }
 
 int hg_update_dot_ntiles(int64_t n) { return (int)cdiv(n, kTileRows); }

@@ -171,7 +171,7 @@ spmv_sell16_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ sp
 // (deterministic).  A CTA holds kBlock/32/S slices.  Same per-entry arithmetic as the kernel above;
 // the per-row summation order differs (S interleaved partial sums).
 template <int S>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(S > 8 ? S * 32 : kBlock)
 spmv_sell16_split_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ sptr,
                          const uint16_t* __restrict__ scol, const int* __restrict__ sbase,
                          const double* __restrict__ sval, const double* __restrict__ x,
@@ -179,9 +179,10 @@ spmv_sell16_split_kernel(int64_t rows, int64_t nslices, const int64_t* __restric
                          const double* __restrict__ z2, double g2, const double* __restrict__ ref,
                          double* __restrict__ stat) {
     constexpr int U = 4;
-    constexpr int SPB = kBlock / 32 / S;  // slices per CTA
-    __shared__ double s_part[kBlock / 32][32];
-    __shared__ double s_red[kBlock / 32];
+    constexpr int NW = S > 8 ? S : kBlock / 32;  // warps per CTA
+    constexpr int SPB = NW / S;                  // slices per CTA
+    __shared__ double s_part[NW][32];
+    __shared__ double s_red[NW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int part = warp % S, ls = warp / S;
     const int64_t slice = (int64_t)blockIdx.x * SPB + ls;
@@ -228,7 +229,7 @@ spmv_sell16_split_kernel(int64_t rows, int64_t nslices, const int64_t* __restric
         if (threadIdx.x == 0) {
             double t = 0.0;
 #pragma unroll
-            for (int w = 0; w < kBlock / 32; ++w) t += s_red[w];
+            for (int w = 0; w < NW; ++w) t += s_red[w];
             stat[blockIdx.x] = t;
         }
     }
@@ -430,11 +431,13 @@ bool hg_csr16_ready(hg_ctx* ctx, const hg_matrix* cm) {
 
 int hg_k_spmv_sell16(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
                      const hg_spmv_epilogue& ep, double bytes, int* nparts) {
-    // one warp per slice needs >= ~32 warps per SM; with fewer slices S warps share one
-    const int64_t target = (int64_t)ctx->sm_count * 32;
+    // One warp per slice wants several waves of warps (the kernel keeps ~48 warps per SM resident): with
+    // fewer slices the last, partly filled wave runs latency-bound on a few warps per SM (ncu, 256^2 / 512^2:
+    // 1.15 waves, 3.5 / 5.0 TB/s).  S warps then share a slice so that there are >= 4 waves of warp tasks.
+    const int64_t target = (int64_t)ctx->sm_count * 48 * 4;
     int S = 1;
-    while (S < 8 && m->sell_slices * S < target) S *= 2;
-    const int64_t grid = cdiv(m->sell_slices * S, kBlock / 32);
+    while (S < 16 && m->sell_slices * S < target && m->sell_entries / (m->sell_slices * S * 2) >= 128) S *= 2;
+    const int64_t grid = S > 8 ? m->sell_slices : cdiv(m->sell_slices * S, kBlock / 32);
     HG_REQUIRE(grid < (int64_t)2147483647, "spmv: too many rows for one launch");
     if (nparts && ep.stat) *nparts = (int)grid;
     hg_launch_scope scope(ctx, HG_K_SPMV, bytes);
@@ -443,7 +446,8 @@ int hg_k_spmv_sell16(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y
     if (S == 1) spmv_sell16_kernel<4><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
     else if (S == 2) spmv_sell16_split_kernel<2><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
     else if (S == 4) spmv_sell16_split_kernel<4><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
-    else spmv_sell16_split_kernel<8><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
+    else if (S == 8) spmv_sell16_split_kernel<8><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
+    else spmv_sell16_split_kernel<16><<<(unsigned)grid, 512, 0, ctx->stream>>>(HG_SELL16_ARGS);
 #undef HG_SELL16_ARGS
     HG_CUDA(cudaGetLastError());
     return HG_OK;

@@ -1,6 +1,7 @@
-/* Minimal declarations of the MEX C API used by hgmres_mex.cpp — for SYNTAX CHECKS ONLY
- * (`g++ -fsyntax-only -Istub`).  The real mex.h ships with MATLAB / Octave, neither of
- * which exists in the build container, so the gateway is unverified at run time. */
+/* Minimal declarations of the MEX C API used by hgmres_mex.cpp.  The real mex.h ships with MATLAB /
+ * Octave, neither of which exists in the build container; this header serves the syntax check
+ * (`g++ -fsyntax-only -Istub`) and the mock MATLAB API the gateway is EXECUTED against in
+ * tests/test_gpu_mex.py (tests/mex_mock/mex_mock.cpp implements these functions). */
 #ifndef HG_STUB_MEX_H
 #define HG_STUB_MEX_H
 #include <stddef.h>
@@ -24,6 +25,7 @@ mwIndex* mxGetIr(const mxArray*);
 mwIndex* mxGetJc(const mxArray*);
 double mxGetScalar(const mxArray*);
 int mxGetString(const mxArray*, char*, mwSize);
+void* mxCalloc(size_t, size_t);
 mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
 mxArray* mxCreateDoubleScalar(double);
 void mexErrMsgIdAndTxt(const char*, const char*, ...);

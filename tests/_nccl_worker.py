@@ -61,6 +61,50 @@ for mode in (1, 2, 0):
     dist.broadcast(t0, src=0)
     assert torch.equal(t, t0), mode
     ar.close()
+# a deeper Krylov space on a larger slice: every tile shape of the whole-step kernel (k <= 16 / 40 / 96 / 208,
+# csrc/cgs2_step.cu) with its in-kernel collectives, against the separate-kernel peer path and the oracle
+N2, nv2, K2 = 64, 48, 110
+A2, B2, b2, xt2 = ct.make_ct_problem(N2, nv2, "fan", "pixel")
+A2_p, B2_p, (lo2, hi2) = sharding.shard_host_matrices(A2, B2, P, rank)
+dA2, dB2 = hg.DeviceMatrix.from_any(A2_p, ctx), hg.DeviceMatrix.from_any(B2_p, ctx)
+op2 = lambda v: np.asarray(B2 @ (A2 @ v)).ravel() + lam * v
+Qo2, Ho2, betao2, _ = oracle.arnoldi(op2, np.asarray(B2 @ b2).ravel(), K2, orth="cgs2")
+hg.set_option("dist_transport", 2)
+H2 = {}
+for max_n in (400000, 0, 400000):
+    hg.set_option("cgs_step_max_n", max_n)
+    ar2 = ShardedArnoldi(comm, dA2, dB2, K2)
+    ar2.set_rhs(b2[lo2:hi2])
+    ar2.reset(lam)
+    l0 = ctx.launch_count
+    ar2.steps(K2)
+    Hk, betak, kk = ar2.get()
+    launches = ctx.launch_count - l0
+    assert kk == K2 and abs(betak - betao2) / betao2 < 1e-13
+    if max_n in H2:
+        assert np.array_equal(Hk, H2[max_n])  # deterministic
+    else:
+        H2[max_n] = Hk.copy()
+        H2[("launches", max_n)] = launches
+    for j in range(40):  # the well-determined columns against the oracle
+        assert np.linalg.norm(Hk[:j + 2, j] - Ho2[:j + 2, j]) <= 1e-10 * np.linalg.norm(Ho2[:j + 2, j]), (max_n, j)
+    Qs = np.column_stack([ar2.q_slice(j)[0] for j in range(K2 + 1)])
+    G2 = torch.from_numpy(Qs.T @ Qs).cuda()
+    dist.all_reduce(G2)
+    assert float((G2.cpu() - torch.eye(K2 + 1, dtype=torch.float64)).abs().max()) < 1e-12, max_n
+    t = torch.from_numpy(Hk.copy()).cuda()
+    t0 = t.clone()
+    dist.broadcast(t0, src=0)
+    assert torch.equal(t, t0), max_n  # bit-identical H on every rank
+    ar2.close()
+hg.set_option("cgs_step_max_n", 400000)
+hg.set_option("dist_transport", 0)
+assert H2[("launches", 400000)] <= 4 * K2 + 8 < H2[("launches", 0)], H2[("launches", 400000)]
+for j in range(40):
+    assert np.linalg.norm(H2[400000][:j + 2, j] - H2[0][:j + 2, j]) <= 1e-10 * np.linalg.norm(H2[0][:j + 2, j]), j
+dA2.close()
+dB2.close()
+
 dH = np.linalg.norm(H_by_transport[1] - H_by_transport[2]) / np.linalg.norm(H_by_transport[1])
 assert dH < 1e-12, dH
 assert np.array_equal(H_by_transport[0], H_by_transport[2])

@@ -377,7 +377,7 @@ def test_cgs_staged_stage_against_numpy(hg, ctx, n, k):
     for w1, d in outs:
         assert _rel(w1, ref_w1) < 1e-14
         assert np.max(np.abs(d - ref_d) / scale) < 1e-14
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1], equal_nan=True)
     with pytest.raises(hg._lib.HgError):  # outside its range the staged kernel refuses (callers fall back)
         hg._lib.check(lib.hg_cgs_mid(ctx._h, 1000, 8, V.ctypes.data, n, h.ctypes.data, w0.ctypes.data, 1,
                                      np.zeros(1000).ctypes.data, np.zeros(8).ctypes.data))
@@ -399,7 +399,7 @@ def test_cgs2_whole_step_kernel_against_numpy(hg, ctx, n, k):
         hcol, q = np.zeros(k + 1), np.zeros(n)
         hg._lib.check(lib.hg_cgs2_step(ctx._h, n, k, V.ctypes.data, n, w0.ctypes.data, hcol.ctypes.data, q.ctypes.data))
         outs.append((hcol, q))
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1], equal_nan=True)
     hcol, q = outs[0]
     h1 = V.T @ w0
     w1 = w0 - V @ h1
