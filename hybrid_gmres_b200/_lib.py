@@ -24,7 +24,7 @@ class HgExtras(C.Structure):
 
 
 class HgSolverOpts(C.Structure):
-    _fields_ = [("residual_mode", C.c_int), ("reserved", C.c_int * 7)]
+    _fields_ = [("residual_mode", C.c_int), ("error_mode", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class HgError(RuntimeError):

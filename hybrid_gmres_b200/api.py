@@ -276,9 +276,10 @@ def _array_fingerprint(a) -> tuple:
         h = zlib.crc32(raw[:65536])
         h = zlib.crc32(raw[-65536:], h)
         step = (nb - _SAMPLE_CHUNK_BYTES) // _SAMPLE_CHUNKS
-        starts = (np.arange(_SAMPLE_CHUNKS, dtype=np.int64) * step) & ~np.int64(7)
-        idx = (starts[:, None] + np.arange(_SAMPLE_CHUNK_BYTES, dtype=np.int64)[None, :]).reshape(-1)
-        h = zlib.crc32(raw[idx], h)
+        # _SAMPLE_CHUNKS chunks of _SAMPLE_CHUNK_BYTES bytes, `step` apart: a strided view, one 1 MB copy
+        sample = np.lib.stride_tricks.as_strided(raw, shape=(_SAMPLE_CHUNKS, _SAMPLE_CHUNK_BYTES), strides=(step, 1),
+                                                 writeable=False)
+        h = zlib.crc32(np.ascontiguousarray(sample), h)
     return (a.__array_interface__["data"][0], a.shape, a.dtype.str, h)
 
 
@@ -435,7 +436,7 @@ def _extras(maxit, n, want, want_x=True, aux=False):
 
 
 def _rtp(fn_name, A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm=None, cache=True,
-         stats=None):
+         stats=None, error_mode=0):
     ctx = _ctx_of(ctx, A, B)
     maxit = int(maxit)
     st = {} if (stats is not None or _TRACE) else None
@@ -457,6 +458,7 @@ def _rtp(fn_name, A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, 
         niters, x_valid = C.c_int(), C.c_int()
         opts = HgSolverOpts()
         opts.residual_mode = int(residual_mode)
+        opts.error_mode = int(error_mode)
         want_x = extras is not None and extras.get("want_X", True)
         ex, bufs = _extras(maxit, n, extras is not None, want_x=want_x)
         t0 = time.perf_counter()
@@ -496,24 +498,27 @@ def _rtp(fn_name, A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, 
 
 
 def hybrid_ab_gmres_rtp(A, B, b, x_true, tol, maxit, lam, *, ctx=None, residual_mode=0, extras=None,
-                        nperm=None, cache=True, stats=None):
+                        nperm=None, cache=True, stats=None, error_mode=0):
     """``hybrid_ab_gmres_rtp.m:1`` — same positional arguments and outputs.
     ``x`` is ``None`` exactly when the reference leaves it unassigned (``:25``).
     ``nperm`` (optional, e.g. ``ct.tile_permutation(N)``) runs the solve with the n-space in that
     order on the device; inputs and outputs stay in the caller's order.  Host matrices stay resident
     on the device between calls (``cache=False`` uploads afresh; see :func:`clear_matrix_cache`).
     ``extras`` (dict) receives ``H``, ``beta`` and the iterates ``X`` (skip those with
-    ``extras={"want_X": False}``); ``stats`` (dict) the wall-clock breakdown of the call in ms."""
+    ``extras={"want_X": False}``); ``stats`` (dict) the wall-clock breakdown of the call in ms.
+    ``error_mode`` 0 (default) takes the error history from the orthonormal basis
+    (``||y||^2 - 2 y'Q'x_true + ||x_true||^2``) and forms ``x`` once at the end; 1 forms ``x_k`` and
+    ``x_k - x_true`` at every iteration as ``:33,36`` do (``hg_solver_opts.error_mode``)."""
     return _rtp("hg_hybrid_ab_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm,
-                cache, stats)
+                cache, stats, error_mode)
 
 
 def hybrid_ba_gmres_rtp(A, B, b, x_true, tol, maxit, lam, *, ctx=None, residual_mode=0, extras=None,
-                        nperm=None, cache=True, stats=None):
+                        nperm=None, cache=True, stats=None, error_mode=0):
     """``hybrid_ba_gmres_rtp.m:1`` — same positional arguments and outputs (keyword arguments: see
     :func:`hybrid_ab_gmres_rtp`)."""
     return _rtp("hg_hybrid_ba_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm,
-                cache, stats)
+                cache, stats, error_mode)
 
 
 def _gkb(fn_name, A, b, x_true, tol, maxit, lam, ctx, At, extras, five_outputs=False):

@@ -358,6 +358,16 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     HG_REQUIRE(maxit >= 1, "rtp solver: maxit must be >= 1");
     HG_CUDA(cudaSetDevice(ctx->device));
     const int residual_mode = opts ? opts->residual_mode : 0;
+    // error_mode 0 (default): ||x_k - x_true|| from the orthonormal basis, x formed once at the end (see below);
+    // 1: form x_k and the difference explicitly at every iteration (hybrid_ba_gmres_rtp.m:30,33 literally).
+    // The literal residual mode and a request for every iterate (extras->X_hist) need x_k anyway.
+    static const int env_error_mode = [] {
+        const char* e = getenv("HG_ERROR_MODE");
+        return e ? atoi(e) : -1;
+    }();
+    int error_mode = opts ? opts->error_mode : 0;
+    if (env_error_mode >= 0) error_mode = env_error_mode;
+    if (residual_mode != 0 || (extras && extras->X_hist)) error_mode = 1;
     const int64_t n = A->cols, m = A->rows;
     const bool trace = getenv("HG_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -372,8 +382,8 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     // host-visible result of an iteration has RING slots so that a slot is rewritten only after the
     // host has consumed it.
     constexpr int RING = 4;
-    DBuf d_x[2], d_xt, d_y, d_g, stat_e, stat_r;
-    PinBuf h_y, h_g, h_s;
+    DBuf d_x[2], d_xt, d_y, d_g, d_c, stat_e, stat_r;
+    PinBuf h_y, h_g, h_s, h_c;
     EventRing ev;
     HG_TRY(ev.create(RING));
     HG_TRY(d_x[0].alloc((size_t)n));
@@ -381,8 +391,10 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     HG_TRY(d_xt.alloc((size_t)n));
     HG_TRY(d_y.alloc((size_t)maxit + 1));
     HG_TRY(d_g.alloc((size_t)maxit + 2));
+    HG_TRY(d_c.alloc((size_t)maxit + 2));
     HG_TRY(stat_e.alloc(hg_stat_capacity(ctx, std::max(n, m))));
     HG_TRY(stat_r.alloc(hg_stat_capacity(ctx, std::max(n, m))));
+    HG_TRY(h_c.alloc((size_t)maxit + 2));
     HG_TRY(h_y.alloc((size_t)RING * (maxit + 1)));
     HG_TRY(h_g.alloc((size_t)RING * (maxit + 2)));
     HG_TRY(h_s.alloc((size_t)RING * 2));
@@ -397,6 +409,17 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     const double norm_b = std::sqrt(nb2), norm_xt = std::sqrt(nx2);
     const double t_norms = now();
     HG_TRY(hg_arnoldi_reset(a, lambda));
+    // c_j = q_j' x_true, one dot product per basis vector: with an orthonormal basis (CGS2: 1e-15)
+    //   ||Q_k y - x_true||^2 = ||y||^2 - 2 y'c + ||x_true||^2
+    // gives the error history in O(n) per iteration instead of the O(k n) product x = Q_k y_k
+    auto queue_c = [&](int j) -> int {  // j: 0-based basis column
+        int ns = 0;
+        HG_TRY(hg_k_multidot(ctx, a->Q + (size_t)j * a->ldq, a->ldq, n, 1, d_xt.p, a->partials, &ns));
+        HG_TRY(hg_k_reduce(ctx, a->partials, ns, 1, d_c.p + j, false, nullptr, false));
+        HG_CUDA(cudaMemcpyAsync(h_c.p + j, d_c.p + j, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        return HG_OK;
+    };
+    if (error_mode == 0) HG_TRY(queue_c(0));
     HG_CUDA(cudaStreamSynchronize(ctx->stream));
     const double beta = a->h_beta[0];
 
@@ -428,6 +451,7 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     // discarded when the loop ends early.
     int enq = 0;         // Arnoldi steps queued so far
     int last_x = 0;      // last iteration whose iterate exists (0: none; BA then returns its zeros, :4)
+    int x_formed = 0;    // last iteration whose iterate was actually written to d_x[k & 1]
     auto queue_step = [&](int kk) -> int {
         HG_TRY(hg_arnoldi_steps(a, 1));
         if (kind == RTP_AB) {
@@ -439,16 +463,19 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
             HG_CUDA(cudaMemcpyAsync(h_g.p + (size_t)(kk % RING) * (maxit + 2), d_g.p, (size_t)(kk + 1) * 8,
                                     cudaMemcpyDeviceToHost, ctx->stream));
         }
+        if (error_mode == 0 && kk < maxit) HG_TRY(queue_c(kk));  // q_{kk+1}' x_true (needed from iteration kk+1 on)
         if (kk == 1) HG_CUDA(cudaEventRecord(ev.e[0], ctx->stream));
         return HG_OK;
     };
+    std::vector<double> err_alg(maxit, 0.0);  // error_mode 0: error norms formed on the host
+    std::vector<char> err_explicit(maxit, 0);
     auto finish_iterate = [&](int j, bool* stop) -> int {  // histories of iteration j, stop rule
         const double tw = now();
         HG_CUDA(cudaEventSynchronize(ev.e[j % RING]));
         t_wait += now() - tw;
         const double* hs = h_s.p + (size_t)(j % RING) * 2;
         residual_norm[j - 1] = hs[1] / norm_b;
-        error_norm[j - 1] = hs[0] / norm_xt;
+        error_norm[j - 1] = (error_mode == 0 && !err_explicit[j - 1]) ? err_alg[j - 1] / norm_xt : hs[0] / norm_xt;
         last_x = j;
         *stop = residual_norm[j - 1] <= tol;  // :38 / :35
         return HG_OK;
@@ -503,12 +530,32 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
         }
         t_host += now() - th;
         HG_CUDA(cudaMemcpyAsync(d_y.p, yk, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+        bool form_x = error_mode != 0;
+        if (error_mode == 0) {
+            // ||x_k - x_true||^2 = ||y||^2 - 2 y'c + ||x_true||^2 in extended precision; when the error is small
+            // against ||x_true|| the subtraction cancels, so below 1 % relative error the iterate and the
+            // difference are formed explicitly for this iteration (rounding of the formula: ~1e-15 ||x_true||^2)
+            long double yy = 0.0L, yc = 0.0L;
+            for (int j = 0; j < k; ++j) {
+                yy += (long double)yk[j] * yk[j];
+                yc += (long double)yk[j] * h_c.p[j];
+            }
+            const long double e2 = yy - 2.0L * yc + (long double)nx2;
+            if (e2 > 1e-4L * (long double)nx2) {
+                err_alg[k - 1] = (double)sqrtl(e2);
+            } else {
+                err_explicit[k - 1] = 1;
+                form_x = true;
+            }
+            if (form_x) x_formed = k;
+        }
         // x = Q(:,1:k)*yk fused with ||x - x_true||^2          (:33,36 / :30,33)
         double* xk = d_x[k & 1].p;
         if (residual_mode == 0) {
             // ... and ||b - A*x|| with A*x = (A*Q_k) yk from the cached columns, both norms finished by the
             // last block of the same launch
-            HG_TRY(hg_k_iterate(ctx, a->Q, a->ldq, n, a->T + a->ldt, a->ldt, m, k, d_y.p, a->d_b, xk, d_xt.p,
+            // (error_mode 0: only the residual job; x is formed once, after the loop)
+            HG_TRY(hg_k_iterate(ctx, a->Q, a->ldq, form_x ? n : 0, a->T + a->ldt, a->ldt, m, k, d_y.p, a->d_b, xk, d_xt.p,
                                 stat_e.p, reinterpret_cast<unsigned int*>(ctx->d_scalars + 40), ctx->d_scalars + 1));
         } else {
             int np_e = 0, np_r = 0;
@@ -537,6 +584,12 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     *niters = k;
     const bool have_x = (kind == RTP_BA) || last_x > 0;  // BA initialises x = zeros (hybrid_ba_gmres_rtp.m:4)
     const double t_loop_end = now();
+    if (error_mode == 0 && last_x > 0 && x_formed != last_x) {
+        // x = Q(:,1:k)*yk for the iteration the reference stops at, formed once     (:33 / :30)
+        const double* yl = h_y.p + (size_t)(last_x % RING) * (maxit + 1);
+        HG_CUDA(cudaMemcpyAsync(d_y.p, yl, (size_t)last_x * 8, cudaMemcpyHostToDevice, ctx->stream));
+        HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n, last_x, d_y.p, 1.0, nullptr, d_x[last_x & 1].p, nullptr, nullptr, nullptr));
+    }
     HG_CUDA(cudaMemcpyAsync(x, d_x[last_x & 1].p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     HG_CUDA(cudaStreamSynchronize(ctx->stream));  // also drains a discarded speculative step
     g_solve_stats[0] = t_setup - t_begin;

@@ -137,13 +137,15 @@ __device__ __forceinline__ void peer_allreduce(const StepPeer& pr, int which, do
                     break;
                 }
             }
-            __threadfence_system();  // acquire: later reads of peer-written rows come after the observed epochs
             v = ok ? __longlong_as_double((long long)((w0 >> 32) | (w1 & 0xffffffff00000000ull))) : 0.0;
         }
         double s = 0.0;
         for (int r = 0; r < P; ++r) s += __shfl_sync(0xffffffffu, v, r);  // rank order
         if (lane == 0) sh[j] = s;
     }
+    // acquire, once per exchange (a system-scope fence per polled word costs microseconds): reads of
+    // peer-written rows that follow come after the observed epochs
+    __threadfence_system();
     __syncthreads();
 }
 
@@ -481,31 +483,47 @@ int launch_step(hg_ctx* ctx, StepArgs& a) {
     return HG_OK;
 }
 
-int g_step_max_n = -1;
+int g_step_max_n = -1, g_step_max_n_dist = -1;
 
 }  // namespace
 
 // Largest Krylov vector length for which the whole-step kernel is used (option "cgs_step_max_n" / env
-// HG_CGS_STEP_MAX_N; 0 disables).  Above it the separate streaming kernels win: their multi-dot and update
-// sweeps run at 6.5-6.6 TB/s, the staged pipeline of this kernel at ~5.3.
+// HG_CGS_STEP_MAX_N; 0 disables).  Measured on one B200, 200-step cycles (profiles/r02_cgs_step_compare.jsonl):
+// 155 vs 166 us per step at n = 65 536, 256 vs 255 at 132 496, 457 vs 432 at 262 144 — above ~130 000 rows the
+// separate streaming kernels win (their multi-dot and update sweeps run at 6.5 TB/s, the staged pipeline of
+// this kernel at ~4.5), below it the seven launches and three second-stage reductions they need cost more.
 int64_t hg_cgs2_step_max_n() {
     if (g_step_max_n < 0) {
         const char* e = getenv("HG_CGS_STEP_MAX_N");
-        g_step_max_n = e ? atoi(e) : 400000;
+        g_step_max_n = e ? atoi(e) : 140000;
     }
     return g_step_max_n;
 }
 void hg_cgs2_step_max_n_set(int v) { g_step_max_n = v < 0 ? 0 : v; }
+// the same for a rank's slice on several GPUs (option "cgs_step_max_n_dist" / env HG_CGS_STEP_MAX_N_DIST):
+// there the kernel also replaces the pull, three all-reduce kernels and the scale kernel of the peer transport
+int64_t hg_cgs2_step_max_n_dist() {
+    if (g_step_max_n_dist < 0) {
+        const char* e = getenv("HG_CGS_STEP_MAX_N_DIST");
+        g_step_max_n_dist = e ? atoi(e) : 300000;
+    }
+    return g_step_max_n_dist;
+}
+void hg_cgs2_step_max_n_dist_set(int v) { g_step_max_n_dist = v < 0 ? 0 : v; }
 
 bool hg_cgs2_step_eligible(const hg_ctx* ctx, int64_t n, int k) {
     (void)ctx;
     return k >= 1 && k <= 208 && n >= 1 && n <= hg_cgs2_step_max_n();
 }
+bool hg_cgs2_step_eligible_dist(const hg_ctx* ctx, int64_t n_p, int k) {
+    (void)ctx;
+    return k >= 1 && k <= 208 && n_p >= 1 && n_p <= hg_cgs2_step_max_n_dist();
+}
 
 // partials capacity needed: (k + 2) * sm_count doubles
 int hg_k_cgs2_step(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* w0, double* w1,
                    double* qnext, double* Hcol, double* hcur, double* partials) {
-    HG_REQUIRE(hg_cgs2_step_eligible(ctx, n, k), "cgs2_step: (n, k) out of range");
+    HG_REQUIRE(k >= 1 && k <= 208 && n >= 1, "cgs2_step: (n, k) out of range");
     StepArgs a;
     a.V = V;
     a.ld = ld;
@@ -535,7 +553,7 @@ int hg_k_cgs2_step_peer(hg_comm* c, const double* V, int64_t ld, int64_t n_p, in
                         double* qnext, double* Hcol, double* hcur, double* partials, int64_t row0,
                         const double* q_slice, double shift, int buf) {
     hg_ctx* ctx = c->ctx;
-    HG_REQUIRE(hg_cgs2_step_eligible(ctx, n_p, k) && k + 1 <= c->lay.kpad, "cgs2_step_peer: (n, k) out of range");
+    HG_REQUIRE(k >= 1 && k <= 208 && n_p >= 1 && k + 1 <= c->lay.kpad, "cgs2_step_peer: (n, k) out of range");
     StepArgs a;
     a.V = V;
     a.ld = ld;

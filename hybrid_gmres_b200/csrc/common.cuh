@@ -240,8 +240,10 @@ int hg_k_cgs_mid_staged(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int
 
 // whole CGS2 step in one persistent cooperative kernel (cgs2_step.cu): small / medium Krylov vectors
 bool hg_cgs2_step_eligible(const hg_ctx* ctx, int64_t n, int k);
+bool hg_cgs2_step_eligible_dist(const hg_ctx* ctx, int64_t n_p, int k);
 int64_t hg_cgs2_step_max_n();
 void hg_cgs2_step_max_n_set(int v);
+void hg_cgs2_step_max_n_dist_set(int v);
 int hg_k_cgs2_step(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* w0, double* w1,
                    double* qnext, double* Hcol, double* hcur, double* partials);
 

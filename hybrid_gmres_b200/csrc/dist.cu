@@ -328,7 +328,7 @@ static int darnoldi_step(hg_darnoldi* a, int kk) {
         HG_TRY(hg_k_spmv(ctx, a->A, hg_peer_qfull(c, a->qbuf), tcol, ep, nullptr));  // u_p = A_p q
         HG_TRY(hg_k_spmv(ctx, a->B, tcol, hg_peer_ypart(c), ep, nullptr));           // partial B^p u_p
         HG_TRY(hg_k_peer_signal(c, HG_FLAG_Y));
-        if (hg_cgs2_step_eligible(ctx, a->n_p, kk)) {
+        if (hg_cgs2_step_eligible_dist(ctx, a->n_p, kk)) {
             // slices of a few hundred thousand rows: reduce-scatter, CGS2 with its three all-reduces, all-gather
             // and normalisation in ONE persistent kernel (cgs2_step.cu) — 4 launches per step instead of 10
             a->qbuf ^= 1;
@@ -432,7 +432,7 @@ extern "C" int hg_darnoldi_step_bytes(hg_darnoldi* a, int k, double* bytes) {
     HG_REQUIRE(a && bytes, "hg_darnoldi_step_bytes: NULL");
     // this rank's share of S(k) (hg_arnoldi_step_bytes) plus the replicated q / partial w vectors
     const double np = (double)a->n_p, mp = (double)a->m_p, n = (double)a->n_pad;
-    const bool one_pass = a->peer && (hg_cgs2_step_eligible(a->ctx, a->n_p, k) ||
+    const bool one_pass = a->peer && (hg_cgs2_step_eligible_dist(a->ctx, a->n_p, k) ||
                                       (hg_cgs_fused_mode() == 2 && hg_cgs_staged_nparts(a->ctx, a->n_p, k) > 0));
     *bytes = hg_spmv_stream_bytes(a->A) + hg_spmv_stream_bytes(a->B) + 16.0 * mp + 16.0 * n + 72.0 * np +
              (one_pass ? 24.0 : 32.0) * (double)k * np;

@@ -297,6 +297,10 @@ extern "C" int hg_set_option(const char* name, int value) {
         hg_cgs2_step_max_n_set(value);
         return HG_OK;
     }
+    if (strcmp(name, "cgs_step_max_n_dist") == 0) {
+        hg_cgs2_step_max_n_dist_set(value);
+        return HG_OK;
+    }
     if (strcmp(name, "cgs_alternate") == 0) {
         g_cgs_alternate = value ? 1 : 0;
         return HG_OK;

@@ -73,9 +73,10 @@ int hg_version(void);
  * "cgs_alternate": 0 (default; env HG_CGS_ALTERNATE=1 enables) the CGS2 update kernels walk the rows
  * from the end, so each sweep over the basis starts on the ~100 MB the previous one left in L2
  * (measured neutral on B200).
- * "cgs_step_max_n" / env HG_CGS_STEP_MAX_N (default 400000; 0 disables): Krylov vectors up to this length
+ * "cgs_step_max_n" / env HG_CGS_STEP_MAX_N (default 140000; 0 disables): Krylov vectors up to this length
  * run the whole CGS2 step (orthogonalisation, norm, normalisation) in ONE persistent cooperative kernel
- * (csrc/cgs2_step.cu) instead of seven launches.
+ * (csrc/cgs2_step.cu) instead of seven launches.  "cgs_step_max_n_dist" / HG_CGS_STEP_MAX_N_DIST (default
+ * 300000): the same for a rank's slice on several GPUs, where the kernel also does the step's collectives.
  * "dist_transport": see hg_comm_transport. */
 int hg_set_option(const char* name, int value);
 
@@ -184,8 +185,8 @@ int hg_cgs_mid(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, const
 
 /* One whole CGS2 step (two-pass classical Gram-Schmidt, norm, normalisation) of w0 against the k columns of
  * V in the single persistent cooperative kernel of csrc/cgs2_step.cu: hcol[0..k) = V'w0 + V'(w0 - V V'w0),
- * hcol[k] = ||v||, q = v / ||v||.  1 <= k <= 208 and n <= option "cgs_step_max_n" (default 400000), else
- * HG_ERR_INVALID — larger vectors use the separate streaming kernels. */
+ * hcol[k] = ||v||, q = v / ||v||.  1 <= k <= 208, else HG_ERR_INVALID.  (The solvers use this kernel for
+ * vectors up to option "cgs_step_max_n"; longer ones run the separate streaming kernels.) */
 int hg_cgs2_step(hg_ctx* ctx, int64_t n, int k, const double* V, int64_t ld, const double* w0, double* hcol,
                  double* q);
 
@@ -244,7 +245,12 @@ int hg_darnoldi_step_bytes(hg_darnoldi* a, int k, double* bytes);
 typedef struct hg_solver_opts {
     int residual_mode; /* 0: r = b - W*y from the cached A*Q columns (default)
                           1: literal r = b - A*x SpMV (hybrid_ab_gmres_rtp.m:35) */
-    int reserved[7];
+    int error_mode;    /* 0 (default): ||x_k - x_true||^2 = ||y_k||^2 - 2 y_k'c + ||x_true||^2 with c = Q_k'x_true
+                          (one dot product per new basis vector; exact for an orthonormal basis, which CGS2
+                          delivers to 1e-15), x_k formed explicitly only when that error is below 1 % of
+                          ||x_true|| (cancellation) and once for the returned iterate;
+                          1: x_k = Q_k y_k and the difference formed at every iteration (:33,36 literally) */
+    int reserved[6];
 } hg_solver_opts;
 
 /* Optional extra outputs for parity tests (any pointer may be NULL). */

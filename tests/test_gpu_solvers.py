@@ -387,3 +387,45 @@ def test_config2_256_ba_rtp_vs_oracle(hg, ctx, b_kind):
         assert ratio[k] <= 1.0, (name, k + 1, d[k], sens[k], [f"{v:.1e}" for v in d[38:]], [f"{v:.1e}" for v in sens[38:]])
     assert np.max(d_res[:20]) < TOL and np.max(d_x[:20]) < TOL  # before the first sensitive stretch: the plain bar
     assert abs(ex_d["beta"] - ex_o["beta"]) / ex_o["beta"] < 1e-13
+
+
+def test_rtp_error_history_modes_agree(hg, ctx, ct48_unmatched):
+    """error_mode 0 (default: ||x_k - x_true|| from the orthonormal basis, x formed once) against error_mode 1
+    (x_k and the difference formed at every iteration, hybrid_ba_gmres_rtp.m:30,33 literally) and the oracle."""
+    import oracle
+    A, B, b, x_true = ct48_unmatched
+    for f, fo in ((hg.hybrid_ba_gmres_rtp, oracle.hybrid_ba_gmres_rtp), (hg.hybrid_ab_gmres_rtp, oracle.hybrid_ab_gmres_rtp)):
+        x0, e0, r0, it0 = f(A, B, b, x_true, 1e-6, 40, 1e-2, ctx=ctx, error_mode=0)
+        x1, e1, r1, it1 = f(A, B, b, x_true, 1e-6, 40, 1e-2, ctx=ctx, error_mode=1)
+        xo, eo, ro, ito = fo(A, B, b, x_true, 1e-6, 40, 1e-2)
+        assert it0 == it1 == ito
+        assert np.max(np.abs(e0 - e1) / e1) < 1e-10 and np.array_equal(r0, r1)
+        assert np.max(np.abs(e0 - eo) / eo) < 1e-8
+        assert np.linalg.norm(x0 - x1) <= 1e-13 * np.linalg.norm(x1)
+        # early stop: the iterate returned is the one of the stopping iteration
+        xs, es, rs, its = f(A, B, b, x_true, float(r1[7]) * 1.0000001, 40, 1e-2, ctx=ctx)
+        xso, eso, rso, itso = fo(A, B, b, x_true, float(r1[7]) * 1.0000001, 40, 1e-2)
+        assert its == itso == 8 and np.linalg.norm(xs - xso) <= 1e-8 * np.linalg.norm(xso)
+
+
+def test_rtp_error_history_small_errors_fall_back_to_explicit(hg, ctx):
+    """A consistent, well conditioned problem converges to a relative error far below 1 %: there the
+    algebraic formula would cancel, so those iterations form x_k explicitly — the history must follow the
+    oracle down to 1e-9 relative error with the usual 1e-8 agreement."""
+    import oracle
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    m, n = 600, 400
+    A = sp.random(m, n, 0.05, random_state=7, format="csr") + sp.vstack([sp.identity(n) * 3.0, sp.csr_matrix((m - n, n))])
+    A = A.tocsr()
+    B = A.T.tocsr()
+    x_true = rng.standard_normal(n)
+    b = A @ x_true
+    x, err, res, it = hg.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, 60, 1e-12, ctx=ctx)
+    xo, erro, reso, ito = oracle.hybrid_ba_gmres_rtp(A, B, b, x_true, 0.0, 60, 1e-12)
+    assert it == ito and erro[-1] < 1e-6  # the regime the guard exists for
+    ok = erro > 1e-9
+    assert np.max(np.abs(err[ok] - erro[ok]) / erro[ok]) < 1e-6
+    big = erro > 1e-6
+    assert np.max(np.abs(err[big] - erro[big]) / erro[big]) < 1e-8
+    assert np.linalg.norm(x - xo) <= 1e-8 * np.linalg.norm(xo)
