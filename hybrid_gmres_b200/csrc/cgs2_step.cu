@@ -102,7 +102,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 // All-reduce of sh[0..ncols) over the ranks.  CTA 0 stores this rank's sums into every rank's inbox (own
 // included); EVERY CTA then polls its rank's inbox and adds the P contributions in rank order, so all CTAs
 // of all ranks end with identical bits.  Inbox entry (j, src) is 16 bytes at ((j * P + src) * 2) words.
-__device__ __forceinline__ void peer_allreduce(const StepPeer& pr, int which, double* sh, int ncols, int warp, int lane) {
+__device__ __forceinline__ void peer_allreduce(const StepPeer& pr, int which, double* sh, int ncols, double* stage,
+                                               int warp, int lane) {
     const int P = pr.t.P;
     const unsigned int epoch = pr.ar_epoch[which];
     __syncthreads();  // sh holds the local sums
@@ -118,31 +119,35 @@ __device__ __forceinline__ void peer_allreduce(const StepPeer& pr, int which, do
         }
     }
     __syncthreads();  // CTA 0: everything read from sh before it is overwritten
+    // every thread polls one (column, rank) entry at a time — ncols * P entries over 512 threads, i.e. one or
+    // two NVLink latencies per exchange instead of one per column — then thread j adds its P values in rank order
     const unsigned long long* inbox = reinterpret_cast<const unsigned long long*>(pr.t.base[pr.t.rank] + pr.inbox_off[which]);
-    for (int j = warp; j < ncols; j += kWarps) {
-        double v = 0.0;
-        if (lane < P) {
-            const unsigned long long* src = inbox + ((size_t)j * P + lane) * 2;
-            const long long t0 = clock64();
-            unsigned long long w0, w1;
-            bool ok = true;
-            for (;;) {
-                w0 = ld_relaxed_sys_u64(src);
-                w1 = ld_relaxed_sys_u64(src + 1);
-                if ((unsigned int)w0 == epoch && (unsigned int)w1 == epoch) break;
-                if (clock64() - t0 > kStepSpinLimit) {
-                    *pr.err = 1ull;
-                    __threadfence_system();
-                    ok = false;
-                    break;
-                }
+    double* vals = stage;  // ncols * P doubles of scratch (the tile stages are idle between sweeps)
+    for (int idx = threadIdx.x; idx < ncols * P; idx += kThreads) {
+        const unsigned long long* src = inbox + (size_t)idx * 2;  // entry (j, src rank) = j * P + rank
+        const long long t0 = clock64();
+        unsigned long long w0, w1;
+        bool ok = true;
+        for (;;) {
+            w0 = ld_relaxed_sys_u64(src);
+            w1 = ld_relaxed_sys_u64(src + 1);
+            if ((unsigned int)w0 == epoch && (unsigned int)w1 == epoch) break;
+            if (clock64() - t0 > kStepSpinLimit) {
+                *pr.err = 1ull;
+                ok = false;
+                break;
             }
-            v = ok ? __longlong_as_double((long long)((w0 >> 32) | (w1 & 0xffffffff00000000ull))) : 0.0;
         }
-        double s = 0.0;
-        for (int r = 0; r < P; ++r) s += __shfl_sync(0xffffffffu, v, r);  // rank order
-        if (lane == 0) sh[j] = s;
+        vals[idx] = ok ? __longlong_as_double((long long)((w0 >> 32) | (w1 & 0xffffffff00000000ull))) : 0.0;
     }
+    __syncthreads();
+    for (int j = threadIdx.x; j < ncols; j += kThreads) {
+        double s = 0.0;
+        for (int r = 0; r < P; ++r) s += vals[j * P + r];  // rank order
+        sh[j] = s;
+    }
+    (void)warp;
+    (void)lane;
     // acquire, once per exchange (a system-scope fence per polled word costs microseconds): reads of
     // peer-written rows that follow come after the observed epochs
     __threadfence_system();
@@ -222,26 +227,32 @@ __global__ void __launch_bounds__(kThreads, 1) cgs2_step_kernel(StepArgs a) {
             }
         }
         __syncthreads();
-        for (int i = 0; i < my_tiles; ++i) {
-            const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)i * G) * TR;
-            for (int t2 = threadIdx.x; t2 < TR / 2; t2 += kThreads) {
-                const int64_t r = r0 + 2 * t2;  // n (= n_p) is a multiple of 32: pairs never straddle it
-                if (r < n) {
-                    double2 sacc = make_double2(0.0, 0.0);
-#pragma unroll 4
-                    for (int pp = 0; pp < pr.t.P; ++pp) {  // fixed rank order: every rank forms the same bits
-                        const double2 v = __ldcg(reinterpret_cast<const double2*>(
+        // all threads over all row pairs of this CTA's tiles at once: the P remote loads of a pair are issued
+        // together, so the sweep costs about one NVLink round trip (tile by tile it was my_tiles of them)
+        const int pairs_per_tile = TR / 2;
+        for (int idx = threadIdx.x; idx < my_tiles * pairs_per_tile; idx += kThreads) {
+            const int i = idx / pairs_per_tile, t2 = idx % pairs_per_tile;
+            const int64_t r = ((int64_t)blockIdx.x + (int64_t)i * G) * TR + 2 * t2;  // n (= n_p) is a multiple of 32
+            if (r < n) {
+                double2 vv[HG_MAX_PEERS];
+#pragma unroll
+                for (int pp = 0; pp < HG_MAX_PEERS; ++pp)
+                    if (pp < pr.t.P)
+                        vv[pp] = __ldcg(reinterpret_cast<const double2*>(
                             reinterpret_cast<const double*>(pr.t.base[pp] + pr.ypart_off) + pr.row0 + r));
-                        sacc.x += v.x;
-                        sacc.y += v.y;
+                double2 sacc = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int pp = 0; pp < HG_MAX_PEERS; ++pp)  // fixed rank order: every rank forms the same bits
+                    if (pp < pr.t.P) {
+                        sacc.x += vv[pp].x;
+                        sacc.y += vv[pp].y;
                     }
-                    if (pr.shift != 0.0) {
-                        const double2 qv = *reinterpret_cast<const double2*>(pr.q_slice + r);
-                        sacc.x += pr.shift * qv.x;
-                        sacc.y += pr.shift * qv.y;
-                    }
-                    *reinterpret_cast<double2*>(a.w0w + r) = sacc;
+                if (pr.shift != 0.0) {
+                    const double2 qv = *reinterpret_cast<const double2*>(pr.q_slice + r);
+                    sacc.x += pr.shift * qv.x;
+                    sacc.y += pr.shift * qv.y;
                 }
+                *reinterpret_cast<double2*>(a.w0w + r) = sacc;
             }
         }
         __threadfence();  // staged below through cp.async (L2)
@@ -293,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) cgs2_step_kernel(StepArgs a) {
     cp_async_wait_0();
     grid.sync();
     reduce_partials(a.partials, G, k, sh, warp, lane);
-    if constexpr (PEER) peer_allreduce(a.peer, 0, sh, k, warp, lane);
+    if constexpr (PEER) peer_allreduce(a.peer, 0, sh, k, st0, warp, lane);
     __syncthreads();
     if (blockIdx.x == 0)
         for (int j = threadIdx.x; j < k; j += kThreads) a.Hcol[j] = sh[j];  // h1
@@ -373,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) cgs2_step_kernel(StepArgs a) {
     __threadfence();  // w1 rows of this CTA are re-read below through cp.async (L2)
     grid.sync();
     reduce_partials(a.partials, G, k, sh, warp, lane);
-    if constexpr (PEER) peer_allreduce(a.peer, 1, sh, k, warp, lane);
+    if constexpr (PEER) peer_allreduce(a.peer, 1, sh, k, st0, warp, lane);
     __syncthreads();
     if (blockIdx.x == 0)
         for (int j = threadIdx.x; j < k; j += kThreads) {
@@ -451,19 +462,32 @@ __global__ void __launch_bounds__(kThreads, 1) cgs2_step_kernel(StepArgs a) {
         if (lane == 0) scratch[32] = s;
     }
     // PEER: this exchange is also the barrier that makes every rank's pushed rows visible here
-    if constexpr (PEER) peer_allreduce(a.peer, 2, scratch + 32, 1, warp, lane);
+    if constexpr (PEER) peer_allreduce(a.peer, 2, scratch + 32, 1, st0, warp, lane);
     __syncthreads();
     const double nrm = sqrt(scratch[32]);  // H(k+1,k) = norm(v)
     if (blockIdx.x == 0 && threadIdx.x == 0) a.Hcol[k] = nrm;
     // ------------------------------------------------------------------ sweep 4: V(:,k+1) = v / H(k+1,k)
-    for (int i = 0; i < my_tiles; ++i) {
-        const int64_t row = ((int64_t)blockIdx.x + (int64_t)i * G) * TR + threadIdx.x;
-        if (threadIdx.x < TR && row < n) a.qnext[row] = a.qnext[row] / nrm;  // division, as the reference (:26)
+    // all threads over all rows of this CTA's tiles at once (tile by tile it was my_tiles dependent round trips)
+    for (int idx = threadIdx.x; idx < my_tiles * TR; idx += kThreads) {
+        const int64_t row = ((int64_t)blockIdx.x + (int64_t)(idx / TR) * G) * TR + idx % TR;
+        if (row < n) a.qnext[row] = __ldcg(a.qnext + row) / nrm;  // division, as the reference (:26)
     }
     if constexpr (PEER) {  // ... and this rank's copy of the replicated vector (rows from all ranks)
-        double* qf = reinterpret_cast<double*>(a.peer.t.base[a.peer.t.rank] + a.peer.qfull_off);
-        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < a.peer.n_pad; i += (int64_t)G * kThreads)
-            qf[i] = __ldcg(qf + i) / nrm;
+        double2* qf = reinterpret_cast<double2*>(a.peer.t.base[a.peer.t.rank] + a.peer.qfull_off);
+        const int64_t n2 = a.peer.n_pad / 2;  // n_pad is a multiple of 32
+        const int64_t stride = (int64_t)G * kThreads;
+        int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+        for (; i + 3 * stride < n2; i += 4 * stride) {
+            double2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldcg(qf + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) qf[i + u * stride] = make_double2(v[u].x / nrm, v[u].y / nrm);
+        }
+        for (; i < n2; i += stride) {
+            const double2 v = __ldcg(qf + i);
+            qf[i] = make_double2(v.x / nrm, v.y / nrm);
+        }
     }
 }
 
@@ -500,12 +524,17 @@ int64_t hg_cgs2_step_max_n() {
     return g_step_max_n;
 }
 void hg_cgs2_step_max_n_set(int v) { g_step_max_n = v < 0 ? 0 : v; }
-// the same for a rank's slice on several GPUs (option "cgs_step_max_n_dist" / env HG_CGS_STEP_MAX_N_DIST):
-// there the kernel also replaces the pull, three all-reduce kernels and the scale kernel of the peer transport
+// The same for a rank's slice on several GPUs (option "cgs_step_max_n_dist" / env HG_CGS_STEP_MAX_N_DIST), where
+// the kernel also replaces the pull, three all-reduce kernels and the scale kernel of the peer transport: 4
+// launches per step instead of 10.  OFF by default (0): measured on B200s (profiles/r02_multi_gpu.md) it does not
+// beat the separate kernels — 8 GPUs x 131 072-row slices 2 575 vs 3 300 it/s before the pull / poll / scale
+// loops were parallelised, 2 GPUs x 131 072 rows 3 445 vs 3 692 after, a tie at 32 768 rows — because each of
+// its three in-kernel exchanges costs a grid barrier + a redundant reduction + an NVLink round trip in sequence,
+// where the separate all-reduce kernel works on all coefficients at once.  Kept as a tested option.
 int64_t hg_cgs2_step_max_n_dist() {
     if (g_step_max_n_dist < 0) {
         const char* e = getenv("HG_CGS_STEP_MAX_N_DIST");
-        g_step_max_n_dist = e ? atoi(e) : 300000;
+        g_step_max_n_dist = e ? atoi(e) : 0;
     }
     return g_step_max_n_dist;
 }

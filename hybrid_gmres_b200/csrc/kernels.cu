@@ -195,8 +195,20 @@ reduce_kernel(const double* __restrict__ partials, int np, double* __restrict__ 
               int accumulate, double* __restrict__ out2, int do_sqrt) {
     const int j = blockIdx.x;
     const double* p = partials + (int64_t)j * np;
-    double v = 0.0;
-    for (int i = threadIdx.x; i < np; i += blockDim.x) v += p[i];
+    // eight independent partial sums per thread: the loads of a thread are in flight together (one block
+    // sums up to tens of thousands of per-CTA partials of an SpMV epilogue; a single dependent chain made
+    // this kernel ~15 us at 512^2).  Fixed order: bit-identical reruns.
+    double a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = 0.0;
+    int i = threadIdx.x;
+    const int stride = blockDim.x;
+    for (; i + 7 * stride < np; i += 8 * stride) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] += p[i + u * stride];
+    }
+    for (; i < np; i += stride) a[0] += p[i];
+    double v = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     v = block_sum(v);
     if (threadIdx.x == 0) {
         if (out2) out2[j] = v;

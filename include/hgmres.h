@@ -75,8 +75,9 @@ int hg_version(void);
  * (measured neutral on B200).
  * "cgs_step_max_n" / env HG_CGS_STEP_MAX_N (default 140000; 0 disables): Krylov vectors up to this length
  * run the whole CGS2 step (orthogonalisation, norm, normalisation) in ONE persistent cooperative kernel
- * (csrc/cgs2_step.cu) instead of seven launches.  "cgs_step_max_n_dist" / HG_CGS_STEP_MAX_N_DIST (default
- * 300000): the same for a rank's slice on several GPUs, where the kernel also does the step's collectives.
+ * (csrc/cgs2_step.cu) instead of seven launches.  "cgs_step_max_n_dist" / HG_CGS_STEP_MAX_N_DIST (default 0 =
+ * off: measured slower than the separate kernels): the same for a rank's slice on several GPUs, where the
+ * kernel also does the step's collectives.
  * "dist_transport": see hg_comm_transport. */
 int hg_set_option(const char* name, int value);
 

@@ -97,7 +97,7 @@ for max_n in (4000000, 0, 4000000):
     dist.broadcast(t0, src=0)
     assert torch.equal(t, t0), max_n  # bit-identical H on every rank
     ar2.close()
-hg.set_option("cgs_step_max_n_dist", 300000)
+hg.set_option("cgs_step_max_n_dist", 0)
 hg.set_option("dist_transport", 0)
 assert H2[("launches", 4000000)] <= 4 * K2 + 8 < H2[("launches", 0)], H2[("launches", 4000000)]
 for j in range(20):

@@ -445,3 +445,32 @@ def test_arnoldi_whole_step_kernel_matches_separate_kernels(hg, ctx):
     for j in range(20):
         assert np.linalg.norm(H1[:j + 2, j] - H0[:j + 2, j]) <= 1e-9 * np.linalg.norm(H0[:j + 2, j]), j
     assert np.max(np.abs(Q.T @ Q - np.eye(K + 1))) < 1e-12
+
+
+def test_malformed_sparse_inputs_are_rejected(hg, ctx):
+    """hg_matrix_from_csr / _from_csc validate the caller's arrays on the device (pointer array monotone and
+    ending at nnz, indices inside the matrix) and return HG_ERR_INVALID instead of reading or scattering out
+    of bounds in every later product (the transposition of a CSC upload uses the indices as addresses)."""
+    from hybrid_gmres_b200._lib import HgError
+    indptr = np.array([0, 2, 3, 5], dtype=np.int64)
+    indices = np.array([0, 2, 1, 0, 3], dtype=np.int32)
+    data = np.arange(5, dtype=np.float64) + 1.0
+    ok = hg.DeviceMatrix.from_csr(indptr, indices, data, (3, 4), ctx)
+    assert np.allclose(ok.matvec(np.ones(4)), [3.0, 3.0, 9.0])
+    ok.close()
+    for bad_ptr, bad_idx in ((np.array([0, 3, 2, 5], dtype=np.int64), indices),            # decreasing pointer
+                             (np.array([0, 2, 3, 4], dtype=np.int64), indices),            # does not end at nnz
+                             (np.array([1, 2, 3, 5], dtype=np.int64), indices),            # does not start at 0
+                             (indptr, np.array([0, 2, 1, 0, 4], dtype=np.int32)),          # column == cols
+                             (indptr, np.array([0, -1, 1, 0, 3], dtype=np.int32))):        # negative column
+        with pytest.raises(HgError) as e:
+            hg.DeviceMatrix.from_csr(bad_ptr, bad_idx, data, (3, 4), ctx)
+        assert e.value.status == 1 and "malformed" in str(e.value)
+    # MATLAB-style CSC with 64-bit indices: a row index outside the matrix (also one that only differs above bit 31)
+    jc = np.array([0, 2, 3, 5, 5], dtype=np.int64)
+    for bad_ir in (np.array([0, 3, 1, 0, 2], dtype=np.int64), np.array([0, 2 ** 32 + 1, 1, 0, 2], dtype=np.int64)):
+        with pytest.raises(HgError) as e:
+            hg.DeviceMatrix.from_csc(jc, bad_ir, data, (3, 4), ctx)
+        assert e.value.status == 1
+    good = hg.DeviceMatrix.from_csc(jc, np.array([0, 2, 1, 0, 2], dtype=np.int64), data, (3, 4), ctx)
+    assert np.allclose(good.matvec(np.ones(4)), [5.0, 3.0, 7.0])

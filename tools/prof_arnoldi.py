@@ -13,7 +13,7 @@ dA0 = hg.ct_projector(N, angles, p, "fan", ctx=ctx)
 dB0 = hg.ct_backprojector(N, angles, p, "fan", ctx=ctx)
 b = dA0.matvec(hg.ct.shepp_logan(N))
 q = tile_permutation(N, 4)
-dA, dB = dA0.permute(None, q), dB0.permute(q, None)
+dA, dB = dA0.permute(None, q, sort=False), dB0.permute(q, None)  # as bench.py builds them
 dA0.close(); dB0.close()
 print(dA.spmv_form, dB.spmv_form)
 ar = hg.Arnoldi(dA, dB, "n", steps)
