@@ -506,9 +506,10 @@ def hybrid_ab_gmres_rtp(A, B, b, x_true, tol, maxit, lam, *, ctx=None, residual_
     on the device between calls (``cache=False`` uploads afresh; see :func:`clear_matrix_cache`).
     ``extras`` (dict) receives ``H``, ``beta`` and the iterates ``X`` (skip those with
     ``extras={"want_X": False}``); ``stats`` (dict) the wall-clock breakdown of the call in ms.
-    ``error_mode`` 0 (default) takes the error history from the orthonormal basis
+    ``error_mode`` 2 takes the error history from the orthonormal basis
     (``||y||^2 - 2 y'Q'x_true + ||x_true||^2``) and forms ``x`` once at the end; 1 forms ``x_k`` and
-    ``x_k - x_true`` at every iteration as ``:33,36`` do (``hg_solver_opts.error_mode``)."""
+    ``x_k - x_true`` at every iteration as ``:33,36`` do; 0 (default) picks 2 for n >= 200000
+    (``hg_solver_opts.error_mode``)."""
     return _rtp("hg_hybrid_ab_gmres_rtp", A, B, b, x_true, tol, maxit, lam, ctx, residual_mode, extras, nperm,
                 cache, stats, error_mode)
 

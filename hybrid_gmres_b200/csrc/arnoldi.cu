@@ -358,7 +358,7 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     HG_REQUIRE(maxit >= 1, "rtp solver: maxit must be >= 1");
     HG_CUDA(cudaSetDevice(ctx->device));
     const int residual_mode = opts ? opts->residual_mode : 0;
-    // error_mode 0 (default): ||x_k - x_true|| from the orthonormal basis, x formed once at the end (see below);
+    // error_mode 2: ||x_k - x_true|| from the orthonormal basis, x formed once at the end (see below);
     // 1: form x_k and the difference explicitly at every iteration (hybrid_ba_gmres_rtp.m:30,33 literally).
     // The literal residual mode and a request for every iterate (extras->X_hist) need x_k anyway.
     static const int env_error_mode = [] {
@@ -367,8 +367,12 @@ int rtp_solver(RtpKind kind, hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B
     }();
     int error_mode = opts ? opts->error_mode : 0;
     if (env_error_mode >= 0) error_mode = env_error_mode;
-    if (residual_mode != 0 || (extras && extras->X_hist)) error_mode = 1;
     const int64_t n = A->cols, m = A->rows;
+    // auto: the algebraic form pays once x = Q_k y_k (8 k n bytes) costs more than the two small launches the
+    // extra dot product needs — measured: a gain at 1024^2 (loop 338 -> 319 ms), a loss at 256^2 (5 950 -> 5 380 it/s)
+    if (error_mode == 0) error_mode = n >= 200000 ? 2 : 1;
+    if (residual_mode != 0 || (extras && extras->X_hist)) error_mode = 1;
+    error_mode = error_mode == 2 ? 0 : 1;  // below: 0 algebraic, 1 explicit
     const bool trace = getenv("HG_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();

@@ -132,6 +132,11 @@ struct hg_matrix {
 // 16-byte granular bulk copies of the streaming SpMV may over-read safely
 constexpr int kNnzPad = 16;
 
+#include <mutex>
+// serialises the lazily built per-matrix SpMV forms (sliced copy, 16-bit companions, streaming work table):
+// two host threads using one hg_matrix through different contexts build them once
+std::mutex& hg_matrix_form_mutex();
+
 int hg_ensure_partials(hg_ctx* ctx, size_t ndoubles);
 // doubles a per-block `stat` partial buffer needs for a vector / SpMV of `rows` rows: the block kernels
 // write at most rows/8 + 1024 partials, the streaming SpMV one per work unit (sm_count * 8)

@@ -223,6 +223,11 @@ int hg_matrix_alloc(hg_ctx* ctx, int64_t rows, int64_t cols, int64_t nnz, hg_mat
     return HG_OK;
 }
 
+std::mutex& hg_matrix_form_mutex() {
+    static std::mutex mu;
+    return mu;
+}
+
 void hg_matrix_pick_tpr(hg_matrix* m) {
     const double mean = m->rows > 0 ? (double)m->nnz / (double)m->rows : 0.0;
     int tpr = 2;

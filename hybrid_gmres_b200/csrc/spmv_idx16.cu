@@ -380,6 +380,8 @@ void hg_sell_compress(hg_ctx* ctx, hg_matrix* m) {
 bool hg_csr16_ready(hg_ctx* ctx, const hg_matrix* cm) {
     hg_matrix* m = const_cast<hg_matrix*>(cm);  // lazily built cache
     if (m->csr16_state != 0) return m->csr16_state > 0;
+    std::lock_guard<std::mutex> lk(hg_matrix_form_mutex());
+    if (m->csr16_state != 0) return m->csr16_state > 0;
     m->csr16_state = -1;
     if (m->rows == 0 || m->nnz == 0) return false;
     std::vector<int64_t> ptr((size_t)m->rows + 1), gptr((size_t)m->rows + 1);

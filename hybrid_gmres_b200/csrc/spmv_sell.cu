@@ -236,6 +236,8 @@ spmv_sell32_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ sp
 bool hg_sell_ready(hg_ctx* ctx, const hg_matrix* cm) {
     hg_matrix* m = const_cast<hg_matrix*>(cm);  // lazily built cache, like unit_row
     if (m->sell_state != 0) return m->sell_state > 0;
+    std::lock_guard<std::mutex> lk(hg_matrix_form_mutex());
+    if (m->sell_state != 0) return m->sell_state > 0;  // another thread built it meanwhile
     m->sell_state = -1;
     if (m->rows < 64 || m->nnz < 8 * m->rows) return false;  // short rows: TPR<32 CSR kernels do fine
     const int64_t nslices = cdiv(m->rows, 32);

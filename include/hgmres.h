@@ -246,11 +246,12 @@ int hg_darnoldi_step_bytes(hg_darnoldi* a, int k, double* bytes);
 typedef struct hg_solver_opts {
     int residual_mode; /* 0: r = b - W*y from the cached A*Q columns (default)
                           1: literal r = b - A*x SpMV (hybrid_ab_gmres_rtp.m:35) */
-    int error_mode;    /* 0 (default): ||x_k - x_true||^2 = ||y_k||^2 - 2 y_k'c + ||x_true||^2 with c = Q_k'x_true
-                          (one dot product per new basis vector; exact for an orthonormal basis, which CGS2
-                          delivers to 1e-15), x_k formed explicitly only when that error is below 1 % of
-                          ||x_true|| (cancellation) and once for the returned iterate;
-                          1: x_k = Q_k y_k and the difference formed at every iteration (:33,36 literally) */
+    int error_mode;    /* 2: ||x_k - x_true||^2 = ||y_k||^2 - 2 y_k'c + ||x_true||^2 with c = Q_k'x_true (one dot
+                          product per new basis vector; exact for an orthonormal basis, which CGS2 delivers to
+                          1e-15), x_k formed explicitly only when that error is below 1 % of ||x_true||
+                          (cancellation) and once for the returned iterate;
+                          1: x_k = Q_k y_k and the difference formed at every iteration (:33,36 literally);
+                          0 (default): 2 for n >= 200000, where the product costs more than the extra dot, else 1 */
     int reserved[6];
 } hg_solver_opts;
 
