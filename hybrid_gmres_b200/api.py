@@ -212,10 +212,10 @@ class DeviceMatrix:
 
     @property
     def spmv_form(self) -> str:
-        """Which SpMV kernel this matrix runs with ("csr", "sell32" or "stream")."""
+        """Which SpMV kernel this matrix runs with ("csr", "sell32", "stream" or "group")."""
         f = C.c_int()
         check(self.ctx._lib.hg_matrix_spmv_form(self.ctx._h, self._h, C.byref(f)))
-        return ("csr", "sell32", "stream")[f.value & 15]
+        return ("csr", "sell32", "stream", "group")[f.value & 15]
 
     @property
     def spmv_index_bits(self) -> int:

@@ -126,6 +126,13 @@ struct hg_matrix {
     int32_t* csr_base = nullptr;     // csr_groups
     int64_t* csr_gptr = nullptr;     // rows+1: first group of each row
     int64_t csr_groups = 0;
+    // row-group interleaved copy for the gather-bound row-per-warp matrices (lazily built, spmv_group.cu)
+    int grp_state = 0;            // 0 not examined, 1 built, -1 not eligible
+    int grp_G = 0;                // rows per group
+    int64_t grp_groups = 0, grp_entries = 0;
+    int64_t* grp_ptr = nullptr;   // grp_groups+1 entry offsets (multiples of 32)
+    int32_t* grp_col = nullptr;   // grp_entries
+    double* grp_val = nullptr;
 };
 
 // colind / vals are allocated with this many zero entries of tail padding so the
@@ -277,6 +284,17 @@ int hg_k_spmv_sell16(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y
 int hg_k_spmv_csr16(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
                     const hg_spmv_epilogue& ep, double bytes, int* nparts);
 void hg_idx16_free(hg_matrix* m);
+
+// row-group interleaved form (spmv_group.cu): option "spmv_group" / env HG_SPMV_GROUP
+#ifndef HG_SPMV_GROUP_DEFAULT
+#define HG_SPMV_GROUP_DEFAULT 0
+#endif
+int hg_spmv_group();
+void hg_spmv_group_set(int v);
+bool hg_group_ready(hg_ctx* ctx, const hg_matrix* m);
+void hg_group_free(hg_matrix* m);
+int hg_k_spmv_group(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y, const hg_spmv_epilogue& ep,
+                    double bytes, int* nparts);
 
 // transposition (matrix.cu)
 int hg_transpose_device(hg_ctx* ctx, const hg_matrix* m, hg_matrix** out);

@@ -611,6 +611,8 @@ int hg_k_spmv(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
     if (hg_spmv_stream_eligible(m)) return hg_k_spmv_stream(ctx, m, x, y, ep, nparts);
     if ((hg_spmv_mode() == 0 || hg_spmv_mode() == 3) && hg_sell_ready(ctx, m))
         return hg_k_spmv_sell(ctx, m, x, y, ep, spmv_bytes(m, ep, y != nullptr), nparts);
+    if (m->tpr == 32 && hg_spmv_mode() == 0 && hg_group_ready(ctx, m))
+        return hg_k_spmv_group(ctx, m, x, y, ep, spmv_bytes(m, ep, y != nullptr), nparts);
     if (m->tpr == 32 && hg_spmv_mode() == 0 && hg_idx16_csr_enabled() && hg_csr16_ready(ctx, m))
         return hg_k_spmv_csr16(ctx, m, x, y, ep, spmv_bytes(m, ep, y != nullptr), nparts);
     const int tpr = m->tpr;

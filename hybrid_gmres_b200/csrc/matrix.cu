@@ -254,6 +254,7 @@ extern "C" int hg_matrix_destroy(hg_matrix* m) {
     hg_dfree(m->sell_col);
     hg_dfree(m->sell_val);
     hg_idx16_free(m);
+    hg_group_free(m);
     delete m;
     return HG_OK;
 }
@@ -656,6 +657,8 @@ extern "C" int hg_matrix_spmv_form(hg_ctx* ctx, const hg_matrix* m, int* form) {
     if (hg_spmv_stream_eligible(m)) *form = 2;
     else if (m->rows > 0 && (hg_spmv_mode() == 0 || hg_spmv_mode() == 3) && hg_sell_ready(ctx, m))
         *form = m->sell_col16 ? 1 | 16 : 1;
+    else if (m->rows > 0 && m->tpr == 32 && hg_spmv_mode() == 0 && hg_group_ready(ctx, m))
+        *form = 3;
     else if (m->rows > 0 && m->tpr == 32 && hg_spmv_mode() == 0 && hg_idx16_csr_enabled() && hg_csr16_ready(ctx, m))
         *form = 0 | 16;
     else *form = 0;

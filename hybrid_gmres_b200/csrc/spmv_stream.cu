@@ -301,6 +301,10 @@ extern "C" int hg_set_option(const char* name, int value) {
         hg_cgs2_step_max_n_dist_set(value);
         return HG_OK;
     }
+    if (strcmp(name, "spmv_group") == 0) {
+        hg_spmv_group_set(value);
+        return HG_OK;
+    }
     if (strcmp(name, "cgs_alternate") == 0) {
         g_cgs_alternate = value ? 1 : 0;
         return HG_OK;
