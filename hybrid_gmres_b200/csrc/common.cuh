@@ -287,7 +287,7 @@ void hg_idx16_free(hg_matrix* m);
 
 // row-group interleaved form (spmv_group.cu): option "spmv_group" / env HG_SPMV_GROUP
 #ifndef HG_SPMV_GROUP_DEFAULT
-#define HG_SPMV_GROUP_DEFAULT 0
+#define HG_SPMV_GROUP_DEFAULT 4
 #endif
 int hg_spmv_group();
 void hg_spmv_group_set(int v);

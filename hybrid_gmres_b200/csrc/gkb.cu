@@ -317,18 +317,23 @@ int hybrid_lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
         }
         // projected problem on the host                           (:37-44)
         const double alpha_k1 = alpha1, beta_k1 = beta_k;
+        // T = Bk'*Bk and T^2 (:41-42).  Bk is bidiagonal, so T is tridiagonal and T^2 pentadiagonal: only the
+        // non-zero terms of the reference's dense products are formed, in the same (increasing) order of the
+        // summation index — the skipped terms are exact zeros, so the values are those of the dense products.
         T.assign((size_t)k * k, 0.0);
         for (int j = 0; j < k; ++j)
-            for (int i = 0; i < k; ++i) {
+            for (int i = std::max(0, j - 1); i <= std::min(k - 1, j + 1); ++i) {
                 double acc = 0.0;
-                for (int r = 0; r <= k; ++r) acc += Bk[(size_t)i * ldb + r] * Bk[(size_t)j * ldb + r];
+                for (int r = std::max(i, j); r <= std::min(i, j) + 1; ++r)  // rows where both columns are non-zero
+                    acc += Bk[(size_t)i * ldb + r] * Bk[(size_t)j * ldb + r];
                 T[(size_t)j * k + i] = acc;
             }
         LHS.assign((size_t)k * k, 0.0);
         for (int j = 0; j < k; ++j)
-            for (int i = 0; i < k; ++i) {
+            for (int i = std::max(0, j - 2); i <= std::min(k - 1, j + 2); ++i) {
                 double acc = 0.0;
-                for (int r = 0; r < k; ++r) acc += T[(size_t)r * k + i] * T[(size_t)j * k + r];
+                for (int r = std::max(0, std::max(i, j) - 1); r <= std::min(k - 1, std::min(i, j) + 1); ++r)
+                    acc += T[(size_t)r * k + i] * T[(size_t)j * k + r];
                 LHS[(size_t)j * k + i] = acc;
             }
         LHS[0] += (alpha_k1 * beta_k1) * (alpha_k1 * beta_k1);

@@ -78,6 +78,9 @@ int hg_version(void);
  * (csrc/cgs2_step.cu) instead of seven launches.  "cgs_step_max_n_dist" / HG_CGS_STEP_MAX_N_DIST (default 0 =
  * off: measured slower than the separate kernels): the same for a rank's slice on several GPUs, where the
  * kernel also does the step's collectives.
+ * "spmv_group" / env HG_SPMV_GROUP (default 4; 0 off, 2, 4, 8): long-row matrices that run the row-per-warp
+ * kernel (ray-driven projectors) get a copy in which G adjacent rows are interleaved per warp, so a warp-wide
+ * gather serves G adjacent rays from the same cache lines (csrc/spmv_group.cu: L1 wavefronts 66 % -> 48 %).
  * "dist_transport": see hg_comm_transport. */
 int hg_set_option(const char* name, int value);
 

@@ -481,25 +481,29 @@ def test_spmv_row_group_form_matches_csr(hg, ctx, G):
     """csrc/spmv_group.cu — G adjacent rows interleaved per warp (the gather-bound projector A): same products
     as the row-per-warp CSR kernel up to summation order, ragged groups and a row count that is not a
     multiple of G, all epilogues; bit-identical reruns."""
+    import scipy.sparse as sp
     from hybrid_gmres_b200.ct import ct_projector
-    N = 96
-    angles = np.arange(45) * 4.0
+    N = 256
+    angles = np.arange(21) * (360.0 / 21)
     try:
         hg.set_option("spmv_group", 0)
-        d0 = ct_projector(N, angles, 135, "fan", ctx=ctx)  # 6075 rows (odd), ~130 entries per row
-        assert d0.spmv_form == "csr"
+        d0 = ct_projector(N, angles, 363, "fan", ctx=ctx)  # 7623 rows (odd), ~227 entries per row
+        form0 = d0.spmv_form
         x = np.random.default_rng(5).standard_normal(d0.shape[1])
         y0 = d0.matvec(x)
+        M = sp.csr_matrix(tuple(reversed(d0.download())), shape=d0.shape)
         hg.set_option("spmv_group", G)
-        d1 = ct_projector(N, angles, 135, "fan", ctx=ctx)
-        assert d1.spmv_form == "group"
+        d1 = hg.DeviceMatrix.from_csr(M.indptr, M.indices, M.data, M.shape, ctx)
+        if form0 == "csr":
+            assert d1.spmv_form == "group"
         y1, y2 = d1.matvec(x), d1.matvec(x)
         assert np.array_equal(y1, y2)
         assert np.max(np.abs(y1 - y0)) <= 1e-13 * np.max(np.abs(y0))
+        assert np.max(np.abs(y1 - M @ x)) <= 1e-13 * np.max(np.abs(y0))
         # through a solver: shift epilogue, residual statistics
         import oracle
         from oracle import ct
-        A, B, b, x_true = ct.make_ct_problem(64, 60, "fan", "pixel", noise=0.01)
+        A, B, b, x_true = ct.make_ct_problem(128, 30, "fan", "pixel", noise=0.01)
         xs, es, rs, its = hg.hybrid_ba_gmres_rtp(A, B, b, x_true, 1e-6, 20, 1e-2, ctx=ctx, residual_mode=1, cache=False)
         xo, eo, ro, ito = oracle.hybrid_ba_gmres_rtp(A, B, b, x_true, 1e-6, 20, 1e-2)
         assert its == ito and np.max(np.abs(rs - ro) / ro) < 1e-8 and np.max(np.abs(es - eo) / eo) < 1e-8
