@@ -231,6 +231,11 @@ int hg_spmv_group() {
     return g_group;
 }
 void hg_spmv_group_set(int v) {
+    if (v < 0) {  // back to the built-in default (large matrices only)
+        g_group = HG_SPMV_GROUP_DEFAULT;
+        g_group_explicit = false;
+        return;
+    }
     g_group = (v == 2 || v == 4 || v == 8) ? v : 0;
     g_group_explicit = true;
 }

@@ -508,4 +508,4 @@ def test_spmv_row_group_form_matches_csr(hg, ctx, G):
         xo, eo, ro, ito = oracle.hybrid_ba_gmres_rtp(A, B, b, x_true, 1e-6, 20, 1e-2)
         assert its == ito and np.max(np.abs(rs - ro) / ro) < 1e-8 and np.max(np.abs(es - eo) / eo) < 1e-8
     finally:
-        hg.set_option("spmv_group", 0)
+        hg.set_option("spmv_group", -1)  # back to the default (G = 4 for matrices of >= 100 000 rows)
