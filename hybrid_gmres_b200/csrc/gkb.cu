@@ -117,6 +117,30 @@ struct Gkb {
         *host = hs[slot];
         return HG_OK;
     }
+    // ---- lagged histories ---------------------------------------------------------------------------
+    // The error / residual norms of iteration k are queued without a host synchronisation (device slots
+    // 20..22 -> pinned ring) and read after the first synchronisation of iteration k+1, which follows them in
+    // the stream: an iteration synchronises twice (beta, alpha) instead of four or five times.  The stop rule
+    // of iteration k is therefore applied one half-step later; x still holds x_k at that point.
+    int enqueue_norm(int np, int dslot) {  // sqrt of the global sum of np partials at stat.p -> ds[dslot]
+        if (comm) {
+            HG_TRY(hg_k_reduce(ctx, stat.p, np, 1, ds + 33, false, nullptr, false));
+            HG_TRY(hg_comm_allreduce(comm, ds + 33, 1, st));
+            return hg_k_reduce(ctx, ds + 33, 1, 1, ds + dslot, false, nullptr, true);
+        }
+        return hg_k_reduce(ctx, stat.p, np, 1, ds + dslot, false, nullptr, true);
+    }
+    int residual_enqueue(const double* x, double* r_out, int dslot) {  // ||b - A x|| -> ds[dslot]
+        int np = 0;
+        HG_TRY(apply_A(x, r_out, -1.0, b.p, 1.0, nullptr, true, 0, &np));
+        return enqueue_norm(np, dslot);
+    }
+    int hist_copy(int k) {  // ds[20..23) -> ring slot of iteration k
+        HG_CUDA(cudaMemcpyAsync(hs + 40 + (k & 1) * 4, ds + 20, 24, cudaMemcpyDeviceToHost, st));
+        return HG_OK;
+    }
+    const double* hist(int k) const { return hs + 40 + (k & 1) * 4; }  // {err, res, ar} of iteration k
+
     // out(m) = alpha*A*v + g1*z1, v an n-slice; optional stat partials at stat.p (+offset)
     int apply_A(const double* v, double* out, double alpha, const double* z1, double g1, const double* ref,
                 bool want_stat, int stat_off, int* np) {
@@ -221,13 +245,24 @@ int hybrid_lsqr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
         extras->aux[0] = alpha_aug;
         extras->aux[maxit + 1] = beta_aug;
     }
-    int k;
+    int k, pending = 0;
+    bool stopped = false;
     for (k = 1; k <= maxit; ++k) {
         // u_hat = A_aug*v - alpha*u                               (:22)
         int np1 = 0, np2 = 0;
         HG_TRY(g.apply_A(v, t1, 1.0, u1, -alpha_aug, nullptr, true, 0, &np1));
         HG_TRY(hg_k_axpby(ctx, nl, sl, v, -alpha_aug, u2, t2, nullptr, g.stat.p + np1, &np2));
         HG_TRY(g.norm_from_stat(np1 + np2, 5, &beta_aug));  // :23
+        if (k > 1) {  // histories of iteration k-1 have landed: stop rule of that iteration (:45, strict)
+            error_norm[k - 2] = g.hist(k - 1)[0] / g.norm_xt;
+            residual_norm[k - 2] = g.hist(k - 1)[1] / g.norm_b;
+            pending = 0;
+            if (residual_norm[k - 2] < tol) {
+                k = k - 1;
+                stopped = true;
+                break;
+            }
+        }
         HG_TRY(hg_k_scale_div(ctx, t1, m, g.ds + 5));       // :24
         HG_TRY(hg_k_scale_div(ctx, t2, nl, g.ds + 5));
         swap_ptr(u1, t1);
@@ -247,19 +282,22 @@ int hybrid_lsqr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
         phi_bar = s * phi_bar;
         // x, w updates + error                                   (:39-42)
         HG_TRY(hg_k_lsqr_update(ctx, nl, dx, w, v, phi / rho, theta / rho, g.xt.p, g.stat.p, &np));
-        double en = 0, rn = 0;
-        HG_TRY(g.norm_from_stat(np, 7, &en));
-        HG_TRY(g.residual(dx, nullptr, &rn));  // :43
-        error_norm[k - 1] = en / g.norm_xt;
-        residual_norm[k - 1] = rn / g.norm_b;
+        HG_TRY(g.enqueue_norm(np, 20));               // :42
+        HG_TRY(g.residual_enqueue(dx, nullptr, 21));  // :43
+        HG_TRY(g.hist_copy(k));
+        pending = k;
         if (extras && extras->aux) {
             extras->aux[k] = alpha_aug;
             extras->aux[maxit + 1 + k] = beta_aug;
         }
         if (extras && extras->X_hist) HG_TRY(g.fetch_x(dx, extras->X_hist + (size_t)(k - 1) * n));
-        if (residual_norm[k - 1] < tol) break;  // :45 strict
     }
-    if (k > maxit) k = maxit;
+    if (!stopped) k = maxit;
+    if (pending) {  // the last iteration's histories
+        HG_CUDA(cudaStreamSynchronize(st));
+        error_norm[pending - 1] = g.hist(pending)[0] / g.norm_xt;
+        residual_norm[pending - 1] = g.hist(pending)[1] / g.norm_b;
+    }
     *niters = k;
     return g.fetch_x(dx, x);
 }
@@ -296,14 +334,34 @@ int hybrid_lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
     HG_TRY(g.norm_from_stat(np, 6, &alpha1));
     HG_TRY(hg_k_scale_div(ctx, V, nl, g.ds + 6));  // :15-16
     for (int i = 0; i < maxit; ++i) error_norm[i] = residual_norm[i] = 0.0;
-    std::vector<double> T, LHS, RHS, y;
-    int k;
+    std::vector<double> T, LHS, RHS;
+    struct PinY {
+        double* p = nullptr;
+        ~PinY() { hg_hfree(p); }
+    } hy;
+    if (hg_hmalloc_cur((void**)&hy.p, (size_t)2 * maxit * sizeof(double)) != cudaSuccess) {
+        hg_set_error("hybrid_lsmr: pinned allocation failed");
+        return HG_ERR_NOMEM;
+    }
+    int k, pending = 0;
+    bool stopped = false;
     for (k = 1; k <= maxit; ++k) {
         double* v = V + (size_t)(k - 1) * ldv;
         Bk[(size_t)(k - 1) * ldb + (k - 1)] = alpha1;  // :23
         double beta_k = 0;
         HG_TRY(g.apply_A(v, t, 1.0, u, -alpha1, nullptr, true, 0, &np));  // :24
         HG_TRY(g.norm_from_stat(np, 5, &beta_k));
+        if (k > 1) {  // histories of iteration k-1 have landed: its stop rule (:50)
+            error_norm[k - 2] = g.hist(k - 1)[0] / g.norm_xt;
+            residual_norm[k - 2] = g.hist(k - 1)[1] / g.norm_b;
+            pending = 0;
+            if (residual_norm[k - 2] <= tol) {
+                Bk[(size_t)(k - 1) * ldb + (k - 1)] = 0.0;  // entries the reference never reached
+                k = k - 1;
+                stopped = true;
+                break;
+            }
+        }
         HG_TRY(hg_k_scale_div(ctx, t, m, g.ds + 5));  // :26
         swap_ptr(u, t);
         Bk[(size_t)(k - 1) * ldb + k] = beta_k;  // :27
@@ -340,21 +398,23 @@ int hybrid_lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
         for (int i = 0; i < k; ++i) LHS[(size_t)i * k + i] += lambda;
         RHS.assign(k, 0.0);
         for (int i = 0; i < k; ++i) RHS[i] = Bk[0] * beta1 * T[i];  // B_k(1,1)*beta1*(T*e1)
-        y.assign(k, 0.0);
-        hgd::solve_square(k, LHS.data(), k, RHS.data(), y.data());
-        HG_CUDA(cudaMemcpyAsync(by.p, y.data(), (size_t)k * 8, cudaMemcpyHostToDevice, st));
-        HG_CUDA(cudaStreamSynchronize(st));  // y is pageable host memory
+        double* yk = hy.p + (size_t)(k & 1) * maxit;  // pinned, two slots: no wait for the upload
+        hgd::solve_square(k, LHS.data(), k, RHS.data(), yk);
+        HG_CUDA(cudaMemcpyAsync(by.p, yk, (size_t)k * 8, cudaMemcpyHostToDevice, st));
         // x = V(:,1:k)*yk + error                                 (:45,47)
         HG_TRY(hg_k_lincomb(ctx, V, ldv, nl, k, by.p, 1.0, nullptr, dx, g.xt.p, g.stat.p, &np));
-        double en = 0, rn = 0;
-        HG_TRY(g.norm_from_stat(np, 7, &en));
-        HG_TRY(g.residual(dx, nullptr, &rn));  // :48
-        error_norm[k - 1] = en / g.norm_xt;
-        residual_norm[k - 1] = rn / g.norm_b;
+        HG_TRY(g.enqueue_norm(np, 20));
+        HG_TRY(g.residual_enqueue(dx, nullptr, 21));  // :48
+        HG_TRY(g.hist_copy(k));
+        pending = k;
         if (extras && extras->X_hist) HG_TRY(g.fetch_x(dx, extras->X_hist + (size_t)(k - 1) * n));
-        if (residual_norm[k - 1] <= tol) break;  // :50
     }
-    if (k > maxit) k = maxit;
+    if (!stopped) k = maxit;
+    if (pending) {
+        HG_CUDA(cudaStreamSynchronize(st));
+        error_norm[pending - 1] = g.hist(pending)[0] / g.norm_xt;
+        residual_norm[pending - 1] = g.hist(pending)[1] / g.norm_b;
+    }
     *niters = k;
     if (extras && extras->aux)
         for (int j = 0; j < maxit; ++j) {
@@ -394,10 +454,14 @@ int lsqr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* A
     HG_CUDA(cudaMemcpyAsync(w, v, (size_t)nl * 8, cudaMemcpyDeviceToDevice, st));
     double phi_bar = beta, rho_bar = alpha;
     for (int i = 0; i < maxit; ++i) error_norm[i] = residual_norm[i] = 0.0;
-    int k;
+    int k, pending = 0;
     for (k = 1; k <= maxit; ++k) {
         HG_TRY(g.apply_A(v, t, 1.0, u, -alpha, nullptr, true, 0, &np));  // :22
         HG_TRY(g.norm_from_stat(np, 5, &beta));
+        if (pending) {  // error norm of the previous iteration
+            error_norm[pending - 1] = g.hist(pending)[0] / g.norm_xt;
+            pending = 0;
+        }
         HG_TRY(hg_k_scale_div(ctx, t, m, g.ds + 5));
         swap_ptr(u, t);
         HG_TRY(g.apply_At(u, t3, v, -beta, nullptr, 0.0, true, &np));  // :26
@@ -412,15 +476,19 @@ int lsqr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* A
         const double phi = c * phi_bar;
         phi_bar = s * phi_bar;
         HG_TRY(hg_k_lsqr_update(ctx, nl, dx, w, v, phi / rho, theta / rho, g.xt.p, g.stat.p, &np));  // :40-41
-        double en = 0;
-        HG_TRY(g.norm_from_stat(np, 7, &en));
-        error_norm[k - 1] = en / g.norm_xt;                    // :43
+        HG_TRY(g.enqueue_norm(np, 20));  // :43 — read after the next synchronisation
+        HG_TRY(g.hist_copy(k));
+        pending = k;
         residual_norm[k - 1] = std::fabs(phi_bar) / g.norm_b;  // :44
         if (extras && extras->X_hist) HG_TRY(g.fetch_x(dx, extras->X_hist + (size_t)(k - 1) * n));
         if (residual_norm[k - 1] <= tol) break;  // :46
     }
     if (k > maxit) k = maxit;
     *niters = k;
+    if (pending) {
+        HG_CUDA(cudaStreamSynchronize(st));
+        error_norm[pending - 1] = g.hist(pending)[0] / g.norm_xt;
+    }
     double rn = 0;
     HG_TRY(g.residual(dx, nullptr, &rn));
     residual_norm[k - 1] = rn / g.norm_b;  // :52
@@ -467,10 +535,26 @@ int lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* A
         res_hist[i] = 0.0;
         ar_hist[i] = 0.0;
     }
-    int k;
+    int k, pending = 0;
+    bool stopped = false;
+    auto consume = [&](int j) {  // histories of iteration j from the ring (:70-74)
+        const double en = g.hist(j)[0], rn = g.hist(j)[1], arn = g.hist(j)[2];
+        res_hist[j - 1] = rn / (g.norm_b + eps);
+        ar_hist[j - 1] = arn / (normA * std::max(rn, eps));
+        if (g.have_xt) err_hist[j - 1] = en / g.norm_xt;
+    };
     for (k = 1; k <= maxit; ++k) {
         HG_TRY(g.apply_A(v, t, 1.0, u, -alpha, nullptr, true, 0, &np));  // :34
         HG_TRY(g.norm_from_stat(np, 5, &beta));
+        if (k > 1) {  // histories of iteration k-1 have landed: its stop rule (:76, strict)
+            consume(k - 1);
+            pending = 0;
+            if (res_hist[k - 2] < tol) {
+                k = k - 1;
+                stopped = true;
+                break;
+            }
+        }
         if (beta > 0) HG_TRY(hg_k_scale_div(ctx, t, m, g.ds + 5));  // :36
         swap_ptr(u, t);
         HG_TRY(g.apply_At(u, t3, v, -beta, nullptr, 0.0, true, &np));  // :38
@@ -494,18 +578,19 @@ int lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* A
         const double c0 = (k == 1) ? 0.0 : (thetabar * rho) / (rhoold * rhobarold);  // :64
         HG_TRY(hg_k_lsmr_update(ctx, nl, dx, h, hbar, v, k == 1 ? 1 : 0, c0, zeta / (rho * rhobar),
                                 thetanew / rho, g.have_xt ? g.xt.p : nullptr, g.stat.p, &np));  // :61-67
-        double en = 0, rn = 0, arn = 0;
-        HG_TRY(g.norm_from_stat(np, 7, &en));
-        HG_TRY(g.residual(dx, r, &rn));                                    // :69
+        HG_TRY(g.enqueue_norm(np, 20));
+        HG_TRY(g.residual_enqueue(dx, r, 21));                                  // :69
         HG_TRY(g.apply_At(r, nullptr, nullptr, 0.0, nullptr, 0.0, true, &np));  // norm(A.'*r)  :71
-        HG_TRY(g.norm_from_stat(np, 8, &arn));
-        res_hist[k - 1] = rn / (g.norm_b + eps);              // :70
-        ar_hist[k - 1] = arn / (normA * std::max(rn, eps));   // :71
-        if (g.have_xt) err_hist[k - 1] = en / g.norm_xt;      // :72-74
+        HG_TRY(g.enqueue_norm(np, 22));
+        HG_TRY(g.hist_copy(k));
+        pending = k;
         if (extras && extras->X_hist) HG_TRY(g.fetch_x(dx, extras->X_hist + (size_t)(k - 1) * n));
-        if (res_hist[k - 1] < tol) break;  // :76
     }
-    if (k > maxit) k = maxit;
+    if (!stopped) k = maxit;
+    if (pending) {
+        HG_CUDA(cudaStreamSynchronize(st));
+        consume(pending);
+    }
     *iters = k;
     return g.fetch_x(dx, x);
 }
