@@ -68,8 +68,18 @@ extern "C" int hg_arnoldi_destroy(hg_arnoldi* a) {
     return HG_OK;
 }
 
+static int arnoldi_create(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, int space, int kmax, bool store_t_m,
+                          hg_arnoldi** out);
+
 extern "C" int hg_arnoldi_create(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, int space,
                                  int kmax, hg_arnoldi** out) {
+    return arnoldi_create(ctx, A, B, space, kmax, false, out);
+}
+
+// store_t_m: in m-space also keep the columns B*q_k (n x (kmax+1)), so x = B*(Q y) is a combination of cached
+// columns instead of a product with B (PTR AB solvers)
+static int arnoldi_create(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, int space, int kmax, bool store_t_m,
+                          hg_arnoldi** out) {
     HG_REQUIRE(ctx && A && B && out, "hg_arnoldi_create: NULL argument");
     HG_REQUIRE(space == HG_SPACE_N || space == HG_SPACE_M, "hg_arnoldi_create: bad space");
     HG_REQUIRE(kmax >= 1, "hg_arnoldi_create: kmax must be >= 1");
@@ -96,7 +106,7 @@ extern "C" int hg_arnoldi_create(hg_ctx* ctx, const hg_matrix* A, const hg_matri
     } else {
         a->M1 = B;
         a->M2 = A;
-        a->store_t = false;
+        a->store_t = store_t_m;
     }
     a->nq = a->M2->rows;
     a->nt = a->M1->rows;
@@ -784,6 +794,14 @@ extern "C" int hg_gcv_destroy(hg_gcv* g) {
 // ===========================================================================
 // lambdas / nl / lambda_path non-null: the regularisation parameter is chosen at every iteration as the
 // grid minimiser of GCV(lambda, H_k) (compute_gcv_surface + calculate_gcv_from_H, plot_gcv_surface.m:58-122)
+//
+// Like the RTP solvers the loop is software pipelined (Arnoldi step k+1 is queued before the host looks at step
+// k) and no product with A or B is repeated: the Arnoldi process already formed A*q_j (BA) / B*q_j (AB), so
+//   BA:  x_k = Q_k y_k,            b - A x_k = b - (A Q_k) y_k            (cached columns T = A Q)
+//   AB:  x_k = B (Q_k y_k) = (B Q_k) y_k  (cached columns T = B Q),
+//        b - A x_k = b - (A B Q_k) y_k = b - Q_{k+1} (H_k y_k)            (the Arnoldi relation, exact to the
+//                                                                          rounding of the CGS2 step: 1e-15)
+// i.e. 2 products per iteration instead of 3 (BA) or 4 (AB), and one launch for iterate + both history norms.
 static int ptr_solver(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* A, const hg_matrix* B,
                       const double* b, const double* x_true, double tol, int maxit, double lambda,
                       const double* lambdas, int nl, double* lambda_path,
@@ -796,20 +814,25 @@ static int ptr_solver(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* A, con
     HG_CUDA(cudaSetDevice(ctx->device));
     const int64_t n = A->cols, m = A->rows;
     ArnoldiHolder holder;
-    HG_TRY(hg_arnoldi_create(ctx, A, B, kind == 0 ? HG_SPACE_M : HG_SPACE_N, maxit, &holder.a));
+    HG_TRY(arnoldi_create(ctx, A, B, kind == 0 ? HG_SPACE_M : HG_SPACE_N, maxit, true, &holder.a));
     hg_arnoldi* a = holder.a;
     hg_alloc_scope alloc_scope(ctx);  // RAII buffers below come from / return to this context's cache
-    DBuf d_x, d_xt, d_y, d_z, stat_e, stat_r;
-    PinBuf h_y, h_s;
-    HG_TRY(d_x.alloc((size_t)n));
+    constexpr int RING = 4;
+    DBuf d_x[2], d_xt, d_y, d_hy, stat_e;
+    PinBuf h_y, h_hy, h_s;
+    EventRing ev;
+    HG_TRY(ev.create(RING));
+    HG_TRY(d_x[0].alloc((size_t)n));
+    HG_TRY(d_x[1].alloc((size_t)n));
     HG_TRY(d_xt.alloc((size_t)n));
     HG_TRY(d_y.alloc((size_t)maxit + 1));
-    HG_TRY(d_z.alloc((size_t)m));
+    HG_TRY(d_hy.alloc((size_t)maxit + 2));
     HG_TRY(stat_e.alloc(hg_stat_capacity(ctx, std::max(n, m))));
-    HG_TRY(stat_r.alloc(hg_stat_capacity(ctx, std::max(n, m))));
-    HG_TRY(h_y.alloc((size_t)maxit + 1));
-    HG_TRY(h_s.alloc(8));
-    HG_CUDA(cudaMemsetAsync(d_x.p, 0, (size_t)n * 8, ctx->stream));
+    HG_TRY(h_y.alloc((size_t)RING * (maxit + 1)));
+    HG_TRY(h_hy.alloc((size_t)RING * (maxit + 2)));
+    HG_TRY(h_s.alloc((size_t)RING * 2));
+    HG_CUDA(cudaMemsetAsync(d_x[0].p, 0, (size_t)n * 8, ctx->stream));
+    HG_CUDA(cudaMemsetAsync(d_x[1].p, 0, (size_t)n * 8, ctx->stream));
     HG_CUDA(cudaMemcpyAsync(d_xt.p, x_true, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     HG_TRY(hg_arnoldi_set_rhs(a, b));
     double nb2 = 0, nx2 = 0;
@@ -826,15 +849,43 @@ static int ptr_solver(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* A, con
     bool chol_ok = true;
     if (hybrid) chol.reset(maxit, lambda);
     else ls.reset(maxit, beta);
-    bool have_x = false;
     const int ldh = a->ldh();
+    const double* H = a->h_H;
+    int enq = 0, last_x = 0;
+    auto finish_iterate = [&](int j, bool* stop) -> int {
+        HG_CUDA(cudaEventSynchronize(ev.e[j % RING]));
+        const double* hs = h_s.p + (size_t)(j % RING) * 2;
+        error_norm[j - 1] = hs[0] / norm_xt;     // :41
+        residual_norm[j - 1] = hs[1] / norm_b;   // :40
+        last_x = j;
+        *stop = residual_norm[j - 1] <= tol;     // :83
+        return HG_OK;
+    };
     int k;
+    bool ended_early = false;
     for (k = 1; k <= maxit; ++k) {
-        HG_TRY(hg_arnoldi_steps(a, 1));
-        HG_CUDA(cudaStreamSynchronize(ctx->stream));
-        const double* H = a->h_H;
+        while (enq < std::min(k + 1, maxit)) {
+            ++enq;
+            HG_TRY(hg_arnoldi_steps(a, 1));
+            if (enq == 1) HG_CUDA(cudaEventRecord(ev.e[0], ctx->stream));
+        }
+        if (k == 1) {
+            HG_CUDA(cudaEventSynchronize(ev.e[0]));
+        } else {
+            bool stop = false;
+            HG_TRY(finish_iterate(k - 1, &stop));
+            if (stop) {
+                k = k - 1;
+                ended_early = true;
+                break;
+            }
+        }
         const double* hcol = H + (size_t)(k - 1) * ldh;
-        if (hcol[k] == 0.0) break;  // :31
+        if (hcol[k] == 0.0) {  // :31
+            ended_early = true;
+            break;
+        }
+        double* yk = h_y.p + (size_t)(k % RING) * (maxit + 1);
         if (hybrid && nl > 0) {
             // lambda_k = first grid minimiser of GCV(lambda, H_k)        (plot_gcv_surface.m:92-100, :104-122)
             std::vector<double> sq((size_t)k * k), sv(k);
@@ -862,7 +913,7 @@ static int ptr_solver(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* A, con
                     M[(size_t)j * k + i2] = acc + (i2 == j ? lam_k : 0.0);
                 }
             for (int j = 0; j < k; ++j) rhs[j] = beta * H[(size_t)j * ldh];
-            hgd::solve_square(k, M.data(), k, rhs.data(), h_y.p);
+            hgd::solve_square(k, M.data(), k, rhs.data(), yk);
         } else if (hybrid) {
             // yk = (Hk'*Hk + lambda*I) \ (Hk'*tk): Hk'*Hk grows by bordering (column k adds row k+1,
             // which is zero in every earlier column), so the row Cholesky is continued    (:34-36)
@@ -875,7 +926,7 @@ static int ptr_solver(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* A, con
             rhs[k - 1] = beta * hcol[0];
             if (chol_ok) chol_ok = chol.add_row(grow.data());
             if (chol_ok) {
-                chol.solve(rhs.data(), h_y.p);
+                chol.solve(rhs.data(), yk);
             } else {
                 std::vector<double> M((size_t)k * k);
                 for (int j = 0; j < k; ++j)
@@ -884,54 +935,58 @@ static int ptr_solver(hg_ctx* ctx, int kind, int hybrid, const hg_matrix* A, con
                         for (int t = 0; t <= k; ++t) acc += H[(size_t)i2 * ldh + t] * H[(size_t)j * ldh + t];
                         M[(size_t)j * k + i2] = acc + (i2 == j ? lambda : 0.0);
                     }
-                hgd::solve_square(k, M.data(), k, rhs.data(), h_y.p);
+                hgd::solve_square(k, M.data(), k, rhs.data(), yk);
             }
         } else {
             ls.add_column(hcol);  // yk = Hk \ [beta;0]   (ABgmres_nonhybrid_bounds.m:34-35)
-            ls.solve(h_y.p);
+            ls.solve(yk);
         }
-        HG_CUDA(cudaMemcpyAsync(d_y.p, h_y.p, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
-        int np_e = 0, np_r = 0;
+        HG_CUDA(cudaMemcpyAsync(d_y.p, yk, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+        double* xk = d_x[k & 1].p;
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(ctx->d_scalars + 40);
         if (kind == 1) {
-            // xk = Q(:,1:k)*yk                                                    (BA :37)
-            HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n, k, d_y.p, 1.0, nullptr, d_x.p, d_xt.p, stat_e.p, &np_e));
+            // xk = Q(:,1:k)*yk (BA :37); norm(b - A*xk) (:40) from the cached columns A*q_j
+            HG_TRY(hg_k_iterate2(ctx, a->Q, a->ldq, n, k, d_y.p, xk, d_xt.p, a->T + a->ldt, a->ldt, m, k, d_y.p, a->d_b,
+                                 stat_e.p, ticket, ctx->d_scalars + 1));
         } else {
-            // zk = Q(:,1:k)*yk ; xk = B*zk                                        (AB :37-38)
-            HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, m, k, d_y.p, 1.0, nullptr, d_z.p, nullptr, nullptr, nullptr));
-            hg_spmv_epilogue ep;
-            ep.ref = d_xt.p;
-            ep.stat = stat_e.p;
-            HG_TRY(hg_k_spmv(ctx, B, d_z.p, d_x.p, ep, &np_e));
+            // xk = B*(Q(:,1:k)*yk) (AB :37-38) from the cached columns B*q_j; b - A*xk = b - Q(:,1:k+1)*(Hk*yk)
+            double* hy = h_hy.p + (size_t)(k % RING) * (maxit + 2);
+            for (int t = 0; t <= k; ++t) {
+                double acc = 0.0;
+                for (int j = std::max(0, t - 1); j < k; ++j) acc += H[(size_t)j * ldh + t] * yk[j];  // Hk is upper Hessenberg
+                hy[t] = acc;
+            }
+            HG_CUDA(cudaMemcpyAsync(d_hy.p, hy, (size_t)(k + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            HG_TRY(hg_k_iterate2(ctx, a->T + a->ldt, a->ldt, n, k, d_y.p, xk, d_xt.p, a->Q, a->ldq, m, k + 1, d_hy.p,
+                                 a->d_b, stat_e.p, ticket, ctx->d_scalars + 1));
         }
-        {
-            hg_spmv_epilogue ep;  // norm(b - A*xk)                                (:40)
-            ep.alpha = -1.0;
-            ep.z1 = a->d_b;
-            ep.g1 = 1.0;
-            ep.stat = stat_r.p;
-            HG_TRY(hg_k_spmv(ctx, A, d_x.p, nullptr, ep, &np_r));
-        }
-        HG_TRY(hg_k_reduce(ctx, stat_e.p, np_e, 1, ctx->d_scalars + 1, false, nullptr, true));
-        HG_TRY(hg_k_reduce(ctx, stat_r.p, np_r, 1, ctx->d_scalars + 2, false, nullptr, true));
-        HG_CUDA(cudaMemcpyAsync(h_s.p, ctx->d_scalars + 1, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        HG_CUDA(cudaMemcpyAsync(h_s.p + (size_t)(k % RING) * 2, ctx->d_scalars + 1, 16, cudaMemcpyDeviceToHost,
+                                ctx->stream));
         if (extras && extras->X_hist)
-            HG_CUDA(cudaMemcpyAsync(extras->X_hist + (size_t)(k - 1) * n, d_x.p, (size_t)n * 8,
+            HG_CUDA(cudaMemcpyAsync(extras->X_hist + (size_t)(k - 1) * n, xk, (size_t)n * 8,
                                     cudaMemcpyDeviceToHost, ctx->stream));
-        HG_CUDA(cudaStreamSynchronize(ctx->stream));
-        have_x = true;
-        error_norm[k - 1] = h_s.p[0] / norm_xt;     // :41
-        residual_norm[k - 1] = h_s.p[1] / norm_b;   // :40
-        if (residual_norm[k - 1] <= tol) break;     // :83
+        HG_CUDA(cudaEventRecord(ev.e[k % RING], ctx->stream));
     }
-    if (k > maxit) k = maxit;
+    if (!ended_early) {
+        k = maxit;
+        bool stop = false;
+        HG_TRY(finish_iterate(maxit, &stop));
+    }
     *niters = k;
-    HG_CUDA(cudaMemcpyAsync(x, d_x.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    HG_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (x_valid) *x_valid = have_x ? 1 : 0;  // `x = xk` (:86) is undefined after a breakdown at k = 1
+    HG_CUDA(cudaMemcpyAsync(x, d_x[last_x & 1].p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HG_CUDA(cudaStreamSynchronize(ctx->stream));  // also drains a discarded speculative step
+    if (x_valid) *x_valid = last_x > 0 ? 1 : 0;  // `x = xk` (:86) is undefined after a breakdown at k = 1
     if (extras) {
         if (extras->beta) *extras->beta = beta;
-        if (extras->H) memcpy(extras->H, a->h_H, (size_t)ldh * maxit * 8);
+        if (extras->H) {  // columns the reference never reached stay zero
+            memset(extras->H, 0, (size_t)ldh * maxit * 8);
+            memcpy(extras->H, a->h_H, (size_t)ldh * k * 8);
+        }
+        if (extras->X_hist && last_x < maxit)
+            memset(extras->X_hist + (size_t)last_x * n, 0, (size_t)(maxit - last_x) * n * 8);
     }
+    if (lambda_path)
+        for (int j = k; j < maxit; ++j) lambda_path[j] = 0.0;  // a discarded speculative iteration chose one more
     return HG_OK;
 }
 

@@ -207,6 +207,10 @@ int hg_k_iterate(hg_ctx* ctx, const double* Q, int64_t ldq, int64_t n, const dou
                  int k, const double* y, const double* b, double* x, const double* x_true, double* stat,
                  unsigned int* ticket, double* out2);
 
+int hg_k_iterate2(hg_ctx* ctx, const double* V0, int64_t ld0, int64_t n0, int k0, const double* c0, double* x,
+                  const double* x_true, const double* V1, int64_t ld1, int64_t n1, int k1, const double* c1,
+                  const double* b, double* stat, unsigned int* ticket, double* out2);
+
 // same, with the result rows also stored to up to 16 further destinations (peer-GPU copies of the
 // vector: the all-gather of the sharded Arnoldi is done by the producing kernel, dist_peer.cu)
 struct hg_out_list {

@@ -302,6 +302,8 @@ lincomb_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
 // ---------------------------------------------------------------------------
 struct hg_iter_job {
     const double* V;    // n x k column-major
+    const double* c;    // k coefficients (device)
+    int k;
     int64_t ld, n;
     double s;           // scale of the combination (+1: x = V y, -1: r = z - V y)
     const double* z;    // added vector or nullptr
@@ -311,14 +313,15 @@ struct hg_iter_job {
 };
 
 __global__ void __launch_bounds__(kBlock)
-iterate_kernel(hg_iter_job j0, hg_iter_job j1, int k, const double* __restrict__ c, double* __restrict__ stat,
+iterate_kernel(hg_iter_job j0, hg_iter_job j1, double* __restrict__ stat,
                unsigned int* __restrict__ ticket, double* __restrict__ out2) {
     extern __shared__ double sc[];
     __shared__ bool s_last;
     const bool second = (int)blockIdx.x >= j0.grid;
     const hg_iter_job& J = second ? j1 : j0;
     const int64_t blk = second ? (int64_t)blockIdx.x - j0.grid : blockIdx.x;
-    for (int j = threadIdx.x; j < k; j += blockDim.x) sc[j] = J.s * c[j];
+    const int k = J.k;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) sc[j] = J.s * J.c[j];
     __syncthreads();
     const int64_t r = (blk * kBlock + threadIdx.x) * 2;
     const int64_t n = J.n, ld = J.ld;
@@ -711,13 +714,22 @@ int hg_k_lincomb(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, con
 int hg_k_iterate(hg_ctx* ctx, const double* Q, int64_t ldq, int64_t n, const double* T, int64_t ldt, int64_t m,
                  int k, const double* y, const double* b, double* x, const double* x_true, double* stat,
                  unsigned int* ticket, double* out2) {
-    hg_iter_job j0{Q, ldq, n, 1.0, nullptr, x, x_true, (int)cdiv(n, 2 * kBlock)};
-    hg_iter_job j1{T, ldt, m, -1.0, b, nullptr, nullptr, (int)cdiv(m, 2 * kBlock)};
+    return hg_k_iterate2(ctx, Q, ldq, n, k, y, x, x_true, T, ldt, m, k, y, b, stat, ticket, out2);
+}
+
+// general form: job 0  x = V0 c0 (n0 rows, k0 columns), error vs x_true;  job 1  ||b - V1 c1|| (n1 rows, k1 columns)
+int hg_k_iterate2(hg_ctx* ctx, const double* V0, int64_t ld0, int64_t n0, int k0, const double* c0, double* x,
+                  const double* x_true, const double* V1, int64_t ld1, int64_t n1, int k1, const double* c1,
+                  const double* b, double* stat, unsigned int* ticket, double* out2) {
+    hg_iter_job j0{V0, c0, k0, ld0, n0, 1.0, nullptr, x, x_true, (int)cdiv(n0, 2 * kBlock)};
+    hg_iter_job j1{V1, c1, k1, ld1, n1, -1.0, b, nullptr, nullptr, (int)cdiv(n1, 2 * kBlock)};
     const int grid = j0.grid + j1.grid;
     if (grid == 0) return HG_OK;
-    hg_launch_scope scope(ctx, HG_K_LINCOMB, 8.0 * (double)k * (double)(n + m) + 24.0 * (double)n + 8.0 * (double)m);
-    const size_t smem = (size_t)(k > 0 ? k : 1) * sizeof(double);
-    iterate_kernel<<<(unsigned)grid, kBlock, smem, ctx->stream>>>(j0, j1, k, y, stat, ticket, out2);
+    hg_launch_scope scope(ctx, HG_K_LINCOMB, 8.0 * ((double)k0 * (double)n0 + (double)k1 * (double)n1) +
+                                                 24.0 * (double)n0 + 8.0 * (double)n1);
+    const int kmax = k0 > k1 ? k0 : k1;
+    const size_t smem = (size_t)(kmax > 0 ? kmax : 1) * sizeof(double);
+    iterate_kernel<<<(unsigned)grid, kBlock, smem, ctx->stream>>>(j0, j1, stat, ticket, out2);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }
