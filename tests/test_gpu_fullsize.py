@@ -163,6 +163,51 @@ def test_config3_512_solver_equivalences(hg, ctx):
     ctx.trim()
 
 
+def test_config3_512_solvers_vs_oracle(hg, ctx):
+    """BASELINE configs[2] at its real size against the ORACLE (not only device-vs-device identities): 512^2
+    parallel beam, 180 views, matched B = A' (the run_equivalence_plots.m:3-22 shape), 60 M non-zeros —
+    hybrid LSQR and hybrid LSMR against the NumPy restatement (pinned to the executed reference source) and
+    hybrid AB-GMRES (RTP) against the OpenMP C oracle: histories and every iterate <= 1e-8 over the first 8
+    iterations (Golub-Kahan without reorthogonalisation is not reproducible much further, see
+    test_gkb_solvers_vs_oracle), identical stopping iteration."""
+    import scipy.sparse as sp
+    import oracle
+    from oracle import cport
+    from hybrid_gmres_b200.ct import ct_projector, shepp_logan
+    N, K, lam = 512, 8, 1e-2
+    angles = np.arange(180) * 1.0
+    p = int(round(math.sqrt(2.0) * N))
+    dA = ct_projector(N, angles, p, "parallel", ctx=ctx)
+    dAt = dA.transpose()
+    x_true = shepp_logan(N)
+    b = dA.matvec(x_true)
+    e = np.random.default_rng(0).standard_normal(b.shape[0])
+    b = b + 0.01 * np.linalg.norm(b) * e / np.linalg.norm(e)
+    A = sp.csr_matrix(tuple(reversed(dA.download())), shape=dA.shape)
+    At = sp.csr_matrix(tuple(reversed(dAt.download())), shape=dAt.shape)
+    assert abs(At - A.T.tocsr()).max() == 0  # the device transposition is exact
+
+    def rel_cols(X, Y):
+        return max(np.linalg.norm(X[:, i] - Y[:, i]) / np.linalg.norm(Y[:, i]) for i in range(Y.shape[1]))
+
+    for f_dev, f_orc in ((hg.hybrid_lsqr_solver, oracle.hybrid_lsqr_solver), (hg.hybrid_lsmr_solver, oracle.hybrid_lsmr_solver)):
+        exd, exo = {}, {}
+        x, err, res, it = f_dev(dA, b, x_true, 1e-6, K, lam, ctx=ctx, At=dAt, extras=exd)
+        xo, erro, reso, ito = f_orc(A, b, x_true, 1e-6, K, lam, extras=exo)
+        assert it == ito == K
+        assert np.max(np.abs(res - reso) / reso) < 1e-8 and np.max(np.abs(err - erro) / erro) < 1e-8, f_dev.__name__
+        assert rel_cols(exd["X"], exo["X"]) < 1e-8, f_dev.__name__
+    cport.use_all_cores()
+    exd, exo = {}, {}
+    x, err, res, it = hg.hybrid_ab_gmres_rtp(dA, dAt, b, x_true, 1e-6, 20, lam, ctx=ctx, extras=exd)
+    xo, erro, reso, ito = cport.hybrid_ab_gmres_rtp(A, At, b, x_true, 1e-6, 20, lam, "mgs", exo, want_X=True)
+    assert it == ito
+    assert np.max(np.abs(res - reso) / reso) < 1e-8 and np.max(np.abs(err - erro) / erro) < 1e-8
+    assert rel_cols(exd["X"], exo["X"]) < 1e-8
+    dA.close(), dAt.close()
+    ctx.trim()
+
+
 # ------------------------------------------------------------------------------------------------
 # BASELINE configs[3] at its real size: solver parity against the OpenMP C oracle
 # ------------------------------------------------------------------------------------------------
