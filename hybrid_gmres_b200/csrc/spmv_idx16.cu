@@ -192,16 +192,41 @@ spmv_sell16_split_kernel(int64_t rows, int64_t nslices, const int64_t* __restric
     double a[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) a[u] = 0.0;
-    for (int64_t i = s + (int64_t)part * (U * 32) + lane; i - lane < e; i += (int64_t)S * (U * 32)) {
-        const int b = __ldg(sbase + ((i - lane) >> 7));
-        int c[U];
-        double v[U];
+    // software pipelined like spmv_sell16_kernel: the (offset, value) loads of this warp's next batch are in
+    // flight while the gathers of the current one resolve (a warp has only a handful of batches here, so an
+    // un-pipelined loop exposes two dependent latencies per batch: ncu long-scoreboard 47 at 256^2)
+    constexpr int64_t STEP = (int64_t)S * (U * 32);
+    int64_t i = s + (int64_t)part * (U * 32) + lane;
+    bool ok = i - lane < e;  // whole groups: all U entries of a batch exist or none
+    int b = ok ? __ldg(sbase + ((i - lane) >> 7)) : 0;
+    int c[U];
+    double v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) c[u] = ld_stream(scol + i + u * 32);
+    for (int u = 0; u < U; ++u) c[u] = ok ? ld_stream(scol + i + u * 32) : 0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = ld_stream(sval + i + u * 32);
+    for (int u = 0; u < U; ++u) v[u] = ok ? ld_stream(sval + i + u * 32) : 0.0;
+    while (ok) {  // warp uniform
+        double xg[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) a[u] = fma(v[u], __ldg(x + b + c[u]), a[u]);
+        for (int u = 0; u < U; ++u) xg[u] = __ldg(x + b + c[u]);
+        const int64_t in = i + STEP;
+        const bool okn = in - lane < e;
+        int cn[U];
+        double vn[U];
+        const int bn = okn ? __ldg(sbase + ((in - lane) >> 7)) : 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) cn[u] = okn ? ld_stream(scol + in + u * 32) : 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) vn[u] = okn ? ld_stream(sval + in + u * 32) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            a[u] = fma(v[u], xg[u], a[u]);
+            c[u] = cn[u];
+            v[u] = vn[u];
+        }
+        b = bn;
+        i = in;
+        ok = okn;
     }
     s_part[warp][lane] = (a[0] + a[1]) + (a[2] + a[3]);
     __syncthreads();

@@ -38,7 +38,7 @@ def main():
         angles = np.arange(nv) * 2.0
         p = int(round(math.sqrt(2.0) * N))
         q = tile_permutation(N, 4)
-        for P in (1, 8):
+        for P in [int(v) for v in os.environ.get("SHARDS", "1,8").split(",")]:
             mine = np.arange(0, nv, P)
             A0 = hg.ct_projector(N, angles[mine], p, "fan", ctx=ctx)
             B0 = hg.ct_backprojector(N, angles[mine], p, "fan", ctx=ctx)
