@@ -113,9 +113,7 @@ static int arnoldi_create(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* B, i
     a->ldq = round_up(std::max<int64_t>(a->nq, 1), 32);
     a->ldt = round_up(std::max<int64_t>(a->nt, 1), 32);
     const int nslabs = hg_multidot_nslabs(ctx, std::max(a->nq, a->nt));
-    const size_t npart = (size_t)(kmax + 2) *
-                         (size_t)(std::max(std::max(nslabs, ctx->sm_count),
-                                           hg_update_dot_ntiles(std::max(a->nq, a->nt))) + 1);
+    const size_t npart = (size_t)(kmax + 2) * (size_t)(std::max(nslabs, ctx->sm_count) + 1);
     const size_t nstat = hg_stat_capacity(ctx, std::max(a->nq, a->nt));
     cudaError_t e = cudaSuccess;
     auto alloc = [&](double** p, size_t n) {
@@ -229,19 +227,14 @@ static int arnoldi_step(hg_arnoldi* a, int kk) {
     if (hg_cgs_fused_mode() == 2 && hg_cgs_staged_nparts(ctx, a->nq, kk) > 0) {
         // v -= Q h1 and h2 = Q' v in one pass over Q: the tile is staged in shared memory by cp.async
         HG_TRY(hg_k_cgs_mid_staged(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, a->w0, a->w1, a->partials, &ns));
-    } else if (hg_cgs_fused()) {
-        // v -= Q h1 and h2 = Q' v in one kernel: the second read of the Q tile is an L2 hit
-        HG_TRY(hg_k_update_dot(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, a->w0, a->w1, a->partials, &ns));
     } else {
-        // the updates sweep the rows backwards: they start on the part of Q the forward multi-dot
-        // sweep just left in L2, and leave the low rows there for the next forward sweep
         HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr,
-                                 nullptr, nullptr, nullptr, hg_cgs_alternate()));
+                                 nullptr, nullptr, nullptr));
         HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->nq, kk, a->w1, a->partials, &ns));
     }
     HG_TRY(hg_k_reduce(ctx, a->partials, ns, kk, Hcol, true, a->d_hcur, false));
     HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->nq, kk, a->d_hcur, -1.0, a->w1, qnext, nullptr,
-                             a->stat, &np, nullptr, hg_cgs_alternate()));
+                             a->stat, &np, nullptr));
     // H(k+1,k) = norm(v) ; Q(:,k+1) = v / H(k+1,k)       (:24,26)
     HG_TRY(hg_k_reduce(ctx, a->stat, np, 1, Hcol + kk, false, nullptr, true));
     HG_TRY(hg_k_scale_div(ctx, qnext, a->nq, Hcol + kk));

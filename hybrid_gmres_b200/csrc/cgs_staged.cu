@@ -1,7 +1,7 @@
 // CGS2 middle stage with the basis tile staged in shared memory:
 //     w1 = w0 - V h1      and      partials = V^T w1
 // in ONE pass over V (the separate update + multi-dot kernels read V twice: 32kn -> 24kn bytes per
-// Arnoldi step).  An earlier fused kernel (update_dot_kernel, profiles/r01_cgs_fusion.md) re-read
+// Arnoldi step).  An earlier fused kernel (removed; numbers in profiles/r01_cgs_fusion.md) re-read
 // the tile from L2 and stalled DRAM while it computed: 49 % DRAM utilisation, slower than the two
 // streaming kernels.  Here a persistent CTA per SM owns two ~100 KB stages: while the warps work on
 // the tile in one stage (phase A: V_tile h -> w1 tile; phase B: V_tile^T w1 tile, both from shared

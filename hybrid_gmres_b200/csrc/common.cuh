@@ -219,13 +219,7 @@ struct hg_out_list {
 };
 int hg_k_lincomb_push(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* c,
                       double s, const double* z, double* out, const double* ref, double* stat,
-                      int* nparts, const hg_out_list* extra, bool reverse = false);
-bool hg_cgs_alternate();  // option "cgs_alternate" (default off): CGS2 updates sweep the rows backwards
-
-// fused CGS2 middle stage: w1 = w0 - V h ; partials[j*ntiles + tile] = sum_tile V[:,j].*w1
-int hg_update_dot_ntiles(int64_t n);
-int hg_k_update_dot(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* h,
-                    const double* w0, double* w1, double* partials, int* ntiles);
+                      int* nparts, const hg_out_list* extra);
 
 // v[i] = v[i] / *d_div   (division, as `v / H(k+1,k)` in the reference)
 int hg_k_scale_div(hg_ctx* ctx, double* v, int64_t n, const double* d_div);
@@ -264,8 +258,7 @@ int hg_k_cgs2_step(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, c
                    double* qnext, double* Hcol, double* hcur, double* partials);
 
 // options (spmv_stream.cu)
-bool hg_cgs_fused();      // 1: L2-re-read fused kernel (update_dot_kernel)
-int hg_cgs_fused_mode();  // 0 separate kernels, 1 update_dot_kernel, 2 shared-memory-staged fused kernel
+int hg_cgs_fused_mode();  // 0 separate update / multi-dot kernels, 2 (default) shared-memory-staged one-pass kernel
 
 // streaming SpMV (spmv_stream.cu)
 bool hg_spmv_stream_eligible(const hg_matrix* m);

@@ -345,7 +345,7 @@ static int darnoldi_step(hg_darnoldi* a, int kk) {
             HG_TRY(hg_k_cgs_mid_staged(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, a->w0, a->w1, a->partials, &ns));
         } else {
             HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w0, a->w1, nullptr, nullptr, nullptr,
-                                     nullptr, hg_cgs_alternate()));
+                                     nullptr));
             HG_TRY(hg_k_multidot(ctx, a->Q, a->ldq, a->n_p, kk, a->w1, a->partials, &ns));
         }
         HG_TRY(hg_k_reduce_allreduce(c, a->partials, ns, kk, a->d_hcur, Hcol, true, false));  // H(1:k,k) = h1 + h2
@@ -354,8 +354,7 @@ static int darnoldi_step(hg_darnoldi* a, int kk) {
         a->qbuf ^= 1;
         hg_out_list push;
         hg_peer_push_list(c, a->qbuf, a->row0, &push);
-        HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w1, qnext, nullptr, a->stat, &np, &push,
-                                 hg_cgs_alternate()));
+        HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w1, qnext, nullptr, a->stat, &np, &push));
         HG_TRY(hg_k_reduce_allreduce(c, a->stat, np, 1, Hcol + kk, nullptr, false, true));     // H(k+1,k) = norm(v)
         HG_TRY(hg_k_scale2(c, hg_peer_qfull(c, a->qbuf), a->n_pad, qnext, a->n_p, Hcol + kk));  // q_{k+1} = v / H(k+1,k)
         HG_CUDA(cudaMemcpyAsync(a->h_H + (size_t)(kk - 1) * a->ldh(), Hcol, (size_t)(kk + 1) * 8,

@@ -227,13 +227,11 @@ __global__ void __launch_bounds__(kBlock)
 lincomb_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
                const double* __restrict__ c, double s, const double* __restrict__ z,
                double* __restrict__ out, const double* __restrict__ ref,
-               double* __restrict__ stat, hg_out_list extra, int reverse) {
+               double* __restrict__ stat, hg_out_list extra) {
     extern __shared__ double sc[];
     for (int j = threadIdx.x; j < k; j += blockDim.x) sc[j] = s * c[j];
     __syncthreads();
-    // reverse: walk the rows from the end, so a kernel that follows a forward sweep over the same
-    // basis (the CGS2 multi-dot) starts on the rows that sweep left in L2
-    const int64_t blk = reverse ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
+    const int64_t blk = blockIdx.x;
     const int64_t r = (blk * kBlock + threadIdx.x) * 2;
     double sq = 0.0;
     if (r + 1 < n) {
@@ -384,107 +382,6 @@ iterate_kernel(hg_iter_job j0, hg_iter_job j1, double* __restrict__ stat,
             __syncthreads();
         }
         if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch on this stream
-    }
-}
-
-// ---------------------------------------------------------------------------
-// CGS2 middle stage, fused:  w1 = w0 - V h1   and   partials = V^T w1   on a row tile.
-// A CTA owns kTileRows rows.  Phase A streams the tile of V from HBM (warps own columns,
-// lanes own row pairs, per-warp partial sums combined in a fixed order through shared
-// memory); phase B re-reads the same tile — 8*kTileRows*k bytes, which the 126 MB L2 still
-// holds because all resident CTAs together touch < 60 MB between the two reads — and forms
-// the second-pass coefficients.  V therefore crosses HBM three times per Arnoldi step
-// instead of four.
-// ---------------------------------------------------------------------------
-constexpr int kTileRows = 64;
-
-__global__ void __launch_bounds__(kBlock)
-update_dot_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k,
-                  const double* __restrict__ h, const double* __restrict__ w0,
-                  double* __restrict__ w1, double* __restrict__ partials, int ntiles) {
-    extern __shared__ double sh[];                 // k coefficients
-    __shared__ double sred[kBlock / 32][kTileRows];
-    __shared__ double sw1[kTileRows];
-    for (int j = threadIdx.x; j < k; j += blockDim.x) sh[j] = h[j];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int NW = kBlock / 32;
-    const int64_t r0 = (int64_t)blockIdx.x * kTileRows;
-    const int64_t r = r0 + 2 * lane;
-    const bool ok2 = r + 1 < n, ok1 = r < n;
-    __syncthreads();
-    // ---- phase A: this warp's share of V_tile * h1
-    double ax = 0.0, ay = 0.0;
-    const double* p = V + r;
-    int j = warp;
-    for (; j + 7 * NW < k; j += 8 * NW) {
-        double2 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const double* q = p + (int64_t)(j + u * NW) * ld;
-            v[u] = ok2 ? ld_stream2(q) : make_double2(ok1 ? ld_stream(q) : 0.0, 0.0);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            ax = fma(sh[j + u * NW], v[u].x, ax);
-            ay = fma(sh[j + u * NW], v[u].y, ay);
-        }
-    }
-    for (; j < k; j += NW) {
-        const double* q = p + (int64_t)j * ld;
-        const double2 v = ok2 ? ld_stream2(q) : make_double2(ok1 ? ld_stream(q) : 0.0, 0.0);
-        ax = fma(sh[j], v.x, ax);
-        ay = fma(sh[j], v.y, ay);
-    }
-    sred[warp][2 * lane] = ax;
-    sred[warp][2 * lane + 1] = ay;
-    __syncthreads();
-    if (threadIdx.x < kTileRows) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) s += sred[w][threadIdx.x];
-        const int64_t rr = r0 + threadIdx.x;
-        double out = 0.0;
-        if (rr < n) {
-            out = w0[rr] - s;
-            w1[rr] = out;
-        }
-        sw1[threadIdx.x] = out;
-    }
-    __syncthreads();
-    // ---- phase B: second-pass coefficients of the tile (V_tile comes from L2)
-    // A warp takes 32 columns at a time (j = jg + warp + NW*u, u = 0..31); every lane forms its
-    // row pair's contribution to each of them, and a butterfly "transpose-reduce" (31 shuffles
-    // for 32 sums instead of 5 per sum — the per-column warp reduction made the first version
-    // of this kernel shuffle-bound, profiles/r01_cgs_fusion.md) leaves the total of column u in
-    // lane u.
-    const double wx = sw1[2 * lane], wy = sw1[2 * lane + 1];
-    for (int jg = 0; jg < k; jg += 32 * NW) {
-        double pu[32];
-#pragma unroll
-        for (int u0 = 0; u0 < 32; u0 += 8) {
-            double2 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int jj = jg + warp + NW * (u0 + u);
-                const double* q = p + (int64_t)jj * ld;
-                v[u] = (jj < k && ok2) ? ld_stream2(q)
-                                       : make_double2((jj < k && ok1) ? ld_stream(q) : 0.0, 0.0);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) pu[u0 + u] = fma(v[u].x, wx, v[u].y * wy);
-        }
-#pragma unroll
-        for (int half = 16; half >= 1; half >>= 1) {
-            const bool up = (lane & half) != 0;
-#pragma unroll
-            for (int u = 0; u < half; ++u) {
-                const double send = up ? pu[u] : pu[u + half];
-                const double keep = up ? pu[u + half] : pu[u];
-                pu[u] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-            }
-        }
-        const int jj = jg + warp + NW * lane;
-        if (jj < k) partials[(int64_t)jj * ntiles + blockIdx.x] = pu[0];
     }
 }
 
@@ -683,7 +580,7 @@ int hg_k_reduce(hg_ctx* ctx, const double* partials, int np, int k, double* out,
 
 int hg_k_lincomb_push(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* c,
                       double s, const double* z, double* out, const double* ref, double* stat,
-                      int* nparts, const hg_out_list* extra, bool reverse) {
+                      int* nparts, const hg_out_list* extra) {
     const int64_t grid = cdiv(cdiv(n, 2), kBlock);
     if (nparts) *nparts = stat ? (int)grid : 0;
     if (n <= 0) return HG_OK;
@@ -695,10 +592,10 @@ int hg_k_lincomb_push(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k
     hg_launch_scope scope(ctx, HG_K_LINCOMB, bytes);
     const size_t smem = (size_t)(k > 0 ? k : 1) * sizeof(double);
     if (extra && extra->n > 0)
-        lincomb_kernel<true><<<(unsigned)grid, kBlock, smem, ctx->stream>>>(V, ld, n, k, c, s, z, out, ref, stat, *extra, reverse ? 1 : 0);
+        lincomb_kernel<true><<<(unsigned)grid, kBlock, smem, ctx->stream>>>(V, ld, n, k, c, s, z, out, ref, stat, *extra);
     else
         lincomb_kernel<false><<<(unsigned)grid, kBlock, smem, ctx->stream>>>(V, ld, n, k, c, s, z, out, ref, stat,
-                                                                            hg_out_list(), reverse ? 1 : 0);
+                                                                            hg_out_list());
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }
@@ -706,7 +603,7 @@ int hg_k_lincomb_push(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k
 int hg_k_lincomb(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* c,
                  double s, const double* z, double* out, const double* ref, double* stat,
                  int* nparts) {
-    return hg_k_lincomb_push(ctx, V, ld, n, k, c, s, z, out, ref, stat, nparts, nullptr, false);
+    return hg_k_lincomb_push(ctx, V, ld, n, k, c, s, z, out, ref, stat, nparts, nullptr);
 }
 
 // x = Q y (+ ||x - x_true||) and ||b - T y|| in one launch; out2[0] = error norm, out2[1] = residual norm
@@ -730,21 +627,6 @@ int hg_k_iterate2(hg_ctx* ctx, const double* V0, int64_t ld0, int64_t n0, int k0
     const int kmax = k0 > k1 ? k0 : k1;
     const size_t smem = (size_t)(kmax > 0 ? kmax : 1) * sizeof(double);
     iterate_kernel<<<(unsigned)grid, kBlock, smem, ctx->stream>>>(j0, j1, stat, ticket, out2);
-    HG_CUDA(cudaGetLastError());
-    return HG_OK;
-}
-
-int hg_update_dot_ntiles(int64_t n) { return (int)cdiv(n, kTileRows); }
-
-int hg_k_update_dot(hg_ctx* ctx, const double* V, int64_t ld, int64_t n, int k, const double* h,
-                    const double* w0, double* w1, double* partials, int* ntiles) {
-    const int nt = (int)cdiv(n, kTileRows);
-    if (ntiles) *ntiles = nt;
-    if (n <= 0 || k <= 0) return HG_OK;
-    // algorithmic bytes: one stream of V for the update, one for the dot, w0 in, w1 out
-    hg_launch_scope scope(ctx, HG_K_LINCOMB, 16.0 * (double)n * (double)k + 16.0 * (double)n);
-    update_dot_kernel<<<nt, kBlock, (size_t)k * sizeof(double), ctx->stream>>>(V, ld, n, k, h, w0, w1,
-                                                                              partials, nt);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }

@@ -255,24 +255,14 @@ static int spmv_mode() {
 
 int hg_spmv_mode() { return spmv_mode(); }
 
-static int g_cgs_alternate = -1;
-bool hg_cgs_alternate() {
-    if (g_cgs_alternate < 0) {
-        const char* e = getenv("HG_CGS_ALTERNATE");
-        g_cgs_alternate = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured neutral on B200
-    }
-    return g_cgs_alternate != 0;
-}
-
 static int g_cgs_fused = -1;
 int hg_cgs_fused_mode() {
     if (g_cgs_fused < 0) {
         const char* e = getenv("HG_CGS_FUSED");
-        g_cgs_fused = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;  // default: shared-memory-staged one-pass kernel
+        g_cgs_fused = (e && e[0] == '0') ? 0 : 2;  // default: shared-memory-staged one-pass kernel
     }
     return g_cgs_fused;
 }
-bool hg_cgs_fused() { return hg_cgs_fused_mode() == 1; }
 
 void hg_dist_transport_set(int v);
 void hg_idx16_set(int v);
@@ -280,7 +270,7 @@ void hg_idx16_set(int v);
 extern "C" int hg_set_option(const char* name, int value) {
     HG_REQUIRE(name, "hg_set_option: NULL name");
     if (strcmp(name, "cgs_fused") == 0) {
-        HG_REQUIRE(value >= 0 && value <= 2, "hg_set_option: cgs_fused must be 0, 1 or 2");
+        HG_REQUIRE(value == 0 || value == 2, "hg_set_option: cgs_fused must be 0 or 2");
         g_cgs_fused = value;
         return HG_OK;
     }
@@ -303,10 +293,6 @@ extern "C" int hg_set_option(const char* name, int value) {
     }
     if (strcmp(name, "spmv_group") == 0) {
         hg_spmv_group_set(value);
-        return HG_OK;
-    }
-    if (strcmp(name, "cgs_alternate") == 0) {
-        g_cgs_alternate = value ? 1 : 0;
         return HG_OK;
     }
     if (strcmp(name, "dist_transport") == 0) {

@@ -68,11 +68,9 @@ int hg_version(void);
  * "cgs_fused" / env HG_CGS_FUSED: the first CGS2 update and the second-pass dot products in one pass
  * over the basis (it crosses HBM three times per step instead of four).  2 (default): tiles staged in
  * shared memory by cp.async, persistent CTAs (csrc/cgs_staged.cu; 599 -> 634 it/s on the headline
- * workload); 1: the first attempt that re-reads the tile from L2 (slower than the separate kernels,
- * profiles/r01_cgs_fusion.md); 0: separate update and multi-dot kernels.
- * "cgs_alternate": 0 (default; env HG_CGS_ALTERNATE=1 enables) the CGS2 update kernels walk the rows
- * from the end, so each sweep over the basis starts on the ~100 MB the previous one left in L2
- * (measured neutral on B200).
+ * workload); 0: separate update and multi-dot kernels.  (Two measured-slower experiments of round 1 — an
+ * L2-re-read fused kernel and backwards-walking update sweeps — were removed in round 2; their numbers are
+ * in profiles/r01_cgs_fusion.md.)
  * "cgs_step_max_n" / env HG_CGS_STEP_MAX_N (default 140000; 0 disables): Krylov vectors up to this length
  * run the whole CGS2 step (orthogonalisation, norm, normalisation) in ONE persistent cooperative kernel
  * (csrc/cgs2_step.cu) instead of seven launches.  "cgs_step_max_n_dist" / HG_CGS_STEP_MAX_N_DIST (default 0 =

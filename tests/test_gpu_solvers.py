@@ -256,19 +256,25 @@ def test_cross_solver_identity(hg, ctx, ct64):
 
 
 def test_cgs_fused_option_matches_default(hg, ctx, ct64):
-    """The opt-in fused CGS2 middle stage (update + second-pass dot products in one kernel,
-    butterfly transpose-reduce) gives the same Arnoldi factorisation as the separate kernels."""
+    """The one-pass CGS2 middle stage (update + second-pass dot products from a shared-memory tile,
+    `cgs_fused` = 2) gives the same Arnoldi factorisation as the separate kernels (`cgs_fused` = 0).  The
+    whole-step kernel is switched off so that the middle stage under test is the one that runs; the removed
+    L2-re-read variant (1) is refused."""
     A, B, b, x_true = ct64
     out = {}
     try:
-        for fused in (0, 1):
+        hg.set_option("cgs_step_max_n", 0)
+        for fused in (0, 2):
             hg.set_option("cgs_fused", fused)
             ex = {}
             r = hg.hybrid_ba_gmres_rtp(A, B, b, x_true, 1e-6, 45, 1e-2, ctx=ctx, extras=ex)
             out[fused] = (r, ex)
+        with pytest.raises(Exception):
+            hg.set_option("cgs_fused", 1)
     finally:
         hg.set_option("cgs_fused", 2)
-    (r0, e0), (r1, e1) = out[0], out[1]
+        hg.set_option("cgs_step_max_n", 140000)
+    (r0, e0), (r1, e1) = out[0], out[2]
     assert r0[3] == r1[3]
     assert np.max(_colwise(e1["H"], e0["H"], r0[3])) < 1e-11
     assert np.max(np.abs(r0[2] - r1[2]) / r0[2]) < 1e-11
