@@ -219,7 +219,8 @@ class DeviceMatrix:
 
     @property
     def spmv_index_bits(self) -> int:
-        """16 when the SpMV streams 16-bit column offsets from per-group bases, else 32."""
+        """16 when the SpMV streams 16-bit column offsets (from per-group bases; per-lane differences in the "group"
+        form), else 32."""
         f = C.c_int()
         check(self.ctx._lib.hg_matrix_spmv_form(self.ctx._h, self._h, C.byref(f)))
         return 16 if f.value & 16 else 32

@@ -133,6 +133,8 @@ struct hg_matrix {
     int64_t* grp_ptr = nullptr;   // grp_groups+1 entry offsets (multiples of 32)
     int32_t* grp_col = nullptr;   // grp_entries
     double* grp_val = nullptr;
+    int32_t* grp_col0 = nullptr;  // 16-bit form: first column of each lane (grp_groups * 32) ...
+    int16_t* grp_d16 = nullptr;   // ... and per-lane column differences round to round (grp_entries); grp_col unused
 };
 
 // colind / vals are allocated with this many zero entries of tail padding so the
@@ -290,6 +292,8 @@ int hg_spmv_group();
 void hg_spmv_group_set(int v);
 bool hg_group_ready(hg_ctx* ctx, const hg_matrix* m);
 void hg_group_free(hg_matrix* m);
+int hg_spmv_group16();
+void hg_spmv_group16_set(int v);
 int hg_k_spmv_group(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y, const hg_spmv_epilogue& ep,
                     double bytes, int* nparts);
 

@@ -10,6 +10,12 @@
 // row 1, ... (lane l: row l / E, entry tE + l % E); rows shorter than the longest of their group are padded
 // with zero values whose column is the row's last valid one (no extra line).  Same entries, per-row traversal
 // order kept; the per-row summation order differs from the CSR kernel (E interleaved partial sums).
+//
+// 16-bit column stream (default, option "spmv_group16"): lane l of a group visits entries l%E, l%E + E, l%E + 2E ...
+// of its ray, E pixels further along the ray each round, so the column index moves by a few image rows per round:
+// the stream holds that per-lane DIFFERENCE as int16 (first round: absolute int32 per lane), 10 instead of 12 bytes
+// per non-zero.  The decode is one integer add per entry; sums, order and results are bit-identical to the 32-bit
+// form.  A matrix with a difference outside int16 keeps the 32-bit form.
 #include <algorithm>
 #include <vector>
 
@@ -29,6 +35,11 @@ __device__ __forceinline__ int ld_stream(const int* p) {
     int v;
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
+}
+__device__ __forceinline__ int ld_stream(const short* p) {
+    short v;
+    asm volatile("ld.global.nc.L1::no_allocate.s16 %0, [%1];" : "=h"(v) : "l"(p));
+    return (int)v;
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -74,6 +85,126 @@ __global__ void group_fill_kernel(int64_t rows, int64_t ngroups, const int64_t* 
         const bool ok = k < len;
         gcol[i] = ok ? colind[rs + k] : pad_col;
         gval[i] = ok ? vals[rs + k] : 0.0;
+    }
+}
+
+// the same rounds with the column stream as per-lane differences: col0[g*32 + lane] is the lane's first column,
+// d16[i] = column(i) - column(i - 32) (0 in the first round); *overflow is set when a difference leaves int16
+template <int G>
+__global__ void group_fill16_kernel(int64_t rows, int64_t ngroups, const int64_t* __restrict__ rowptr,
+                                    const int32_t* __restrict__ colind, const double* __restrict__ vals,
+                                    const int64_t* __restrict__ gptr, int32_t* __restrict__ col0,
+                                    short* __restrict__ d16, double* __restrict__ gval, int* __restrict__ overflow) {
+    constexpr int E = 32 / G;
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= ngroups) return;
+    const int64_t row = g * G + lane / E;
+    const int e0 = lane % E;
+    const int64_t rs = row < rows ? rowptr[row] : 0;
+    const int64_t len = row < rows ? rowptr[row + 1] - rs : 0;
+    const int pad_col = len > 0 ? colind[rs + len - 1] : 0;
+    const int64_t s = gptr[g], e = gptr[g + 1];
+    int prev = e0 < len ? colind[rs + e0] : pad_col;
+    col0[g * 32 + lane] = prev;
+    bool bad = false;
+    int64_t t = 0;
+    for (int64_t i = s + lane; i < e; i += 32, ++t) {
+        const int64_t k = t * E + e0;
+        const bool ok = k < len;
+        const int c = ok ? colind[rs + k] : pad_col;
+        const int d = c - prev;
+        bad |= d < -32768 || d > 32767;
+        d16[i] = (short)d;
+        gval[i] = ok ? vals[rs + k] : 0.0;
+        prev = c;
+    }
+    if (bad) atomicExch(overflow, 1);
+}
+
+template <int G>
+__global__ void __launch_bounds__(kBlock)
+spmv_group16_kernel(int64_t rows, int64_t ngroups, const int64_t* __restrict__ gptr, const int* __restrict__ col0,
+                    const short* __restrict__ d16, const double* __restrict__ gval, const double* __restrict__ x,
+                    double* __restrict__ y, double alpha, const double* __restrict__ z1, double g1,
+                    const double* __restrict__ z2, double g2, const double* __restrict__ ref,
+                    double* __restrict__ stat) {
+    constexpr int E = 32 / G;
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    const bool live = g < ngroups;
+    const int64_t s = live ? gptr[g] : 0;
+    const int64_t e = live ? gptr[g + 1] : 0;
+    // same software pipeline as spmv_group_kernel; the running column of the lane is carried through the rounds
+    double a[U];
+    int d[U];
+    double v[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = 0.0;
+    int col = live ? col0[g * 32 + lane] : 0;
+    int64_t i = s + lane;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        ok[u] = i + u * 32 < e;
+        d[u] = ok[u] ? ld_stream(d16 + i + u * 32) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = ok[u] ? ld_stream(gval + i + u * 32) : 0.0;
+    while (i - lane < e) {  // warp uniform
+        double xg[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            col += d[u];  // 0 past the end of the group: the column stays on its last line
+            xg[u] = ok[u] ? __ldg(x + col) : 0.0;
+        }
+        const int64_t in = i + U * 32;
+        int dn[U];
+        double vn[U];
+        bool okn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            okn[u] = in + u * 32 < e;
+            dn[u] = okn[u] ? ld_stream(d16 + in + u * 32) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) vn[u] = okn[u] ? ld_stream(gval + in + u * 32) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            a[u] = fma(v[u], xg[u], a[u]);
+            d[u] = dn[u];
+            v[u] = vn[u];
+            ok[u] = okn[u];
+        }
+        i = in;
+    }
+    double sum = (a[0] + a[1]) + (a[2] + a[3]);
+#pragma unroll
+    for (int o = E / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);  // the E lanes of a row
+    double sq = 0.0;
+    const int64_t row = g * G + lane / E;
+    if (live && (lane % E) == 0 && row < rows) {
+        double out = alpha * sum;
+        if (z1) out += g1 * z1[row];
+        if (z2) out += g2 * z2[row];
+        if (y) y[row] = out;
+        if (stat) {
+            const double dd = ref ? out - ref[row] : out;
+            sq = dd * dd;
+        }
+    }
+    if (stat) {
+        __shared__ double s_red[kBlock / 32];
+        sq = warp_sum(sq);
+        if (lane == 0) s_red[threadIdx.x >> 5] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; ++w) t += s_red[w];
+            stat[blockIdx.x] = t;
+        }
     }
 }
 
@@ -191,15 +322,44 @@ bool build(hg_ctx* ctx, hg_matrix* m) {
     ptr[(size_t)ngroups] = acc;
     if ((double)acc > 1.06 * (double)m->nnz) return false;  // ragged groups: the padding would cost more than the gathers save
     cudaError_t a = hg_dmalloc(ctx, &m->grp_ptr, (size_t)(ngroups + 1) * 8);
-    if (a == cudaSuccess) a = hg_dmalloc(ctx, &m->grp_col, (size_t)(acc + kNnzPad) * 4);
     if (a == cudaSuccess) a = hg_dmalloc(ctx, &m->grp_val, (size_t)(acc + kNnzPad) * 8);
     if (a == cudaSuccess)
         a = cudaMemcpyAsync(m->grp_ptr, ptr.data(), (size_t)(ngroups + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-    if (a == cudaSuccess) {
-        hg_launch_scope scope(ctx, HG_K_SETUP, 24.0 * (double)m->nnz);
-        group_fill_kernel<G><<<(unsigned)cdiv(ngroups * 32, kBlock), kBlock, 0, ctx->stream>>>(
-            m->rows, ngroups, m->rowptr, m->colind, m->vals, m->grp_ptr, m->grp_col, m->grp_val);
-        a = cudaGetLastError();
+    bool have16 = false;
+    if (a == cudaSuccess && hg_spmv_group16()) {
+        // 16-bit column differences; a difference outside int16 anywhere sends the matrix to the 32-bit form
+        int* d_flag = nullptr;
+        int flag = 1;
+        cudaError_t b = hg_dmalloc(ctx, &d_flag, sizeof(int));
+        if (b == cudaSuccess) b = cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream);
+        if (b == cudaSuccess) b = hg_dmalloc(ctx, &m->grp_col0, (size_t)ngroups * 32 * 4);
+        if (b == cudaSuccess) b = hg_dmalloc(ctx, &m->grp_d16, (size_t)(acc + kNnzPad) * 2);
+        if (b == cudaSuccess) {
+            hg_launch_scope scope(ctx, HG_K_SETUP, 22.0 * (double)m->nnz);
+            group_fill16_kernel<G><<<(unsigned)cdiv(ngroups * 32, kBlock), kBlock, 0, ctx->stream>>>(
+                m->rows, ngroups, m->rowptr, m->colind, m->vals, m->grp_ptr, m->grp_col0, m->grp_d16, m->grp_val, d_flag);
+            b = cudaGetLastError();
+        }
+        if (b == cudaSuccess) b = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (b == cudaSuccess) b = cudaStreamSynchronize(ctx->stream);
+        if (d_flag) hg_dfree(d_flag);
+        have16 = b == cudaSuccess && flag == 0;
+        if (!have16) {
+            cudaGetLastError();
+            hg_dfree(m->grp_col0);
+            hg_dfree(m->grp_d16);
+            m->grp_col0 = nullptr;
+            m->grp_d16 = nullptr;
+        }
+    }
+    if (a == cudaSuccess && !have16) {
+        a = hg_dmalloc(ctx, &m->grp_col, (size_t)(acc + kNnzPad) * 4);
+        if (a == cudaSuccess) {
+            hg_launch_scope scope(ctx, HG_K_SETUP, 24.0 * (double)m->nnz);
+            group_fill_kernel<G><<<(unsigned)cdiv(ngroups * 32, kBlock), kBlock, 0, ctx->stream>>>(
+                m->rows, ngroups, m->rowptr, m->colind, m->vals, m->grp_ptr, m->grp_col, m->grp_val);
+            a = cudaGetLastError();
+        }
     }
     if (a == cudaSuccess) a = cudaStreamSynchronize(ctx->stream);  // `ptr` is pageable host memory
     if (a != cudaSuccess) {
@@ -207,9 +367,13 @@ bool build(hg_ctx* ctx, hg_matrix* m) {
         hg_dfree(m->grp_ptr);
         hg_dfree(m->grp_col);
         hg_dfree(m->grp_val);
+        hg_dfree(m->grp_col0);
+        hg_dfree(m->grp_d16);
         m->grp_ptr = nullptr;
         m->grp_col = nullptr;
         m->grp_val = nullptr;
+        m->grp_col0 = nullptr;
+        m->grp_d16 = nullptr;
         return false;
     }
     m->grp_groups = ngroups;
@@ -219,6 +383,17 @@ bool build(hg_ctx* ctx, hg_matrix* m) {
 }
 
 }  // namespace
+
+// 16-bit column differences in the interleaved form: option "spmv_group16" / env HG_SPMV_GROUP16 (default 1)
+static int g_group16 = -1;
+int hg_spmv_group16() {
+    if (g_group16 < 0) {
+        const char* e = getenv("HG_SPMV_GROUP16");
+        g_group16 = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_group16;
+}
+void hg_spmv_group16_set(int v) { g_group16 = v != 0 ? 1 : 0; }
 
 // rows per group of the interleaved form: option "spmv_group" / env HG_SPMV_GROUP = 0 (off), 2, 4 or 8
 int hg_spmv_group() {
@@ -264,9 +439,13 @@ void hg_group_free(hg_matrix* m) {
     hg_dfree(m->grp_ptr);
     hg_dfree(m->grp_col);
     hg_dfree(m->grp_val);
+    hg_dfree(m->grp_col0);
+    hg_dfree(m->grp_d16);
     m->grp_ptr = nullptr;
     m->grp_col = nullptr;
     m->grp_val = nullptr;
+    m->grp_col0 = nullptr;
+    m->grp_d16 = nullptr;
     m->grp_state = 0;
 }
 
@@ -276,6 +455,16 @@ int hg_k_spmv_group(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
     HG_REQUIRE(grid < (int64_t)2147483647, "spmv: too many rows for one launch");
     if (nparts && ep.stat) *nparts = (int)grid;
     hg_launch_scope scope(ctx, HG_K_SPMV, bytes);
+    if (m->grp_d16) {
+#define HG_GRP16_ARGS m->rows, m->grp_groups, m->grp_ptr, m->grp_col0, m->grp_d16, m->grp_val, x, y, ep.alpha, ep.z1, ep.g1, \
+                      ep.z2, ep.g2, ep.ref, ep.stat
+        if (m->grp_G == 2) spmv_group16_kernel<2><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_GRP16_ARGS);
+        else if (m->grp_G == 4) spmv_group16_kernel<4><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_GRP16_ARGS);
+        else spmv_group16_kernel<8><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_GRP16_ARGS);
+#undef HG_GRP16_ARGS
+        HG_CUDA(cudaGetLastError());
+        return HG_OK;
+    }
 #define HG_GRP_ARGS m->rows, m->grp_groups, m->grp_ptr, m->grp_col, m->grp_val, x, y, ep.alpha, ep.z1, ep.g1, ep.z2, ep.g2, \
                     ep.ref, ep.stat
     if (m->grp_G == 2) spmv_group_kernel<2><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_GRP_ARGS);

@@ -496,10 +496,30 @@ def test_spmv_row_group_form_matches_csr(hg, ctx, G):
         d1 = hg.DeviceMatrix.from_csr(M.indptr, M.indices, M.data, M.shape, ctx)
         if form0 == "csr":
             assert d1.spmv_form == "group"
+            # default: the column stream is 16-bit per-lane differences (10 B per non-zero); G = 2 strides 16
+            # entries of a ray per round, which can leave int16 and then keeps the 32-bit stream
+            assert d1.spmv_index_bits == 16 or G == 2
         y1, y2 = d1.matvec(x), d1.matvec(x)
         assert np.array_equal(y1, y2)
         assert np.max(np.abs(y1 - y0)) <= 1e-13 * np.max(np.abs(y0))
         assert np.max(np.abs(y1 - M @ x)) <= 1e-13 * np.max(np.abs(y0))
+        # 32-bit column stream: same rounds, same sums -> identical bits
+        hg.set_option("spmv_group16", 0)
+        d2 = hg.DeviceMatrix.from_csr(M.indptr, M.indices, M.data, M.shape, ctx)
+        if form0 == "csr":
+            assert d2.spmv_form == "group" and d2.spmv_index_bits == 32
+        assert np.array_equal(d2.matvec(x), y1)
+        hg.set_option("spmv_group16", 1)
+        # a matrix whose rows jump by more than int16 between rounds falls back to the 32-bit stream
+        rng = np.random.default_rng(9)
+        nr, per, stride = 2048, 256, 10000
+        cols = (np.arange(per)[None, :] * stride + rng.integers(0, stride, size=(nr, per))).astype(np.int32)
+        W = sp.csr_matrix((rng.standard_normal(nr * per), cols.ravel(), np.arange(nr + 1, dtype=np.int64) * per),
+                          shape=(nr, per * stride))
+        dW = hg.DeviceMatrix.from_csr(W.indptr, W.indices, W.data, W.shape, ctx)
+        xw = rng.standard_normal(W.shape[1])
+        assert dW.spmv_form == "group" and dW.spmv_index_bits == 32
+        assert np.max(np.abs(dW.matvec(xw) - W @ xw)) <= 1e-13 * np.max(np.abs(W @ xw))
         # through a solver: shift epilogue, residual statistics
         import oracle
         from oracle import ct
@@ -508,4 +528,5 @@ def test_spmv_row_group_form_matches_csr(hg, ctx, G):
         xo, eo, ro, ito = oracle.hybrid_ba_gmres_rtp(A, B, b, x_true, 1e-6, 20, 1e-2)
         assert its == ito and np.max(np.abs(rs - ro) / ro) < 1e-8 and np.max(np.abs(es - eo) / eo) < 1e-8
     finally:
+        hg.set_option("spmv_group16", 1)
         hg.set_option("spmv_group", -1)  # back to the default (G = 4 for matrices of >= 100 000 rows)

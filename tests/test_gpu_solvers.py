@@ -192,14 +192,13 @@ def test_gkb_solvers_vs_oracle(hg, ctx, ct48_unmatched, name):
     """Golub-Kahan solvers vs the oracle.  Without reorthogonalisation the GKB recurrences
     amplify rounding differences once Ritz values converge: the oracle run on an input
     perturbed at the 1e-16 level departs from itself by 1e-8 at k~12 and 1e-2 by k~15 on this
-    problem (see DESIGN.md "Parity").  So: strict 1e-8 on the first 8 iterations, and for
-    later iterations a bound scaled by the oracle's own measured sensitivity."""
+    problem (see DESIGN.md "Parity").  So: strict 1e-8 for as many iterations as the oracle's own
+    sensitivity permits (10-11 here, computed below and asserted), a graded bound of 5 x that sensitivity on
+    the well-determined stretch (2e-14 at k <= 5), and a bound scaled by the sensitivity afterwards."""
     import oracle
     A, B, b, x_true = ct48_unmatched
     maxit, lam, tol = 40, 1e-2, 1e-6
     f_dev, f_orc = getattr(hg, name), getattr(oracle, name)
-    rng = np.random.default_rng(11)
-    b_pert = b * (1.0 + 2.2e-16 * rng.standard_normal(b.shape))
 
     def run(f, rhs, **kw):
         ex = {}
@@ -211,15 +210,28 @@ def test_gkb_solvers_vs_oracle(hg, ctx, ct48_unmatched, name):
 
     out_d, Xd = run(f_dev, b, ctx=ctx)
     out_o, Xo = run(f_orc, b)
-    out_p, Xp = run(f_orc, b_pert)
     assert out_d[-1] == out_o[-1]  # iterations
-    sens = np.maximum.accumulate(_iter_rel(Xp, Xo))
+    sens = np.zeros(Xo.shape[1])
+    for seed in (11, 12, 13):  # the oracle against itself, b perturbed in the last bit
+        b_pert = b * (1.0 + 2.2e-16 * np.random.default_rng(seed).standard_normal(b.shape))
+        sens = np.maximum(sens, np.maximum.accumulate(_iter_rel(run(f_orc, b_pert)[1], Xo)))
     diff = _iter_rel(Xd, Xo)
-    assert np.max(diff[:8]) < TOL
+    # strict bar for as long as the problem determines the iterates to it: the leading iterations on which the
+    # oracle's own sensitivity stays below the bar (10 for hybrid LSQR, 11 for the other three; the device
+    # differs from the oracle by 2e-10 / 2e-10 / 4e-10 / 1e-10 at the last of them)
+    k_strict = int(np.argmax(sens >= TOL)) if np.any(sens >= TOL) else len(sens)
+    assert k_strict >= 10, (name, k_strict)
+    assert np.max(diff[:k_strict]) < TOL, (name, k_strict, diff[:k_strict])
+    # graded: while the iterates are well determined the device is within 5 x the oracle's self-sensitivity
+    # (measured <= 1.1 x), floored at rounding level; through the blow-up (k >= 14) within 1e3 x
+    m = min(len(diff), len(sens))
+    well = sens[:m] < 1e-9
+    assert np.all(diff[:m][well] <= np.maximum(2e-14, 5 * sens[:m])[well]), (name, diff[:14], sens[:14])
+    assert np.max(diff[:5]) < 2e-14
     assert np.all(diff <= np.maximum(TOL, 1e3 * sens[: len(diff)]))
     for hd, ho in zip(out_d[1:-1], out_o[1:-1]):  # histories
         assert hd.shape == ho.shape
-        assert np.max(np.abs(hd[:8] - ho[:8]) / np.abs(ho[:8])) < TOL
+        assert np.max(np.abs(hd[:k_strict] - ho[:k_strict]) / np.abs(ho[:k_strict])) < TOL
         rel = np.abs(hd - ho) / np.abs(ho)
         assert np.all(rel <= np.maximum(TOL, 1e3 * sens[: len(rel)]))
 
@@ -393,6 +405,32 @@ def test_config2_256_ba_rtp_vs_oracle(hg, ctx, b_kind):
         assert ratio[k] <= 1.0, (name, k + 1, d[k], sens[k], [f"{v:.1e}" for v in d[38:]], [f"{v:.1e}" for v in sens[38:]])
     assert np.max(d_res[:20]) < TOL and np.max(d_x[:20]) < TOL  # before the first sensitive stretch: the plain bar
     assert abs(ex_d["beta"] - ex_o["beta"]) / ex_o["beta"] < 1e-13
+
+    # Same algorithm on both sides: the device against the oracle's CGS2 variant, per iteration, with the
+    # tightest bound the problem allows — 20 x the CGS2 oracle's own response to the 1e-15 perturbation of b
+    # (window of +-2 iterations), floored at the rounding level of the quantity.  Measured on B200: the
+    # device/oracle difference is at most 5 x that sensitivity at every k (pixel: residual 7e-16 at k=10,
+    # 3e-13 at k=19, 7e-4 at k=26, 2e-14 at k=31; perturbed: <= 2e-10 everywhere), i.e. the device is as close
+    # to the oracle as the oracle is to itself.
+    xq, errq, resq, itq = oracle.hybrid_ba_gmres_rtp(A, B, b_pert, x_true, tol, maxit, lam, orth="cgs2", extras=(ex_q := {}))
+    assert it == itc == itq
+    sens_c = {
+        "residual": window(np.abs(resq - resc) / resc),
+        "iterate": window(_iter_rel(ex_q["X"], ex_c["X"])),
+        "hessenberg": window(_colwise(ex_q["H"], ex_c["H"], it)),
+    }
+    diff_c = {
+        "residual": np.abs(res - resc) / resc,
+        "iterate": _iter_rel(ex_d["X"], ex_c["X"]),
+        "hessenberg": _colwise(ex_d["H"], ex_c["H"], it),
+    }
+    floor = {"residual": 5e-14, "iterate": 1e-12, "hessenberg": 5e-14}
+    for name in diff_c:
+        ratio = diff_c[name] / np.maximum(floor[name], 20 * sens_c[name])
+        k = int(np.argmax(ratio))
+        assert ratio[k] <= 1.0, (name, "cgs2", k + 1, diff_c[name][k], sens_c[name][k])
+    assert np.max(diff_c["residual"][:14]) < 1e-13 and np.max(diff_c["hessenberg"][:14]) < 1e-13
+    assert np.max(diff_c["iterate"][:16]) < 1e-12
 
 
 def test_rtp_error_history_modes_agree(hg, ctx, ct48_unmatched):
