@@ -219,11 +219,11 @@ class DeviceMatrix:
 
     @property
     def spmv_index_bits(self) -> int:
-        """16 when the SpMV streams 16-bit column offsets (from per-group bases; per-lane differences in the "group"
-        form), else 32."""
+        """Width of the column stream the SpMV reads: 8 (byte offsets from a base per slice column, "sell32"), 16
+        (offsets from per-group bases; per-lane differences in the "group" form) or 32."""
         f = C.c_int()
         check(self.ctx._lib.hg_matrix_spmv_form(self.ctx._h, self._h, C.byref(f)))
-        return 16 if f.value & 16 else 32
+        return 8 if f.value & 32 else (16 if f.value & 16 else 32)
 
     def download(self):
         """Return ``(indptr[int64], indices[int32], data[float64])``."""

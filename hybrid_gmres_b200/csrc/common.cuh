@@ -119,6 +119,7 @@ struct hg_matrix {
     int32_t* sell_col = nullptr;  // device, sell_entries, slice-column-major (freed when sell_col16 exists)
     double* sell_val = nullptr;
     // 16-bit column offsets (spmv_idx16.cu): col = base[group] + col16[entry]
+    uint8_t* sell_col8 = nullptr;    // sell_entries; byte offsets [batch of 128][lane][4] from a base per slice column (sell_base: 4 per batch)
     uint16_t* sell_col16 = nullptr;  // sell_entries; group = 128 consecutive entries (4 columns of a slice)
     int32_t* sell_base = nullptr;    // sell_entries / 128
     int csr16_state = 0;             // 0 not examined, 1 built, -1 not eligible
@@ -276,6 +277,8 @@ int hg_k_spmv_sell(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
 // 16-bit column offsets (spmv_idx16.cu)
 bool hg_idx16_enabled();      // sliced form streams 16-bit column offsets (default)
 bool hg_idx16_csr_enabled();  // row-per-warp CSR kernel too (opt-in: option spmv_idx16 = 2)
+bool hg_idx8_wanted(const hg_matrix* m);
+void hg_idx8_set(int v);
 void hg_sell_compress(hg_ctx* ctx, hg_matrix* m);          // after the sliced copy is built
 bool hg_csr16_ready(hg_ctx* ctx, const hg_matrix* m);      // lazily builds the CSR companion arrays
 int hg_k_spmv_sell16(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,

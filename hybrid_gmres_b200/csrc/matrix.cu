@@ -656,7 +656,7 @@ extern "C" int hg_matrix_spmv_form(hg_ctx* ctx, const hg_matrix* m, int* form) {
     HG_CUDA(cudaSetDevice(ctx->device));
     if (hg_spmv_stream_eligible(m)) *form = 2;
     else if (m->rows > 0 && (hg_spmv_mode() == 0 || hg_spmv_mode() == 3) && hg_sell_ready(ctx, m))
-        *form = m->sell_col16 ? 1 | 16 : 1;
+        *form = m->sell_col8 ? 1 | 32 : (m->sell_col16 ? 1 | 16 : 1);
     else if (m->rows > 0 && m->tpr == 32 && hg_spmv_mode() == 0 && hg_group_ready(ctx, m))
         *form = m->grp_d16 ? 3 | 16 : 3;
     else if (m->rows > 0 && m->tpr == 32 && hg_spmv_mode() == 0 && hg_idx16_csr_enabled() && hg_csr16_ready(ctx, m))

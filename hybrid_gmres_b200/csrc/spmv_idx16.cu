@@ -8,6 +8,12 @@
 // 16-bit offsets from a per-group 32-bit base: 10.03 (sliced form) / 10.13 (CSR) bytes per entry.
 // The values, the entry order and the arithmetic are those of the 32-bit kernels (bit-identical
 // results); a matrix with any group spanning >= 65536 columns keeps its 32-bit indices.
+//
+// 8-bit offsets (sliced form, default when they fit; option "spmv_idx8"): the 32 entries of ONE column of a slice
+// are the same view of 32 adjacent pixels — a dozen detector bins — so with a base per slice column the offsets
+// fit a byte: 1 + 4/32 = 1.125 index bytes per entry instead of 2.03 (9.1 against 10.03 bytes per entry).  The
+// four offsets a lane needs for a batch of 128 entries are stored together and arrive as one 32-bit load, the
+// four bases as one 16-byte broadcast load.  Entry order and arithmetic unchanged: bit-identical results.
 #include <algorithm>
 
 #include "common.cuh"
@@ -26,6 +32,31 @@ __device__ __forceinline__ int ld_stream(const uint16_t* p) {
     unsigned short v;
     asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
     return (int)v;
+}
+__device__ __forceinline__ unsigned ld_stream(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+// absolute columns of the four entries lane `lane` owns in the batch of 128 entries that starts at i0
+// (i0 multiple of 128): entry u is i0 + u*32 + lane.  I8: byte offsets stored [lane][u] + one base per slice
+// column; else 16-bit offsets in entry order + one base per batch.
+template <bool I8>
+__device__ __forceinline__ void load_cols(const void* __restrict__ scol, const int* __restrict__ sbase, int64_t i0,
+                                          int lane, bool ok, int (&c)[4]) {
+    if (I8) {
+        const unsigned w = ok ? ld_stream(reinterpret_cast<const unsigned*>(static_cast<const uint8_t*>(scol) + i0) + lane) : 0u;
+        const int4 b = ok ? __ldg(reinterpret_cast<const int4*>(sbase) + (i0 >> 7)) : make_int4(0, 0, 0, 0);
+        c[0] = b.x + (int)(w & 255u);
+        c[1] = b.y + (int)((w >> 8) & 255u);
+        c[2] = b.z + (int)((w >> 16) & 255u);
+        c[3] = b.w + (int)(w >> 24);
+    } else {
+        const uint16_t* p = static_cast<const uint16_t*>(scol) + i0 + lane;
+        const int b = ok ? __ldg(sbase + (i0 >> 7)) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = b + (ok ? ld_stream(p + u * 32) : 0);
+    }
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -67,6 +98,27 @@ sell_compress_kernel(int64_t ngroups, const int32_t* __restrict__ col, uint16_t*
     if (lane == 0) base[g] = lo;
 }
 
+// sliced form, 8-bit: one warp per group of 128 entries; a base per slice column (32 entries), offsets stored
+// [lane][u] so that a lane's four offsets are one 32-bit word
+__global__ void __launch_bounds__(kBlock)
+sell_compress8_kernel(int64_t ngroups, const int32_t* __restrict__ col, uint8_t* __restrict__ col8,
+                      int32_t* __restrict__ base, int* __restrict__ too_wide) {
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= ngroups) return;
+    const int32_t* p = col + g * 128 + lane;
+    const int c0 = p[0], c1 = p[32], c2 = p[64], c3 = p[96];
+    const int l0 = warp_min(c0), l1 = warp_min(c1), l2 = warp_min(c2), l3 = warp_min(c3);
+    const int w = max(max(warp_max(c0) - l0, warp_max(c1) - l1), max(warp_max(c2) - l2, warp_max(c3) - l3));
+    if (w > 255) {
+        if (lane == 0) atomicOr(too_wide, 1);
+        return;
+    }
+    reinterpret_cast<unsigned*>(col8 + g * 128)[lane] =
+        (unsigned)(c0 - l0) | ((unsigned)(c1 - l1) << 8) | ((unsigned)(c2 - l2) << 16) | ((unsigned)(c3 - l3) << 24);
+    if (lane == 0) reinterpret_cast<int4*>(base)[g] = make_int4(l0, l1, l2, l3);
+}
+
 // CSR: one warp per row, a group is 32 consecutive entries of the row
 __global__ void __launch_bounds__(kBlock)
 csr_compress_kernel(int64_t rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -92,10 +144,10 @@ csr_compress_kernel(int64_t rows, const int64_t* __restrict__ rowptr, const int3
 }
 
 // ---- kernels: the 32-bit kernels with `base + offset` in place of the index load -------------
-template <int U>
+template <int U, bool I8>
 __global__ void __launch_bounds__(kBlock)
 spmv_sell16_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ sptr,
-                   const uint16_t* __restrict__ scol, const int* __restrict__ sbase,
+                   const void* __restrict__ scol, const int* __restrict__ sbase,
                    const double* __restrict__ sval, const double* __restrict__ x, double* __restrict__ y,
                    double alpha, const double* __restrict__ z1, double g1, const double* __restrict__ z2,
                    double g2, const double* __restrict__ ref, double* __restrict__ stat) {
@@ -112,22 +164,18 @@ spmv_sell16_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ sp
     for (int u = 0; u < U; ++u) a[u] = 0.0;
     int64_t i = s + lane;
     bool ok = i < e;  // whole groups: all U entries of a batch exist or none
-    int b = ok ? __ldg(sbase + (s >> 7)) : 0;
-#pragma unroll
-    for (int u = 0; u < U; ++u) c[u] = ok ? ld_stream(scol + i + u * 32) : 0;
+    load_cols<I8>(scol, sbase, s, lane, ok, c);
 #pragma unroll
     for (int u = 0; u < U; ++u) v[u] = ok ? ld_stream(sval + i + u * 32) : 0.0;
     while (i - lane < e) {  // warp uniform
         double xg[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) xg[u] = __ldg(x + b + c[u]);
+        for (int u = 0; u < U; ++u) xg[u] = __ldg(x + c[u]);
         const int64_t in = i + U * 32;
         const bool okn = in < e;
         int cn[U];
         double vn[U];
-        const int bn = okn ? __ldg(sbase + ((in - lane) >> 7)) : 0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) cn[u] = okn ? ld_stream(scol + in + u * 32) : 0;
+        load_cols<I8>(scol, sbase, in - lane, lane, okn, cn);
 #pragma unroll
         for (int u = 0; u < U; ++u) vn[u] = okn ? ld_stream(sval + in + u * 32) : 0.0;
 #pragma unroll
@@ -136,7 +184,6 @@ spmv_sell16_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ sp
             c[u] = cn[u];
             v[u] = vn[u];
         }
-        b = bn;
         i = in;
     }
     const double sum = (a[0] + a[1]) + (a[2] + a[3]);
@@ -170,10 +217,10 @@ spmv_sell16_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ sp
 // 128 entries, the S partial sums of a row are combined through shared memory in a fixed order
 // (deterministic).  A CTA holds kBlock/32/S slices.  Same per-entry arithmetic as the kernel above;
 // the per-row summation order differs (S interleaved partial sums).
-template <int S>
+template <int S, bool I8>
 __global__ void __launch_bounds__(S > 8 ? S * 32 : kBlock)
 spmv_sell16_split_kernel(int64_t rows, int64_t nslices, const int64_t* __restrict__ sptr,
-                         const uint16_t* __restrict__ scol, const int* __restrict__ sbase,
+                         const void* __restrict__ scol, const int* __restrict__ sbase,
                          const double* __restrict__ sval, const double* __restrict__ x,
                          double* __restrict__ y, double alpha, const double* __restrict__ z1, double g1,
                          const double* __restrict__ z2, double g2, const double* __restrict__ ref,
@@ -198,24 +245,20 @@ spmv_sell16_split_kernel(int64_t rows, int64_t nslices, const int64_t* __restric
     constexpr int64_t STEP = (int64_t)S * (U * 32);
     int64_t i = s + (int64_t)part * (U * 32) + lane;
     bool ok = i - lane < e;  // whole groups: all U entries of a batch exist or none
-    int b = ok ? __ldg(sbase + ((i - lane) >> 7)) : 0;
     int c[U];
     double v[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) c[u] = ok ? ld_stream(scol + i + u * 32) : 0;
+    load_cols<I8>(scol, sbase, i - lane, lane, ok, c);
 #pragma unroll
     for (int u = 0; u < U; ++u) v[u] = ok ? ld_stream(sval + i + u * 32) : 0.0;
     while (ok) {  // warp uniform
         double xg[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) xg[u] = __ldg(x + b + c[u]);
+        for (int u = 0; u < U; ++u) xg[u] = __ldg(x + c[u]);
         const int64_t in = i + STEP;
         const bool okn = in - lane < e;
         int cn[U];
         double vn[U];
-        const int bn = okn ? __ldg(sbase + ((in - lane) >> 7)) : 0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) cn[u] = okn ? ld_stream(scol + in + u * 32) : 0;
+        load_cols<I8>(scol, sbase, in - lane, lane, okn, cn);
 #pragma unroll
         for (int u = 0; u < U; ++u) vn[u] = okn ? ld_stream(sval + in + u * 32) : 0.0;
 #pragma unroll
@@ -224,7 +267,6 @@ spmv_sell16_split_kernel(int64_t rows, int64_t nslices, const int64_t* __restric
             c[u] = cn[u];
             v[u] = vn[u];
         }
-        b = bn;
         i = in;
         ok = okn;
     }
@@ -358,46 +400,79 @@ bool hg_idx16_enabled() { return idx16_level() >= 1; }
 bool hg_idx16_csr_enabled() { return idx16_level() >= 2; }
 void hg_idx16_set(int v) { g_idx16 = v < 0 ? 0 : (v > 2 ? 2 : v); }
 
+// byte offsets in the sliced form when every slice column spans < 256: option "spmv_idx8" / env HG_IDX8.
+// Default (-1): matrices of >= 4096 slices (131 072 rows) — measured B 595 -> 528 us at 1024^2, 162 -> 156 us at
+// 512^2, but 51 -> 55 us at 256^2, where 16 warps share a slice and each sees only ~6 batches; 1: every
+// matrix that fits; 0: never.
+static int g_idx8 = -2;
+static int idx8_level() {
+    if (g_idx8 == -2) {
+        const char* e = getenv("HG_IDX8");
+        g_idx8 = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
+    }
+    return g_idx8;
+}
+bool hg_idx8_wanted(const hg_matrix* m) {
+    const int l = idx8_level();
+    return l == 1 || (l < 0 && m->sell_slices >= 4096);
+}
+void hg_idx8_set(int v) { g_idx8 = v < 0 ? -1 : (v != 0 ? 1 : 0); }
+
 void hg_idx16_free(hg_matrix* m) {
     hg_dfree(m->sell_col16);
+    hg_dfree(m->sell_col8);
     hg_dfree(m->sell_base);
     hg_dfree(m->csr_col16);
     hg_dfree(m->csr_base);
     hg_dfree(m->csr_gptr);
     m->sell_col16 = nullptr;
+    m->sell_col8 = nullptr;
     m->sell_base = nullptr;
     m->csr_col16 = nullptr;
     m->csr_base = nullptr;
     m->csr_gptr = nullptr;
 }
 
-// Replaces the 32-bit column array of the sliced copy by 16-bit offsets when every group allows it.
-void hg_sell_compress(hg_ctx* ctx, hg_matrix* m) {
-    if (m->sell_state <= 0 || m->sell_col16 || m->sell_entries == 0) return;
+// Replaces the 32-bit column array of the sliced copy by 8-bit offsets (a base per slice column) when every
+// slice column allows it, else by 16-bit offsets (a base per 128 entries) when every group allows that.
+static bool sell_compress_try(hg_ctx* ctx, hg_matrix* m, bool bytes8) {
     const int64_t ng = m->sell_entries / 128;
     int* d_flag = nullptr;
     int h_flag = 1;
-    cudaError_t e = hg_dmalloc(ctx, &m->sell_col16, (size_t)(m->sell_entries + kNnzPad) * 2);
-    if (e == cudaSuccess) e = hg_dmalloc(ctx, &m->sell_base, (size_t)(ng + 1) * 4);
+    cudaError_t e = bytes8 ? hg_dmalloc(ctx, &m->sell_col8, (size_t)(m->sell_entries + kNnzPad))
+                           : hg_dmalloc(ctx, &m->sell_col16, (size_t)(m->sell_entries + kNnzPad) * 2);
+    if (e == cudaSuccess) e = hg_dmalloc(ctx, &m->sell_base, (size_t)(ng + 1) * (bytes8 ? 16 : 4));
     if (e == cudaSuccess) e = hg_dmalloc(ctx, &d_flag, 4);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, 4, ctx->stream);
     if (e == cudaSuccess) {
-        hg_launch_scope scope(ctx, HG_K_SETUP, 6.0 * (double)m->sell_entries);
-        sell_compress_kernel<<<(unsigned)cdiv(ng * 32, kBlock), kBlock, 0, ctx->stream>>>(
-            ng, m->sell_col, m->sell_col16, m->sell_base, d_flag);
+        hg_launch_scope scope(ctx, HG_K_SETUP, (bytes8 ? 5.0 : 6.0) * (double)m->sell_entries);
+        if (bytes8)
+            sell_compress8_kernel<<<(unsigned)cdiv(ng * 32, kBlock), kBlock, 0, ctx->stream>>>(
+                ng, m->sell_col, m->sell_col8, m->sell_base, d_flag);
+        else
+            sell_compress_kernel<<<(unsigned)cdiv(ng * 32, kBlock), kBlock, 0, ctx->stream>>>(
+                ng, m->sell_col, m->sell_col16, m->sell_base, d_flag);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (d_flag) hg_dfree(d_flag);
-    if (e != cudaSuccess || h_flag != 0) {  // a group spans >= 65536 columns (or no memory): keep 32-bit indices
+    if (e != cudaSuccess || h_flag != 0) {  // a group is too wide (or no memory): keep what we had
         cudaGetLastError();
         hg_dfree(m->sell_col16);
+        hg_dfree(m->sell_col8);
         hg_dfree(m->sell_base);
         m->sell_col16 = nullptr;
+        m->sell_col8 = nullptr;
         m->sell_base = nullptr;
-        return;
+        return false;
     }
+    return true;
+}
+
+void hg_sell_compress(hg_ctx* ctx, hg_matrix* m) {
+    if (m->sell_state <= 0 || m->sell_col16 || m->sell_col8 || m->sell_entries == 0) return;
+    if (!(hg_idx8_wanted(m) && sell_compress_try(ctx, m, true)) && !sell_compress_try(ctx, m, false)) return;
     hg_dfree(m->sell_col);  // the 32-bit copy of the sliced indices is no longer read
     m->sell_col = nullptr;
 }
@@ -468,13 +543,24 @@ int hg_k_spmv_sell16(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y
     HG_REQUIRE(grid < (int64_t)2147483647, "spmv: too many rows for one launch");
     if (nparts && ep.stat) *nparts = (int)grid;
     hg_launch_scope scope(ctx, HG_K_SPMV, bytes);
-#define HG_SELL16_ARGS m->rows, m->sell_slices, m->sell_ptr, m->sell_col16, m->sell_base, m->sell_val, x, y, ep.alpha, \
-                       ep.z1, ep.g1, ep.z2, ep.g2, ep.ref, ep.stat
-    if (S == 1) spmv_sell16_kernel<4><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
-    else if (S == 2) spmv_sell16_split_kernel<2><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
-    else if (S == 4) spmv_sell16_split_kernel<4><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
-    else if (S == 8) spmv_sell16_split_kernel<8><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);
-    else spmv_sell16_split_kernel<16><<<(unsigned)grid, 512, 0, ctx->stream>>>(HG_SELL16_ARGS);
+#define HG_SELL16_ARGS m->rows, m->sell_slices, m->sell_ptr, scol, m->sell_base, m->sell_val, x, y, ep.alpha, ep.z1, ep.g1, \
+                       ep.z2, ep.g2, ep.ref, ep.stat
+#define HG_SELL16_LAUNCH(I8)                                                                                      \
+    do {                                                                                                          \
+        if (S == 1) spmv_sell16_kernel<4, I8><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS);        \
+        else if (S == 2) spmv_sell16_split_kernel<2, I8><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS); \
+        else if (S == 4) spmv_sell16_split_kernel<4, I8><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS); \
+        else if (S == 8) spmv_sell16_split_kernel<8, I8><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_SELL16_ARGS); \
+        else spmv_sell16_split_kernel<16, I8><<<(unsigned)grid, 512, 0, ctx->stream>>>(HG_SELL16_ARGS);           \
+    } while (0)
+    if (m->sell_col8) {
+        const void* scol = m->sell_col8;
+        HG_SELL16_LAUNCH(true);
+    } else {
+        const void* scol = m->sell_col16;
+        HG_SELL16_LAUNCH(false);
+    }
+#undef HG_SELL16_LAUNCH
 #undef HG_SELL16_ARGS
     HG_CUDA(cudaGetLastError());
     return HG_OK;

@@ -329,7 +329,7 @@ bool hg_sell_ready(hg_ctx* ctx, const hg_matrix* cm) {
 
 int hg_k_spmv_sell(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
                    const hg_spmv_epilogue& ep, double bytes, int* nparts) {
-    if (m->sell_col16) return hg_k_spmv_sell16(ctx, m, x, y, ep, bytes, nparts);
+    if (m->sell_col16 || m->sell_col8) return hg_k_spmv_sell16(ctx, m, x, y, ep, bytes, nparts);
     const int64_t grid = cdiv(m->sell_slices, kBlock / 32);
     HG_REQUIRE(grid < (int64_t)2147483647, "spmv: too many rows for one launch");
     if (nparts && ep.stat) *nparts = (int)grid;

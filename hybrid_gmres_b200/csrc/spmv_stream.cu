@@ -291,6 +291,10 @@ extern "C" int hg_set_option(const char* name, int value) {
         hg_cgs2_step_max_n_dist_set(value);
         return HG_OK;
     }
+    if (strcmp(name, "spmv_idx8") == 0) {
+        hg_idx8_set(value);
+        return HG_OK;
+    }
     if (strcmp(name, "spmv_group16") == 0) {
         hg_spmv_group16_set(value);
         return HG_OK;

@@ -83,7 +83,7 @@ def test_projector_row_sums_are_chord_lengths(hg, ctx, N, nviews, geometry):
 
 @pytest.mark.parametrize("N,nviews", [(1024, 180), (2048, 300)])
 def test_backprojector_row_sums_count_views(hg, ctx, N, nviews):
-    """(2048, 300): 2.5e9 non-zeros; the sliced 16-bit-offset form is built and used beyond 2^31 entries."""
+    """(2048, 300): 2.5e9 non-zeros; the sliced form with byte offsets is built and used beyond 2^31 entries."""
     from hybrid_gmres_b200.ct import ct_backprojector, tile_permutation
     angles = np.arange(nviews) * (180.0 / nviews)
     p = int(round(math.sqrt(2.0) * N))
@@ -91,23 +91,29 @@ def test_backprojector_row_sums_count_views(hg, ctx, N, nviews):
     assert B.nnz == 2 * nviews * N * N
     if N == 2048:
         assert B.nnz > 2 ** 31
-    assert B.spmv_form == "sell32" and B.spmv_index_bits == 16
+    assert B.spmv_form == "sell32" and B.spmv_index_bits == 8  # 32 adjacent pixels of one view: < 256 bins apart
     ones = np.ones(B.shape[1])
     y = B.matvec(ones)
     assert np.max(np.abs(y - nviews)) <= 1e-12 * nviews
     u = np.random.default_rng(1).standard_normal(B.shape[1])
     yu = B.matvec(u)
     assert np.array_equal(B.matvec(u), yu)
-    if N == 1024:  # 16-bit offsets change the bytes streamed, not the arithmetic: bit-identical to 32-bit
-        hg.set_option("spmv_idx16", 0)
+    if N == 1024:  # 8- / 16-bit offsets change the bytes streamed, not the arithmetic: bit-identical to 32-bit
         try:
+            hg.set_option("spmv_idx8", 0)
+            B16 = B.permute(None, None)
+            assert B16.spmv_form == "sell32" and B16.spmv_index_bits == 16
+            y16 = B16.matvec(u)
+            B16.close()
+            hg.set_option("spmv_idx16", 0)
             B32 = B.permute(None, None)
             assert B32.spmv_form == "sell32" and B32.spmv_index_bits == 32
             y32 = B32.matvec(u)
             B32.close()
         finally:
             hg.set_option("spmv_idx16", 1)
-        assert np.array_equal(y32, yu)
+            hg.set_option("spmv_idx8", -1)
+        assert np.array_equal(y32, yu) and np.array_equal(y16, yu)
     hg.set_option("spmv_mode", 1)  # the row-per-warp kernel on the same matrix
     try:
         q = tile_permutation(N, 4)

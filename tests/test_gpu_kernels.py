@@ -206,15 +206,18 @@ def test_spmv_sliced_form_matches_csr(hg, ctx, rows, per_row, ragged):
     x = rng.standard_normal(M.shape[1])
     ys = {}
     try:
-        for idx16 in (1, 0):
-            hg.set_option("spmv_idx16", idx16)
+        for bits in (8, 16, 32):  # byte offsets are taken when every slice column spans < 256, else 16-bit ones
+            hg.set_option("spmv_idx16", 0 if bits == 32 else 1)
+            hg.set_option("spmv_idx8", 1 if bits == 8 else 0)
             hg.set_option("spmv_mode", 3)
             d = hg.DeviceMatrix.from_any(M, ctx)
-            assert d.spmv_form == "sell32" and d.spmv_index_bits == (16 if idx16 else 32)
+            assert d.spmv_form == "sell32" and d.spmv_index_bits in ((8, 16) if bits == 8 else (bits,))
             y = d.matvec(x)
             assert _rel(y, M @ x) < RTOL
             assert np.array_equal(d.matvec(x), y)  # deterministic
-            ys[idx16] = y
+            ys[bits] = y
+        assert np.array_equal(ys[8], ys[16])  # same kernel shape, same entry order
+        ys = {1: ys[16], 0: ys[32]}
         hg.set_option("spmv_mode", 1)
         d1 = hg.DeviceMatrix.from_any(M, ctx)
         assert d1.spmv_form == "csr"
@@ -222,6 +225,7 @@ def test_spmv_sliced_form_matches_csr(hg, ctx, rows, per_row, ragged):
     finally:
         hg.set_option("spmv_mode", 0)
         hg.set_option("spmv_idx16", 1)
+        hg.set_option("spmv_idx8", -1)
     # few rows: the 16-bit kernel lets several warps share a slice (another summation order); at full size
     # the 16- and 32-bit kernels are bit-identical (tests/test_gpu_fullsize.py)
     assert _rel(ys[0], ys[1]) < RTOL
@@ -314,9 +318,14 @@ def test_spmv_16bit_offsets_bit_identical(hg, ctx, ct64, ct48_unmatched, which):
     shapes agree (the sliced 16-bit kernel splits slices across warps when the matrix has few rows)."""
     M = ct64[0] if which == "A" else ct48_unmatched[1]  # ragged rays (row per warp) / uniform pixel rows (sliced)
     x = np.random.default_rng(15).standard_normal(M.shape[1])
-    assert hg.DeviceMatrix.from_any(M, ctx).spmv_index_bits == (32 if which == "A" else 16)  # defaults
-    hg.set_option("spmv_idx16", 2)  # 16-bit offsets for the row-per-warp kernel too (opt-in)
+    assert hg.DeviceMatrix.from_any(M, ctx).spmv_index_bits == (32 if which == "A" else 16)  # defaults at this size
     try:
+        hg.set_option("spmv_idx8", 1)  # byte offsets whatever the size (default: from 131 072 rows)
+        d8 = hg.DeviceMatrix.from_any(M, ctx)
+        assert d8.spmv_index_bits == (32 if which == "A" else 8)
+        y8 = d8.matvec(x)
+        hg.set_option("spmv_idx16", 2)  # 16-bit offsets for the row-per-warp kernel too (opt-in)
+        hg.set_option("spmv_idx8", 0)
         d16 = hg.DeviceMatrix.from_any(M, ctx)
         assert d16.spmv_index_bits == 16 and d16.spmv_form == ("csr" if which == "A" else "sell32")
         y16 = d16.matvec(x)
@@ -326,6 +335,9 @@ def test_spmv_16bit_offsets_bit_identical(hg, ctx, ct64, ct48_unmatched, which):
         y32 = d32.matvec(x)
     finally:
         hg.set_option("spmv_idx16", 1)
+        hg.set_option("spmv_idx8", -1)
+    if which == "B":
+        assert np.array_equal(y8, y16)  # 8- and 16-bit sliced kernels: same launch shape, same entry order
     if which == "A":
         assert np.array_equal(y16, y32)  # same kernel shape, same entry order: bit-identical
     assert _rel(y16, y32) < RTOL
