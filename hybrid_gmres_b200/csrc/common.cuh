@@ -134,7 +134,7 @@ struct hg_matrix {
     int64_t* grp_ptr = nullptr;   // grp_groups+1 entry offsets (multiples of 32)
     int32_t* grp_col = nullptr;   // grp_entries
     double* grp_val = nullptr;
-    int32_t* grp_col0 = nullptr;  // 16-bit form: first column of each lane (grp_groups * 32) ...
+    int32_t* grp_col0 = nullptr;  // 16-bit form: 4 column checkpoints of each lane (grp_groups * 4 * 32) ...
     int16_t* grp_d16 = nullptr;   // ... and per-lane column differences round to round (grp_entries); grp_col unused
 };
 
@@ -297,6 +297,10 @@ bool hg_group_ready(hg_ctx* ctx, const hg_matrix* m);
 void hg_group_free(hg_matrix* m);
 int hg_spmv_group16();
 void hg_spmv_group16_set(int v);
+int hg_spmv_group_split();
+void hg_spmv_group_split_set(int v);
+int64_t hg_spmv_group_min_rows();
+void hg_spmv_group_min_rows_set(int v);
 int hg_k_spmv_group(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y, const hg_spmv_epilogue& ep,
                     double bytes, int* nparts);
 

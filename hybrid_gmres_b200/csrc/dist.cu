@@ -289,14 +289,13 @@ extern "C" int hg_darnoldi_reset(hg_darnoldi* a, double shift) {
         int ns = 0, npp = 0;
         a->qbuf = 0;
         HG_TRY(hg_k_spmv(ctx, a->B, a->T, hg_peer_ypart(c), ep, nullptr));
-        HG_TRY(hg_k_peer_signal(c, HG_FLAG_Y));
         // r0 slice (pulled) goes to every rank's replicated vector un-normalised; the norm
         // all-reduce is also the barrier for those stores; then everybody scales locally
-        HG_TRY(hg_k_pull_multidot(c, a->row0, nullptr, 0.0, a->Q, a->Q, a->ldq, a->n_p, 0, a->partials, &ns));
+        HG_TRY(hg_k_pull_multidot(c, a->row0, nullptr, 0.0, a->Q, a->Q, a->ldq, a->n_p, 0, a->partials, &ns, true));
         hg_out_list push;
         hg_peer_push_list(c, a->qbuf, a->row0, &push);
         HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->n_p, 0, a->d_hcur, 1.0, a->Q, nullptr, nullptr, a->stat, &npp, &push));
-        HG_TRY(hg_k_reduce_allreduce(c, a->stat, npp, 1, a->d_s + 1, nullptr, false, true));  // beta
+        HG_TRY(hg_k_reduce_allreduce(c, a->stat, npp, 1, a->d_s + 1, nullptr, false, true, true));  // beta
         HG_TRY(hg_k_scale2(c, hg_peer_qfull(c, a->qbuf), a->n_pad, a->Q, a->n_p, a->d_s + 1));
         HG_CUDA(cudaMemcpyAsync(a->h_beta, a->d_s + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
         a->started = true;
@@ -327,8 +326,8 @@ static int darnoldi_step(hg_darnoldi* a, int kk) {
         int ns = 0, np = 0;
         HG_TRY(hg_k_spmv(ctx, a->A, hg_peer_qfull(c, a->qbuf), tcol, ep, nullptr));  // u_p = A_p q
         HG_TRY(hg_k_spmv(ctx, a->B, tcol, hg_peer_ypart(c), ep, nullptr));           // partial B^p u_p
-        HG_TRY(hg_k_peer_signal(c, HG_FLAG_Y));
         if (hg_cgs2_step_eligible_dist(ctx, a->n_p, kk)) {
+            HG_TRY(hg_k_peer_signal(c, HG_FLAG_Y));
             // slices of a few hundred thousand rows: reduce-scatter, CGS2 with its three all-reduces, all-gather
             // and normalisation in ONE persistent kernel (cgs2_step.cu) — 4 launches per step instead of 10
             a->qbuf ^= 1;
@@ -338,8 +337,8 @@ static int darnoldi_step(hg_darnoldi* a, int kk) {
                                     cudaMemcpyDeviceToHost, st));
             return HG_OK;
         }
-        // w0 = sum_p (B^p u_p)[slice] + shift*q[slice], fused with h1 = Q_k' w0
-        HG_TRY(hg_k_pull_multidot(c, a->row0, q_slice, a->shift, a->w0, a->Q, a->ldq, a->n_p, kk, a->partials, &ns));
+        // "B^p u_p complete" to every peer, then w0 = sum_p (B^p u_p)[slice] + shift*q[slice], fused with h1 = Q_k' w0
+        HG_TRY(hg_k_pull_multidot(c, a->row0, q_slice, a->shift, a->w0, a->Q, a->ldq, a->n_p, kk, a->partials, &ns, true));
         HG_TRY(hg_k_reduce_allreduce(c, a->partials, ns, kk, a->d_hcur, Hcol, false, false));
         if (hg_cgs_fused_mode() == 2 && hg_cgs_staged_nparts(ctx, a->n_p, kk) > 0) {
             HG_TRY(hg_k_cgs_mid_staged(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, a->w0, a->w1, a->partials, &ns));
@@ -355,7 +354,7 @@ static int darnoldi_step(hg_darnoldi* a, int kk) {
         hg_out_list push;
         hg_peer_push_list(c, a->qbuf, a->row0, &push);
         HG_TRY(hg_k_lincomb_push(ctx, a->Q, a->ldq, a->n_p, kk, a->d_hcur, -1.0, a->w1, qnext, nullptr, a->stat, &np, &push));
-        HG_TRY(hg_k_reduce_allreduce(c, a->stat, np, 1, Hcol + kk, nullptr, false, true));     // H(k+1,k) = norm(v)
+        HG_TRY(hg_k_reduce_allreduce(c, a->stat, np, 1, Hcol + kk, nullptr, false, true, true));  // H(k+1,k) = norm(v)
         HG_TRY(hg_k_scale2(c, hg_peer_qfull(c, a->qbuf), a->n_pad, qnext, a->n_p, Hcol + kk));  // q_{k+1} = v / H(k+1,k)
         HG_CUDA(cudaMemcpyAsync(a->h_H + (size_t)(kk - 1) * a->ldh(), Hcol, (size_t)(kk + 1) * 8,
                                 cudaMemcpyDeviceToHost, st));
@@ -623,8 +622,9 @@ extern "C" int hg_dist_hybrid_rtp(int kind, hg_ctx* ctx, hg_comm* comm, const hg
         HG_TRY(hg_k_lincomb(ctx, a->Q, a->ldq, n_p, k, d_y.p, 1.0, nullptr, xk, d_xt.p, stat_e.p, &np_e));
         HG_TRY(hg_k_lincomb(ctx, a->T + a->ldt, a->ldt, m_p, k, d_y.p, -1.0, a->T, nullptr, nullptr, stat_r.p, &np_r));
         if (a->peer) {
-            HG_TRY(hg_k_reduce_allreduce(comm, stat_e.p, np_e, 1, ctx->d_scalars + 1, nullptr, false, false));
-            HG_TRY(hg_k_reduce_allreduce(comm, stat_r.p, np_r, 1, ctx->d_scalars + 2, nullptr, false, false));
+            // error and residual sums of squares in one exchange
+            HG_TRY(hg_k_reduce_allreduce(comm, stat_e.p, np_e, 2, ctx->d_scalars + 1, nullptr, false, false, false,
+                                         stat_r.p, np_r));
         } else {
             HG_TRY(hg_k_reduce(ctx, stat_e.p, np_e, 1, ctx->d_scalars + 1, false, nullptr, false));
             HG_TRY(hg_k_reduce(ctx, stat_r.p, np_r, 1, ctx->d_scalars + 2, false, nullptr, false));

@@ -71,16 +71,21 @@ inline double* hg_peer_qfull(hg_comm* c, int buf) {
 int hg_k_peer_barrier(hg_comm* c, int row);
 // signal every peer on flag row `row` (no wait): "everything queued before this is complete"
 int hg_k_peer_signal(hg_comm* c, int row);
-// Waits (in every CTA) for the latest HG_FLAG_Y signal of every rank, then
+// signal: CTA 0 first announces "this rank's partial product is complete" to every peer (a new HG_FLAG_Y epoch; no
+// separate hg_k_peer_signal launch).  Waits (in every CTA) for the latest HG_FLAG_Y signal of every rank, then
 // w[r] = sum_p ypart_p[row0 + r] (+ shift * q_slice[r]) for this rank's slice, stored to w_out,
 // fused with partials[j*nslabs + slab] = sum_slab V[:,j] .* w  (k may be 0)
 int hg_k_pull_multidot(hg_comm* c, int64_t row0, const double* q_slice, double shift, double* w_out,
-                       const double* V, int64_t ld, int64_t n_p, int k, double* partials, int* nslabs);
+                       const double* V, int64_t ld, int64_t n_p, int k, double* partials, int* nslabs,
+                       bool signal = false);
 // out[j] = sum over ranks (rank order) of sum_i partials[j*np + i], j < k; identical bits on every
 // rank.  acc (optional): acc[j] = accumulate ? acc[j] + out[j] : out[j].  do_sqrt: out[j] = sqrt(.)
-// Stores of earlier kernels to peer memory are visible to a rank once it has this result.
+// barrier: stores of earlier kernels to peer memory are visible to a rank once it has this result (system-scope
+// fences on both sides; a plain all-reduce needs none, every word carries its epoch).  partials2/np2 (optional): the
+// last column (j = k-1) is summed from this second array instead — two statistics in one exchange.
 int hg_k_reduce_allreduce(hg_comm* c, const double* partials, int np, int k, double* out, double* acc,
-                          bool accumulate, bool do_sqrt);
+                          bool accumulate, bool do_sqrt, bool barrier = false, const double* partials2 = nullptr,
+                          int np2 = 0);
 // a[0..na) /= *d_div and b[0..nb) /= *d_div (na, nb even)
 int hg_k_scale2(hg_comm* c, double* a, int64_t na, double* b, int64_t nb, const double* d_div);
 // destinations of this rank's rows [row0, row0+n_p) in every rank's replicated vector `buf`

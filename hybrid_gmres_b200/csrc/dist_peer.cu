@@ -101,8 +101,8 @@ __global__ void peer_signal_kernel(hg_peer_tbl t, size_t row_off, unsigned long 
 
 // CTA-wide: until every rank has signalled `epoch` on flag row `row_off`
 __device__ __forceinline__ void wait_all(const hg_peer_tbl& t, size_t row_off, unsigned long long epoch,
-                                         unsigned long long* err) {
-    if (threadIdx.x < t.P)
+                                         unsigned long long* err, int skip = -1) {
+    if (threadIdx.x < t.P && (int)threadIdx.x != skip)  // skip: this rank's own flag (stream order covers it)
         wait_flag(reinterpret_cast<const unsigned long long*>(t.base[t.rank] + row_off) + threadIdx.x, epoch, err);
     __syncthreads();
 }
@@ -114,12 +114,18 @@ __device__ __forceinline__ void wait_all(const hg_peer_tbl& t, size_t row_off, u
 constexpr int kDotWarps = 8;
 
 __global__ void __launch_bounds__(kDotWarps * 32)
-pull_multidot_kernel(hg_peer_tbl t, size_t ypart_off, size_t flag_off, unsigned long long epoch,
+pull_multidot_kernel(hg_peer_tbl t, size_t ypart_off, size_t flag_off, unsigned long long epoch, int signal,
                      unsigned long long* err, int64_t row0, const double* __restrict__ q_slice,
                      double shift, double* __restrict__ w_out, const double* __restrict__ V, int64_t ld,
                      int64_t n, int k, double* __restrict__ partials, int nslabs, int R) {
     extern __shared__ double sw[];
-    wait_all(t, flag_off, epoch, err);  // every rank's B^p u_p is complete
+    // signal: this rank's B^p u_p (the previous kernel of the stream) is complete — CTA 0 tells every peer, no
+    // separate launch; then every CTA waits until every rank has said so
+    if (signal && blockIdx.x == 0 && threadIdx.x < t.P) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long*>(t.base[threadIdx.x] + flag_off) + t.rank, epoch);
+    }
+    wait_all(t, flag_off, epoch, err, signal ? t.rank : -1);
     const int slab = blockIdx.x;
     const int64_t r0 = (int64_t)slab * R;
     const int len = (int)min((int64_t)R, n - r0);
@@ -192,14 +198,18 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
 __global__ void __launch_bounds__(kBlock)
 reduce_allreduce_kernel(const double* __restrict__ partials, int np, int k, hg_peer_tbl t,
                         size_t inbox_off, unsigned int epoch, double* __restrict__ out,
-                        double* __restrict__ acc, int accumulate, int do_sqrt, unsigned long long* err) {
+                        double* __restrict__ acc, int accumulate, int do_sqrt, int barrier,
+                        const double* __restrict__ partials2, int np2, unsigned long long* err) {
     __shared__ double s_red[32];
     __shared__ double s_part[HG_MAX_PEERS];
     const int j = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double* p = partials + (int64_t)j * np;
+    // the last column may come from a second partials array (two statistics in one exchange)
+    const bool second = partials2 != nullptr && j == k - 1;
+    const double* p = second ? partials2 : partials + (int64_t)j * np;
+    const int cnt = second ? np2 : np;
     double v = 0.0;
-    for (int i = threadIdx.x; i < np; i += blockDim.x) v += p[i];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) v += p[i];
     v = warp_sum(v);
     if (lane == 0) s_red[warp] = v;
     __syncthreads();
@@ -207,9 +217,9 @@ reduce_allreduce_kernel(const double* __restrict__ partials, int np, int k, hg_p
         v = lane < (kBlock >> 5) ? s_red[lane] : 0.0;
         v = warp_sum(v);  // every lane of warp 0 holds this rank's sum j
         if (lane < t.P) {
-            // earlier kernels' stores to peer memory (the pushed basis rows) are ordered before the
-            // words that announce them
-            __threadfence_system();
+            // barrier: earlier kernels' stores to peer memory (the pushed basis rows) are ordered before the
+            // words that announce them.  A plain all-reduce needs no fence: a word carries its own epoch.
+            if (barrier) __threadfence_system();
             const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
             unsigned long long* dst = reinterpret_cast<unsigned long long*>(t.base[lane] + inbox_off) +
                                       ((size_t)j * t.P + t.rank) * 2;
@@ -235,7 +245,7 @@ reduce_allreduce_kernel(const double* __restrict__ partials, int np, int k, hg_p
             // acquire side of the exchange: this all-reduce is also the barrier that makes the rows peers
             // pushed into our replicated vector visible to the kernels that follow, so order every later
             // read after the observed epochs (the sender fences before its store)
-            __threadfence_system();
+            if (barrier) __threadfence_system();
             s_part[lane] = ok ? __longlong_as_double((long long)((w0 >> 32) | (w1 & 0xffffffff00000000ull))) : 0.0;
         }
         __syncwarp();
@@ -492,24 +502,32 @@ int hg_k_peer_signal(hg_comm* c, int row) {
 }
 
 int hg_k_pull_multidot(hg_comm* c, int64_t row0, const double* q_slice, double shift, double* w_out,
-                       const double* V, int64_t ld, int64_t n_p, int k, double* partials, int* nslabs) {
+                       const double* V, int64_t ld, int64_t n_p, int k, double* partials, int* nslabs, bool signal) {
     hg_ctx* ctx = c->ctx;
+    if (signal) ++c->bar_seq[HG_FLAG_Y];
     const int R = hg_multidot_slab_rows(ctx, n_p);
     const int ns = (int)cdiv(n_p, R);
     if (nslabs) *nslabs = ns;
-    if (n_p <= 0) return HG_OK;
-    // waits for the epoch of the latest hg_k_peer_signal(HG_FLAG_Y)
+    if (n_p <= 0) {  // nothing to pull here, but the peers still wait for this rank's signal
+        if (signal) {
+            --c->bar_seq[HG_FLAG_Y];
+            return hg_k_peer_signal(c, HG_FLAG_Y);
+        }
+        return HG_OK;
+    }
+    // waits for the epoch of the latest HG_FLAG_Y signal (sent here when `signal`, else by hg_k_peer_signal)
     // local reads: V_k and q slice; remote/local pulls: P slices; write w
     hg_launch_scope scope(ctx, HG_K_MULTIDOT, 8.0 * (double)n_p * (double)(k + c->nranks + 2));
     pull_multidot_kernel<<<ns, kDotWarps * 32, R * sizeof(double), ctx->stream>>>(
-        c->tbl, c->lay.ypart, c->lay.flags + (size_t)HG_FLAG_Y * HG_MAX_PEERS * 8, c->bar_seq[HG_FLAG_Y], c->d_err,
+        c->tbl, c->lay.ypart, c->lay.flags + (size_t)HG_FLAG_Y * HG_MAX_PEERS * 8, c->bar_seq[HG_FLAG_Y],
+        signal ? 1 : 0, c->d_err,
         row0, q_slice, shift, w_out, V, ld, n_p, k, partials, ns, R);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }
 
 int hg_k_reduce_allreduce(hg_comm* c, const double* partials, int np, int k, double* out, double* acc,
-                          bool accumulate, bool do_sqrt) {
+                          bool accumulate, bool do_sqrt, bool barrier, const double* partials2, int np2) {
     if (k <= 0) return HG_OK;
     hg_ctx* ctx = c->ctx;
     HG_REQUIRE(k <= c->lay.kpad, "peer all-reduce: %d coefficients exceed the inbox (%d)", k, c->lay.kpad);
@@ -518,7 +536,8 @@ int hg_k_reduce_allreduce(hg_comm* c, const double* partials, int np, int k, dou
     const unsigned int epoch = (unsigned int)(seq % 0xfffffffeull) + 1u;  // never 0 (= empty inbox)
     hg_launch_scope scope(ctx, HG_K_REDUCE, 8.0 * (double)np * (double)k + 32.0 * k * c->nranks);
     reduce_allreduce_kernel<<<k, kBlock, 0, ctx->stream>>>(partials, np, k, c->tbl, inbox_off, epoch, out, acc,
-                                                            accumulate ? 1 : 0, do_sqrt ? 1 : 0, c->d_err);
+                                                            accumulate ? 1 : 0, do_sqrt ? 1 : 0, barrier ? 1 : 0,
+                                                            partials2, np2, c->d_err);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }

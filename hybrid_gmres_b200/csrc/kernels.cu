@@ -490,7 +490,7 @@ static double spmv_bytes(const hg_matrix* m, const hg_spmv_epilogue& ep, bool st
     double idx = 4.0 * (double)m->nnz;
     if (m->sell_state > 0 && m->sell_col8) idx = 1.0 * (double)m->nnz + 16.0 * (double)(m->sell_entries / 128);
     else if (m->sell_state > 0 && m->sell_col16) idx = 2.0 * (double)m->nnz + 4.0 * (double)(m->sell_entries / 128);
-    else if (m->sell_state <= 0 && m->grp_state > 0 && m->grp_d16) idx = 2.0 * (double)m->nnz + 128.0 * (double)m->grp_groups;
+    else if (m->sell_state <= 0 && m->grp_state > 0 && m->grp_d16) idx = 2.0 * (double)m->nnz + 128.0 * (double)m->grp_groups;  // one 32-lane checkpoint read per warp
     else if (m->sell_state <= 0 && m->csr16_state > 0) idx = 2.0 * (double)m->nnz + 4.0 * (double)m->csr_groups + 8.0 * (double)m->rows;
     double b = 8.0 * (double)m->nnz + idx + 8.0 * (double)(m->rows + 1) + 8.0 * (double)m->cols;
     if (store) b += 8.0 * (double)m->rows;

@@ -88,8 +88,11 @@ __global__ void group_fill_kernel(int64_t rows, int64_t ngroups, const int64_t* 
     }
 }
 
-// the same rounds with the column stream as per-lane differences: col0[g*32 + lane] is the lane's first column,
-// d16[i] = column(i) - column(i - 32) (0 in the first round); *overflow is set when a difference leaves int16
+// the same rounds with the column stream as per-lane differences: d16[i] = column(i) - column(i - 32) (0 in the first
+// round); col0 holds kChunks checkpoints per group — the lane's column on entering round (c * rounds) / kChunks — so
+// that up to kChunks warps can share a group, each starting in the middle of the chain; *overflow is set when a
+// difference leaves int16
+constexpr int kChunks = 4;
 template <int G>
 __global__ void group_fill16_kernel(int64_t rows, int64_t ngroups, const int64_t* __restrict__ rowptr,
                                     const int32_t* __restrict__ colind, const double* __restrict__ vals,
@@ -105,11 +108,16 @@ __global__ void group_fill16_kernel(int64_t rows, int64_t ngroups, const int64_t
     const int64_t len = row < rows ? rowptr[row + 1] - rs : 0;
     const int pad_col = len > 0 ? colind[rs + len - 1] : 0;
     const int64_t s = gptr[g], e = gptr[g + 1];
+    const int64_t R = (e - s) >> 5;
     int prev = e0 < len ? colind[rs + e0] : pad_col;
-    col0[g * 32 + lane] = prev;
     bool bad = false;
     int64_t t = 0;
+    int next_chunk = 0;
     for (int64_t i = s + lane; i < e; i += 32, ++t) {
+        while (next_chunk < kChunks && t == (next_chunk * R) / kChunks) {
+            col0[(g * kChunks + next_chunk) * 32 + lane] = prev;
+            ++next_chunk;
+        }
         const int64_t k = t * E + e0;
         const bool ok = k < len;
         const int c = ok ? colind[rs + k] : pad_col;
@@ -119,10 +127,14 @@ __global__ void group_fill16_kernel(int64_t rows, int64_t ngroups, const int64_t
         gval[i] = ok ? vals[rs + k] : 0.0;
         prev = c;
     }
+    for (; next_chunk < kChunks; ++next_chunk) col0[(g * kChunks + next_chunk) * 32 + lane] = prev;  // empty chunks
     if (bad) atomicExch(overflow, 1);
 }
 
-template <int G>
+// S warps share a group (S = 1, 2 or 4): warp `part` walks the rounds of its kChunks / S chunks from the chunk's
+// checkpoint; the S partial sums of a row are added in a fixed order through shared memory.  Few rows (a rank's
+// shard of A on 8 GPUs: 8 326 groups) otherwise leave the machine under-filled with 4-row warps.
+template <int G, int S>
 __global__ void __launch_bounds__(kBlock)
 spmv_group16_kernel(int64_t rows, int64_t ngroups, const int64_t* __restrict__ gptr, const int* __restrict__ col0,
                     const short* __restrict__ d16, const double* __restrict__ gval, const double* __restrict__ x,
@@ -131,11 +143,17 @@ spmv_group16_kernel(int64_t rows, int64_t ngroups, const int64_t* __restrict__ g
                     double* __restrict__ stat) {
     constexpr int E = 32 / G;
     constexpr int U = 4;
-    const int lane = threadIdx.x & 31;
-    const int64_t g = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    constexpr int NW = kBlock / 32;
+    static_assert(kChunks % S == 0 && NW % S == 0, "warps per group");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int part = warp % S;
+    const int64_t g = (int64_t)blockIdx.x * (NW / S) + warp / S;
     const bool live = g < ngroups;
-    const int64_t s = live ? gptr[g] : 0;
-    const int64_t e = live ? gptr[g + 1] : 0;
+    const int64_t gs = live ? gptr[g] : 0;
+    const int64_t R = live ? (gptr[g + 1] - gs) >> 5 : 0;
+    const int c0 = part * (kChunks / S);
+    const int64_t s = gs + ((c0 * R) / kChunks) * 32;
+    const int64_t e = gs + (((c0 + kChunks / S) * R) / kChunks) * 32;
     // same software pipeline as spmv_group_kernel; the running column of the lane is carried through the rounds
     double a[U];
     int d[U];
@@ -143,7 +161,7 @@ spmv_group16_kernel(int64_t rows, int64_t ngroups, const int64_t* __restrict__ g
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) a[u] = 0.0;
-    int col = live ? col0[g * 32 + lane] : 0;
+    int col = live ? col0[(g * kChunks + c0) * 32 + lane] : 0;
     int64_t i = s + lane;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -156,7 +174,7 @@ spmv_group16_kernel(int64_t rows, int64_t ngroups, const int64_t* __restrict__ g
         double xg[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            col += d[u];  // 0 past the end of the group: the column stays on its last line
+            col += d[u];  // 0 past the end of the chunk: the column stays on its last line
             xg[u] = ok[u] ? __ldg(x + col) : 0.0;
         }
         const int64_t in = i + U * 32;
@@ -182,9 +200,19 @@ spmv_group16_kernel(int64_t rows, int64_t ngroups, const int64_t* __restrict__ g
     double sum = (a[0] + a[1]) + (a[2] + a[3]);
 #pragma unroll
     for (int o = E / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);  // the E lanes of a row
+    if (S > 1) {
+        __shared__ double s_part[NW][32];
+        s_part[warp][lane] = sum;
+        __syncthreads();
+        if (part == 0) {
+            sum = 0.0;
+#pragma unroll
+            for (int t = 0; t < S; ++t) sum += s_part[warp + t][lane];
+        }
+    }
     double sq = 0.0;
     const int64_t row = g * G + lane / E;
-    if (live && (lane % E) == 0 && row < rows) {
+    if (live && part == 0 && (lane % E) == 0 && row < rows) {
         double out = alpha * sum;
         if (z1) out += g1 * z1[row];
         if (z2) out += g2 * z2[row];
@@ -195,14 +223,14 @@ spmv_group16_kernel(int64_t rows, int64_t ngroups, const int64_t* __restrict__ g
         }
     }
     if (stat) {
-        __shared__ double s_red[kBlock / 32];
+        __shared__ double s_red[NW];
         sq = warp_sum(sq);
-        if (lane == 0) s_red[threadIdx.x >> 5] = sq;
+        if (lane == 0) s_red[warp] = sq;
         __syncthreads();
         if (threadIdx.x == 0) {
             double t = 0.0;
 #pragma unroll
-            for (int w = 0; w < kBlock / 32; ++w) t += s_red[w];
+            for (int w = 0; w < NW; ++w) t += s_red[w];
             stat[blockIdx.x] = t;
         }
     }
@@ -332,7 +360,7 @@ bool build(hg_ctx* ctx, hg_matrix* m) {
         int flag = 1;
         cudaError_t b = hg_dmalloc(ctx, &d_flag, sizeof(int));
         if (b == cudaSuccess) b = cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream);
-        if (b == cudaSuccess) b = hg_dmalloc(ctx, &m->grp_col0, (size_t)ngroups * 32 * 4);
+        if (b == cudaSuccess) b = hg_dmalloc(ctx, &m->grp_col0, (size_t)ngroups * kChunks * 32 * 4);
         if (b == cudaSuccess) b = hg_dmalloc(ctx, &m->grp_d16, (size_t)(acc + kNnzPad) * 2);
         if (b == cudaSuccess) {
             hg_launch_scope scope(ctx, HG_K_SETUP, 22.0 * (double)m->nnz);
@@ -394,6 +422,27 @@ int hg_spmv_group16() {
     return g_group16;
 }
 void hg_spmv_group16_set(int v) { g_group16 = v != 0 ? 1 : 0; }
+// warps per group of the 16-bit form: option "spmv_group_split" / env HG_SPMV_GROUP_SPLIT = 1, 2, 4; 0 (default): by size
+static int g_group_split = -1;
+int hg_spmv_group_split() {
+    if (g_group_split < 0) {
+        const char* e = getenv("HG_SPMV_GROUP_SPLIT");
+        const int v = e ? atoi(e) : 0;
+        g_group_split = (v == 1 || v == 2 || v == 4) ? v : 0;
+    }
+    return g_group_split;
+}
+void hg_spmv_group_split_set(int v) { g_group_split = (v == 1 || v == 2 || v == 4) ? v : 0; }
+// smallest matrix that takes the row-group form by default: option "spmv_group_min_rows" / env HG_SPMV_GROUP_MIN_ROWS
+static int64_t g_group_min_rows = -1;
+int64_t hg_spmv_group_min_rows() {
+    if (g_group_min_rows < 0) {
+        const char* e = getenv("HG_SPMV_GROUP_MIN_ROWS");
+        g_group_min_rows = e ? atoll(e) : 16384;
+    }
+    return g_group_min_rows;
+}
+void hg_spmv_group_min_rows_set(int v) { g_group_min_rows = v < 0 ? 16384 : v; }
 
 // rows per group of the interleaved form: option "spmv_group" / env HG_SPMV_GROUP = 0 (off), 2, 4 or 8
 int hg_spmv_group() {
@@ -426,7 +475,7 @@ bool hg_group_ready(hg_ctx* ctx, const hg_matrix* cm) {
     m->grp_state = -1;
     // rows of >= 128 entries on average; small shards (a rank's 33 304 rows at 8 GPUs: 89 vs 73 us) under-fill
     // the machine with 4-row warps, so they keep the row-per-warp kernel
-    if (m->rows < (g_group_explicit ? 1024 : 100000) || m->nnz < 128 * m->rows) return false;
+    if (m->rows < (g_group_explicit ? 1024 : hg_spmv_group_min_rows()) || m->nnz < 128 * m->rows) return false;
     bool ok = false;
     if (G == 2) ok = build<2>(ctx, m);
     else if (G == 4) ok = build<4>(ctx, m);
@@ -456,11 +505,28 @@ int hg_k_spmv_group(hg_ctx* ctx, const hg_matrix* m, const double* x, double* y,
     if (nparts && ep.stat) *nparts = (int)grid;
     hg_launch_scope scope(ctx, HG_K_SPMV, bytes);
     if (m->grp_d16) {
+        // several waves of warps: with fewer groups than ~4 x 48 warps per SM, S warps share a group
+        int S = hg_spmv_group_split();
+        if (S <= 0) {
+            const int64_t target = (int64_t)ctx->sm_count * 48 * 4;
+            S = 1;
+            while (S < kChunks && m->grp_groups * S < target) S *= 2;
+        }
+        while (S > m->grp_G) S /= 2;  // at most one warp per row: the grid (= residual partials) stays <= rows / 8
+        const int64_t grid16 = cdiv(m->grp_groups * S, kBlock / 32);
+        if (nparts && ep.stat) *nparts = (int)grid16;
 #define HG_GRP16_ARGS m->rows, m->grp_groups, m->grp_ptr, m->grp_col0, m->grp_d16, m->grp_val, x, y, ep.alpha, ep.z1, ep.g1, \
                       ep.z2, ep.g2, ep.ref, ep.stat
-        if (m->grp_G == 2) spmv_group16_kernel<2><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_GRP16_ARGS);
-        else if (m->grp_G == 4) spmv_group16_kernel<4><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_GRP16_ARGS);
-        else spmv_group16_kernel<8><<<(unsigned)grid, kBlock, 0, ctx->stream>>>(HG_GRP16_ARGS);
+#define HG_GRP16_LAUNCH(G)                                                                                          \
+    do {                                                                                                            \
+        if (S == 1) spmv_group16_kernel<G, 1><<<(unsigned)grid16, kBlock, 0, ctx->stream>>>(HG_GRP16_ARGS);         \
+        else if (S == 2) spmv_group16_kernel<G, 2><<<(unsigned)grid16, kBlock, 0, ctx->stream>>>(HG_GRP16_ARGS);    \
+        else spmv_group16_kernel<G, 4><<<(unsigned)grid16, kBlock, 0, ctx->stream>>>(HG_GRP16_ARGS);                \
+    } while (0)
+        if (m->grp_G == 2) HG_GRP16_LAUNCH(2);
+        else if (m->grp_G == 4) HG_GRP16_LAUNCH(4);
+        else HG_GRP16_LAUNCH(8);
+#undef HG_GRP16_LAUNCH
 #undef HG_GRP16_ARGS
         HG_CUDA(cudaGetLastError());
         return HG_OK;

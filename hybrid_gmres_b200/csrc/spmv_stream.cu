@@ -295,6 +295,14 @@ extern "C" int hg_set_option(const char* name, int value) {
         hg_idx8_set(value);
         return HG_OK;
     }
+    if (strcmp(name, "spmv_group_split") == 0) {
+        hg_spmv_group_split_set(value);
+        return HG_OK;
+    }
+    if (strcmp(name, "spmv_group_min_rows") == 0) {
+        hg_spmv_group_min_rows_set(value);
+        return HG_OK;
+    }
     if (strcmp(name, "spmv_group16") == 0) {
         hg_spmv_group16_set(value);
         return HG_OK;

@@ -515,13 +515,21 @@ def test_spmv_row_group_form_matches_csr(hg, ctx, G):
         assert np.array_equal(y1, y2)
         assert np.max(np.abs(y1 - y0)) <= 1e-13 * np.max(np.abs(y0))
         assert np.max(np.abs(y1 - M @ x)) <= 1e-13 * np.max(np.abs(y0))
-        # 32-bit column stream: same rounds, same sums -> identical bits
+        # several warps per group (small matrices; default by size): chunks of the rounds from column checkpoints
+        ysplit = {}
+        for S in (1, 2, 4):
+            hg.set_option("spmv_group_split", S)
+            ysplit[S] = d1.matvec(x)
+            assert np.array_equal(d1.matvec(x), ysplit[S])
+            assert np.max(np.abs(ysplit[S] - y0)) <= 1e-13 * np.max(np.abs(y0))
+        # 32-bit column stream: same rounds, same sums as one warp per group -> identical bits
         hg.set_option("spmv_group16", 0)
         d2 = hg.DeviceMatrix.from_csr(M.indptr, M.indices, M.data, M.shape, ctx)
         if form0 == "csr":
             assert d2.spmv_form == "group" and d2.spmv_index_bits == 32
-        assert np.array_equal(d2.matvec(x), y1)
+            assert np.array_equal(d2.matvec(x), ysplit[1]) or d1.spmv_index_bits == 32
         hg.set_option("spmv_group16", 1)
+        hg.set_option("spmv_group_split", 0)
         # a matrix whose rows jump by more than int16 between rounds falls back to the 32-bit stream
         rng = np.random.default_rng(9)
         nr, per, stride = 2048, 256, 10000
@@ -541,4 +549,5 @@ def test_spmv_row_group_form_matches_csr(hg, ctx, G):
         assert its == ito and np.max(np.abs(rs - ro) / ro) < 1e-8 and np.max(np.abs(es - eo) / eo) < 1e-8
     finally:
         hg.set_option("spmv_group16", 1)
+        hg.set_option("spmv_group_split", 0)
         hg.set_option("spmv_group", -1)  # back to the default (G = 4 for matrices of >= 100 000 rows)
