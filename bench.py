@@ -302,7 +302,8 @@ def measure_arnoldi(args, hg, ctx, torch, dist, rank, world, local_rank, workloa
               "nspace_order": args.nspace_order,
               "spmv_form": {"A": f"{dA.spmv_form}/idx{dA.spmv_index_bits}", "B": f"{dB.spmv_form}/idx{dB.spmv_index_bits}"},
               "parallelism": "single",
-              "l2": "inputs (A+B = %.1f GB) exceed the 126 MB L2; no flush needed" % ((nnzA + nnzB) * 12 / 1e9)}
+              "l2": "inputs (A+B = %.1f GB as CSR, >= %.1f GB in the compressed-index forms the kernels stream) exceed the "
+                    "126 MB L2; no flush needed" % ((nnzA + nnzB) * 12 / 1e9, (nnzA + nnzB) * 9 / 1e9)}
     if sharded:
         from hybrid_gmres_b200.distributed import ShardedArnoldi
         ar = ShardedArnoldi(comm, dA, dB, maxit)
