@@ -79,6 +79,14 @@ int hg_version(void);
  * "spmv_group" / env HG_SPMV_GROUP (default 4; 0 off, 2, 4, 8): long-row matrices that run the row-per-warp
  * kernel (ray-driven projectors) get a copy in which G adjacent rows are interleaved per warp, so a warp-wide
  * gather serves G adjacent rays from the same cache lines (csrc/spmv_group.cu: L1 wavefronts 66 % -> 48 %).
+ * "spmv_group16" / HG_SPMV_GROUP16 (default 1): that copy stores its columns as 16-bit per-lane differences (10
+ * instead of 12 bytes per non-zero; automatic 32-bit fall-back).  "spmv_group_split" / HG_SPMV_GROUP_SPLIT (0 = by
+ * size; 1, 2, 4): warps sharing one group.  "spmv_group_min_rows" / HG_SPMV_GROUP_MIN_ROWS (default 16384): smallest
+ * matrix that takes the form by default.
+ * "spmv_idx16" / env HG_IDX16 (default 1; 0 off; 2 also the row-per-warp kernel): 16-bit column offsets from a base
+ * per 128 entries in the sliced form.  "spmv_idx8" / env HG_IDX8 (-1 default: matrices of >= 131 072 rows; 1 always;
+ * 0 never): byte offsets from a base per slice column (9.1 bytes per non-zero) when every slice column spans < 256.
+ * All index widths give bit-identical products.
  * "dist_transport": see hg_comm_transport. */
 int hg_set_option(const char* name, int value);
 
