@@ -157,18 +157,34 @@ cgs_mid_staged_kernel(const double* __restrict__ V, int64_t ld, int64_t n, int k
         double2 wv[NP];
 #pragma unroll
         for (int p = 0; p < NP; ++p) wv[p] = reinterpret_cast<const double2*>(w1t)[32 * p + lane];
+        if (r0 + TR <= n) {  // CTA-uniform: every row of the tile is real (all tiles but possibly the last one)
 #pragma unroll
-        for (int c = 0; c < CPW; ++c) {
-            const int j = warp + kWarps * c;
-            if (j < k) {
-                const double2* col = reinterpret_cast<const double2*>(sv + (size_t)j * TR) + lane;
+            for (int c = 0; c < CPW; ++c) {
+                const int j = warp + kWarps * c;
+                if (j < k) {
+                    const double2* col = reinterpret_cast<const double2*>(sv + (size_t)j * TR) + lane;
 #pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    const double2 v = KEEP ? keep[KEEP ? c : 0][KEEP ? p : 0] : col[32 * p];
-                    // a pair straddling n: its first row is real, its second is padding
-                    const bool first = r0 + 64 * p + 2 * lane < n;
-                    accB[c] = fma(first ? v.x : 0.0, wv[p].x, accB[c]);
-                    accB[c] = fma(live[p] ? v.y : 0.0, wv[p].y, accB[c]);
+                    for (int p = 0; p < NP; ++p) {
+                        const double2 v = KEEP ? keep[KEEP ? c : 0][KEEP ? p : 0] : col[32 * p];
+                        accB[c] = fma(v.x, wv[p].x, accB[c]);
+                        accB[c] = fma(v.y, wv[p].y, accB[c]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) {
+                const int j = warp + kWarps * c;
+                if (j < k) {
+                    const double2* col = reinterpret_cast<const double2*>(sv + (size_t)j * TR) + lane;
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        const double2 v = KEEP ? keep[KEEP ? c : 0][KEEP ? p : 0] : col[32 * p];
+                        // a pair straddling n: its first row is real, its second is padding
+                        const bool first = r0 + 64 * p + 2 * lane < n;
+                        accB[c] = fma(first ? v.x : 0.0, wv[p].x, accB[c]);
+                        accB[c] = fma(live[p] ? v.y : 0.0, wv[p].y, accB[c]);
+                    }
                 }
             }
         }
