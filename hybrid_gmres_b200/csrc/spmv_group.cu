@@ -473,8 +473,8 @@ bool hg_group_ready(hg_ctx* ctx, const hg_matrix* cm) {
     std::lock_guard<std::mutex> lk(hg_matrix_form_mutex());
     if (m->grp_state != 0) return m->grp_state > 0 && m->grp_G == G;
     m->grp_state = -1;
-    // rows of >= 128 entries on average; small shards (a rank's 33 304 rows at 8 GPUs: 89 vs 73 us) under-fill
-    // the machine with 4-row warps, so they keep the row-per-warp kernel
+    // rows of >= 128 entries on average.  Small matrices run with several warps per group (hg_k_spmv_group); below
+    // ~16 000 rows even that under-fills the machine (a rank's 8 326-row shard of the 256^2 problem: 15.4 vs 15.0 us)
     if (m->rows < (g_group_explicit ? 1024 : hg_spmv_group_min_rows()) || m->nnz < 128 * m->rows) return false;
     bool ok = false;
     if (G == 2) ok = build<2>(ctx, m);

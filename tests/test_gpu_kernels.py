@@ -550,4 +550,4 @@ def test_spmv_row_group_form_matches_csr(hg, ctx, G):
     finally:
         hg.set_option("spmv_group16", 1)
         hg.set_option("spmv_group_split", 0)
-        hg.set_option("spmv_group", -1)  # back to the default (G = 4 for matrices of >= 100 000 rows)
+        hg.set_option("spmv_group", -1)  # back to the default (G = 4 for matrices of >= 16 384 rows)
