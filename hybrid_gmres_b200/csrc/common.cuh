@@ -230,6 +230,13 @@ int hg_k_scale_div(hg_ctx* ctx, double* v, int64_t n, const double* d_div);
 int hg_k_axpby(hg_ctx* ctx, int64_t n, double a, const double* x, double b, const double* y,
                double* out, const double* ref, double* stat, int* nparts);
 // LSQR: x += c1*w ; w = v - c2*w ; stat of (x - ref)^2   (hybrid_lsqr_solver.m:39-42)
+// d = a*u_old + b*u_new - (first ? 0 : cprev*d);  [d2 = d - (first ? 0 : c0*d2);]  r -= step*(d2 ? d2 : d);
+// stat: partials of r.^2 (LSQR / LSMR residual from the Golub-Kahan relation, gkb.cu)
+int hg_k_gkb_resid(hg_ctx* ctx, int64_t n, const double* u_old, double a, const double* u_new, double b, double* d,
+                   double cprev, double* d2, double c0, bool first, double* r, double step, double* stat,
+                   int* nparts);
+int hg_gkb_residual_mode();  // 0 (default): residuals of the GKB solvers from the Golub-Kahan relation; 1: b - A*x by SpMV
+void hg_gkb_residual_mode_set(int v);
 int hg_k_lsqr_update(hg_ctx* ctx, int64_t n, double* x, double* w, const double* v, double c1,
                      double c2, const double* ref, double* stat, int* nparts);
 // LSMR: hbar = h - c0*hbar (or hbar = h when first); x += c1*hbar; h = v - c2*h

@@ -245,9 +245,20 @@ int hybrid_lsqr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
         extras->aux[0] = alpha_aug;
         extras->aux[maxit + 1] = beta_aug;
     }
+    // norm(b - A*x) (:43) without a third product per iteration: r_k and d_k = A*w_k follow from the Golub-Kahan
+    // relation A*v_k = alpha_k*u_k + beta_{k+1}*u_{k+1} (hg_k_gkb_resid); gkb_residual = 1 forms b - A*x literally
+    const bool literal_res = hg_gkb_residual_mode() == 1;
+    DBuf bd, br;
+    if (!literal_res) {
+        HG_TRY(bd.alloc(m));
+        HG_TRY(br.alloc(m));
+        if (m) HG_CUDA(cudaMemcpyAsync(br.p, g.b.p, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));  // r_0 = b
+    }
+    double c_prev = 0.0;
     int k, pending = 0;
     bool stopped = false;
     for (k = 1; k <= maxit; ++k) {
+        const double alpha_k = alpha_aug;
         // u_hat = A_aug*v - alpha*u                               (:22)
         int np1 = 0, np2 = 0;
         HG_TRY(g.apply_A(v, t1, 1.0, u1, -alpha_aug, nullptr, true, 0, &np1));
@@ -283,7 +294,14 @@ int hybrid_lsqr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
         // x, w updates + error                                   (:39-42)
         HG_TRY(hg_k_lsqr_update(ctx, nl, dx, w, v, phi / rho, theta / rho, g.xt.p, g.stat.p, &np));
         HG_TRY(g.enqueue_norm(np, 20));               // :42
-        HG_TRY(g.residual_enqueue(dx, nullptr, 21));  // :43
+        if (literal_res) {
+            HG_TRY(g.residual_enqueue(dx, nullptr, 21));  // :43
+        } else {  // t1 holds u_k (top block), u1 holds u_{k+1}
+            HG_TRY(hg_k_gkb_resid(ctx, m, t1, alpha_k, u1, beta_aug, bd.p, c_prev, nullptr, 0.0, k == 1, br.p, phi / rho,
+                                  g.stat.p, &np));
+            HG_TRY(g.enqueue_norm(np, 21));
+            c_prev = theta / rho;
+        }
         HG_TRY(g.hist_copy(k));
         pending = k;
         if (extras && extras->aux) {
@@ -318,10 +336,22 @@ int hybrid_lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
     const int64_t m = g.m, nl = g.nl, n = g.n;
     cudaStream_t st = ctx->stream;
     const int64_t ldv = round_up(std::max<int64_t>(nl, 1), 32);
-    DBuf bu, bt, bV, bx, by;
-    HG_TRY(bu.alloc(m)); HG_TRY(bt.alloc(m)); HG_TRY(bV.alloc((size_t)ldv * maxit, st, true));
+    // norm(b - A*x) (:48) without a third product per iteration: A*V_k = U_{k+1}*B_k (Golub-Kahan relation), so
+    // b - A*V_k*y = U_{k+1}*(beta1*e1 - B_k*y): the u vectors are kept (m x (maxit+1)) and the residual is one
+    // combination of k+1 columns; gkb_residual = 1 forms b - A*x literally
+    const bool literal_res = hg_gkb_residual_mode() == 1;
+    const int64_t ldu = round_up(std::max<int64_t>(m, 1), 32);
+    DBuf bu, bt, bV, bx, by, bU, bz;
+    if (literal_res) {
+        HG_TRY(bu.alloc(m));
+        HG_TRY(bt.alloc(m));
+    } else {
+        HG_TRY(bU.alloc((size_t)ldu * (maxit + 1), st, true));
+        HG_TRY(bz.alloc(maxit + 1));
+    }
+    HG_TRY(bV.alloc((size_t)ldv * maxit, st, true));
     HG_TRY(bx.alloc(nl, st, true)); HG_TRY(by.alloc(maxit));
-    double *u = bu.p, *t = bt.p, *V = bV.p, *dx = bx.p;
+    double *u = literal_res ? bu.p : bU.p, *t = literal_res ? bt.p : bU.p + ldu, *V = bV.p, *dx = bx.p;
     std::vector<double> Bk((size_t)(maxit + 1) * maxit, 0.0);  // (maxit+1) x maxit col-major
     const int ldb = maxit + 1;
     double beta1 = 0, alpha1 = 0;
@@ -339,7 +369,7 @@ int hybrid_lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
         double* p = nullptr;
         ~PinY() { hg_hfree(p); }
     } hy;
-    if (hg_hmalloc_cur((void**)&hy.p, (size_t)2 * maxit * sizeof(double)) != cudaSuccess) {
+    if (hg_hmalloc_cur((void**)&hy.p, (size_t)2 * (2 * maxit + 1) * sizeof(double)) != cudaSuccess) {
         hg_set_error("hybrid_lsmr: pinned allocation failed");
         return HG_ERR_NOMEM;
     }
@@ -363,7 +393,12 @@ int hybrid_lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
             }
         }
         HG_TRY(hg_k_scale_div(ctx, t, m, g.ds + 5));  // :26
-        swap_ptr(u, t);
+        if (literal_res) {
+            swap_ptr(u, t);
+        } else {  // U(:,k+1) stays where it is; the next u_hat goes to the next column
+            u = t;
+            t = u + ldu;
+        }
         Bk[(size_t)(k - 1) * ldb + k] = beta_k;  // :27
         if (k < maxit) {                          // :29-35
             double* vn = V + (size_t)k * ldv;
@@ -398,13 +433,27 @@ int hybrid_lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_ma
         for (int i = 0; i < k; ++i) LHS[(size_t)i * k + i] += lambda;
         RHS.assign(k, 0.0);
         for (int i = 0; i < k; ++i) RHS[i] = Bk[0] * beta1 * T[i];  // B_k(1,1)*beta1*(T*e1)
-        double* yk = hy.p + (size_t)(k & 1) * maxit;  // pinned, two slots: no wait for the upload
+        double* yk = hy.p + (size_t)(k & 1) * (2 * maxit + 1);  // pinned, two slots: no wait for the upload
         hgd::solve_square(k, LHS.data(), k, RHS.data(), yk);
         HG_CUDA(cudaMemcpyAsync(by.p, yk, (size_t)k * 8, cudaMemcpyHostToDevice, st));
         // x = V(:,1:k)*yk + error                                 (:45,47)
         HG_TRY(hg_k_lincomb(ctx, V, ldv, nl, k, by.p, 1.0, nullptr, dx, g.xt.p, g.stat.p, &np));
         HG_TRY(g.enqueue_norm(np, 20));
-        HG_TRY(g.residual_enqueue(dx, nullptr, 21));  // :48
+        if (literal_res) {
+            HG_TRY(g.residual_enqueue(dx, nullptr, 21));  // :48
+        } else {
+            // z = beta1*e1 - B_k*y (B_k lower bidiagonal, (k+1) x k); residual = || U(:,1:k+1) * z ||
+            double* zk = yk + maxit;
+            for (int i = 0; i <= k; ++i) {
+                double acc = 0.0;
+                if (i >= 1) acc += Bk[(size_t)(i - 1) * ldb + i] * yk[i - 1];  // beta_{i+1} y_i
+                if (i < k) acc += Bk[(size_t)i * ldb + i] * yk[i];             // alpha_{i+1} y_{i+1}
+                zk[i] = (i == 0 ? beta1 : 0.0) - acc;
+            }
+            HG_CUDA(cudaMemcpyAsync(bz.p, zk, (size_t)(k + 1) * 8, cudaMemcpyHostToDevice, st));
+            HG_TRY(hg_k_lincomb(ctx, bU.p, ldu, m, k + 1, bz.p, 1.0, nullptr, nullptr, nullptr, g.stat.p, &np));
+            HG_TRY(g.enqueue_norm(np, 21));
+        }
         HG_TRY(g.hist_copy(k));
         pending = k;
         if (extras && extras->X_hist) HG_TRY(g.fetch_x(dx, extras->X_hist + (size_t)(k - 1) * n));
@@ -510,10 +559,19 @@ int lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* A
     HG_TRY(g.init(ctx, comm, A, At, b, x_true));
     const int64_t m = g.m, nl = g.nl, n = g.n;
     cudaStream_t st = ctx->stream;
-    DBuf bu, bt, bv, bt3, bh, bhb, bx, br;
+    DBuf bu, bt, bv, bt3, bh, bhb, bx, br, bah, bahb;
     HG_TRY(bu.alloc(m)); HG_TRY(bt.alloc(m)); HG_TRY(bv.alloc(nl, st, true)); HG_TRY(bt3.alloc(nl, st, true));
     HG_TRY(bh.alloc(nl)); HG_TRY(bhb.alloc(nl, st, true)); HG_TRY(bx.alloc(nl, st, true)); HG_TRY(br.alloc(m));
     double *u = bu.p, *t = bt.p, *v = bv.p, *t3 = bt3.p, *h = bh.p, *hbar = bhb.p, *dx = bx.p, *r = br.p;
+    // r = b - A*x (:69) from the Golub-Kahan relation (A*h_k and A*hbar_k by recurrence, hg_k_gkb_resid) instead of
+    // a product with A; the product A'*r of :71 stays.  gkb_residual = 1 forms b - A*x literally.
+    const bool literal_res = hg_gkb_residual_mode() == 1;
+    if (!literal_res) {
+        HG_TRY(bah.alloc(m));
+        HG_TRY(bahb.alloc(m));
+        if (m) HG_CUDA(cudaMemcpyAsync(r, g.b.p, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));  // r_0 = b
+    }
+    double c_prev = 0.0;
     // norm(A,'fro'): recomputed every iteration by the reference (:71), constant here
     int np = 0;
     double normA = 0;
@@ -544,6 +602,7 @@ int lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* A
         if (g.have_xt) err_hist[j - 1] = en / g.norm_xt;
     };
     for (k = 1; k <= maxit; ++k) {
+        const double alpha_k = alpha;
         HG_TRY(g.apply_A(v, t, 1.0, u, -alpha, nullptr, true, 0, &np));  // :34
         HG_TRY(g.norm_from_stat(np, 5, &beta));
         if (k > 1) {  // histories of iteration k-1 have landed: its stop rule (:76, strict)
@@ -579,7 +638,14 @@ int lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* A
         HG_TRY(hg_k_lsmr_update(ctx, nl, dx, h, hbar, v, k == 1 ? 1 : 0, c0, zeta / (rho * rhobar),
                                 thetanew / rho, g.have_xt ? g.xt.p : nullptr, g.stat.p, &np));  // :61-67
         HG_TRY(g.enqueue_norm(np, 20));
-        HG_TRY(g.residual_enqueue(dx, r, 21));                                  // :69
+        if (literal_res) {
+            HG_TRY(g.residual_enqueue(dx, r, 21));  // :69
+        } else {  // t holds u_k, u holds u_{k+1} (unscaled, i.e. zero, when beta == 0)
+            HG_TRY(hg_k_gkb_resid(ctx, m, t, alpha_k, u, beta, bah.p, c_prev, bahb.p, c0, k == 1, r,
+                                  zeta / (rho * rhobar), g.stat.p, &np));
+            HG_TRY(g.enqueue_norm(np, 21));
+            c_prev = thetanew / rho;
+        }
         HG_TRY(g.apply_At(r, nullptr, nullptr, 0.0, nullptr, 0.0, true, &np));  // norm(A.'*r)  :71
         HG_TRY(g.enqueue_norm(np, 22));
         HG_TRY(g.hist_copy(k));
@@ -596,6 +662,18 @@ int lsmr_impl(hg_ctx* ctx, hg_comm* comm, const hg_matrix* A, const hg_matrix* A
 }
 
 }  // namespace
+
+// Residual histories of the hybrid GKB solvers: 0 (default) from the Golub-Kahan relation (no third product with A per
+// iteration), 1 literal b - A*x by SpMV.  Option "gkb_residual" / env HG_GKB_RESIDUAL.
+static int g_gkb_residual = -1;
+int hg_gkb_residual_mode() {
+    if (g_gkb_residual < 0) {
+        const char* e = getenv("HG_GKB_RESIDUAL");
+        g_gkb_residual = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_gkb_residual;
+}
+void hg_gkb_residual_mode_set(int v) { g_gkb_residual = v == 1 ? 1 : 0; }
 
 extern "C" int hg_hybrid_lsqr_solver(hg_ctx* ctx, const hg_matrix* A, const hg_matrix* At, const double* b,
                                      const double* x_true, double tol, int maxit, double lambda, double* x,

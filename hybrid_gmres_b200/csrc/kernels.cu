@@ -416,6 +416,35 @@ axpby_kernel(int64_t n, double a, const double* __restrict__ x, double b,
     }
 }
 
+// True residual of LSQR on [A; sqrt(lambda) I] without a product with A: the Golub-Kahan relation gives
+// A v_k = alpha_k u_k + beta_{k+1} u_{k+1} (top block), so with d_k = A w_k and r_k = b - A x_k
+//   d_k = A v_k - cprev d_{k-1}   (w_k = v_k - (theta_k / rho_{k-1}) w_{k-1}, hybrid_lsqr_solver.m:40)
+//   r_k = r_{k-1} - step d_k      (x_k = x_{k-1} + (phi_k / rho_k) w_k,       hybrid_lsqr_solver.m:39)
+// stat: partial sums of r_k^2 (hybrid_lsqr_solver.m:43 takes norm(b - A*x))
+// LSMR (d2 != nullptr) updates x along hbar_k = h_k - c0 hbar_{k-1} with h_k in the role of w_k (lsmr_solver.m:61-67):
+//   d_k = A h_k as above,  d2_k = A hbar_k = d_k - c0 d2_{k-1},  r_k = r_{k-1} - step d2_k
+__global__ void __launch_bounds__(kBlock)
+gkb_resid_kernel(int64_t n, const double* __restrict__ u_old, double a, const double* __restrict__ u_new, double b,
+                 double* __restrict__ d, double cprev, double* __restrict__ d2, double c0, int first,
+                 double* __restrict__ r, double step, double* __restrict__ stat) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    double sq = 0.0;
+    if (i < n) {
+        double dn = a * u_old[i] + b * u_new[i];
+        if (!first) dn -= cprev * d[i];
+        d[i] = dn;
+        if (d2) {
+            if (!first) dn -= c0 * d2[i];
+            d2[i] = dn;
+        }
+        const double rn = r[i] - step * dn;
+        r[i] = rn;
+        sq = rn * rn;
+    }
+    const double t = block_sum(sq);
+    if (threadIdx.x == 0) stat[blockIdx.x] = t;
+}
+
 __global__ void __launch_bounds__(kBlock)
 lsqr_update_kernel(int64_t n, double* __restrict__ x, double* __restrict__ w,
                    const double* __restrict__ v, double c1, double c2,
@@ -649,6 +678,19 @@ int hg_k_axpby(hg_ctx* ctx, int64_t n, double a, const double* x, double b, cons
     double bytes = 8.0 * (double)n * (1 + (y ? 1 : 0) + (out ? 1 : 0) + (ref ? 1 : 0));
     hg_launch_scope scope(ctx, HG_K_VECTOR, bytes);
     axpby_kernel<<<(unsigned)grid, kBlock, 0, ctx->stream>>>(n, a, x, b, y, out, ref, stat);
+    HG_CUDA(cudaGetLastError());
+    return HG_OK;
+}
+
+int hg_k_gkb_resid(hg_ctx* ctx, int64_t n, const double* u_old, double a, const double* u_new, double b, double* d,
+                   double cprev, double* d2, double c0, bool first, double* r, double step, double* stat,
+                   int* nparts) {
+    const int64_t grid = cdiv(n, kBlock);
+    if (nparts) *nparts = (int)grid;
+    if (n <= 0) return HG_OK;
+    hg_launch_scope scope(ctx, HG_K_VECTOR, 8.0 * (double)n * (d2 ? 8 : 6));
+    gkb_resid_kernel<<<(unsigned)grid, kBlock, 0, ctx->stream>>>(n, u_old, a, u_new, b, d, cprev, d2, c0, first ? 1 : 0,
+                                                                r, step, stat);
     HG_CUDA(cudaGetLastError());
     return HG_OK;
 }

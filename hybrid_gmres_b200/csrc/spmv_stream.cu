@@ -295,6 +295,10 @@ extern "C" int hg_set_option(const char* name, int value) {
         hg_idx8_set(value);
         return HG_OK;
     }
+    if (strcmp(name, "gkb_residual") == 0) {
+        hg_gkb_residual_mode_set(value);
+        return HG_OK;
+    }
     if (strcmp(name, "spmv_group_split") == 0) {
         hg_spmv_group_split_set(value);
         return HG_OK;

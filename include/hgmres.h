@@ -87,6 +87,9 @@ int hg_version(void);
  * per 128 entries in the sliced form.  "spmv_idx8" / env HG_IDX8 (-1 default: matrices of >= 131 072 rows; 1 always;
  * 0 never): byte offsets from a base per slice column (9.1 bytes per non-zero) when every slice column spans < 256.
  * All index widths give bit-identical products.
+ * "gkb_residual" / env HG_GKB_RESIDUAL (default 0): the hybrid LSQR / hybrid LSMR / LSMR solvers take `b - A*x` of
+ * their residual histories from the Golub-Kahan relation (vector recurrences, no extra product with A); 1 forms it by
+ * SpMV as the reference does.  The iterates do not depend on it.
  * "dist_transport": see hg_comm_transport. */
 int hg_set_option(const char* name, int value);
 

@@ -236,6 +236,41 @@ def test_gkb_solvers_vs_oracle(hg, ctx, ct48_unmatched, name):
         assert np.all(rel <= np.maximum(TOL, 1e3 * sens[: len(rel)]))
 
 
+@pytest.mark.parametrize("name", ["hybrid_lsqr_solver", "hybrid_lsmr_solver", "lsmr_solver"])
+def test_gkb_residual_from_relation_matches_literal(hg, ctx, ct48_unmatched, name):
+    """Default: `b - A*x` (hybrid_lsqr_solver.m:43, hybrid_lsmr_solver.m:48, lsmr_solver.m:69) comes from the
+    Golub-Kahan relation (`A v_k = alpha_k u_k + beta_{k+1} u_{k+1}`: vector recurrences for LSQR / LSMR,
+    `U_{k+1}(beta1 e1 - B_k y)` for hybrid LSMR) instead of one more product with A per iteration; `gkb_residual`
+    = 1 forms it literally.  The iterates do not depend on it (bit-identical); the residual histories (and
+    `norm(A'*r)` of lsmr_solver, a product with the recurrence's r) agree to rounding."""
+    A, B, b, x_true = ct48_unmatched
+    args = (1e-6, 40) if name == "lsmr_solver" else (1e-6, 40, 1e-2)
+    out = {}
+    try:
+        for mode in (0, 1):
+            hg.set_option("gkb_residual", mode)
+            ex = {}
+            out[mode] = (getattr(hg, name)(A, b, x_true, *args, ctx=ctx, extras=ex), ex["X"])
+    finally:
+        hg.set_option("gkb_residual", 0)
+    (r0, X0), (r1, X1) = out[0], out[1]
+    assert r0[-1] == r1[-1] == 40
+    assert np.array_equal(X0, X1) and np.array_equal(r0[0], r1[0]) and np.array_equal(r0[1], r1[1])
+    assert np.max(np.abs(r0[2] - r1[2]) / r1[2]) < 1e-11
+    if name == "lsmr_solver":
+        assert np.max(np.abs(r0[3] - r1[3]) / r1[3]) < 1e-9
+    # and it stops where the literal form stops
+    tol = float(r1[2][24]) * (1 + 1e-9)
+    try:
+        its = []
+        for mode in (0, 1):
+            hg.set_option("gkb_residual", mode)
+            its.append(getattr(hg, name)(A, b, x_true, tol, *args[1:], ctx=ctx)[-1])
+    finally:
+        hg.set_option("gkb_residual", 0)
+    assert its[0] == its[1] <= 25
+
+
 def test_lsmr_defaults_and_missing_x_true(hg, ctx):
     """lsmr_solver.m:3-5 defaults; err_hist is NaN without x_true (:28,72-74)."""
     import oracle
