@@ -156,9 +156,11 @@ int hg_matrix_permute(hg_ctx* ctx, const hg_matrix* m, const int32_t* rowperm, c
 /* Which SpMV kernel this matrix runs with: low 4 bits 0 CSR row-per-thread-group, 1 row-per-lane over
  * 32-row slices (built lazily when rows of a slice have near-equal length), 2 TMA-staged streaming, 3 the
  * row-group interleaved form (csrc/spmv_group.cu; option "spmv_group" / env HG_SPMV_GROUP = rows per group);
- * bit 4 (value 16) set when the column indices are streamed as 16-bit offsets from per-group bases
+ * bit 4 (value 16) set when the column indices are streamed as 16-bit values — offsets from per-group bases
  * (csrc/spmv_idx16.cu: 10 instead of 12 bytes per entry; option "spmv_idx16" / env HG_IDX16: 0 off,
- * 1 (default) for the sliced form, 2 also for the row-per-warp CSR kernel). */
+ * 1 (default) for the sliced form, 2 also for the row-per-warp CSR kernel) or per-lane differences in the
+ * row-group form ("spmv_group16"); bit 5 (value 32) set when the sliced form streams byte offsets from a base per
+ * slice column (9.1 bytes per entry; "spmv_idx8"). */
 int hg_matrix_spmv_form(hg_ctx* ctx, const hg_matrix* m, int* form);
 int hg_matrix_info(const hg_matrix* m, int64_t* rows, int64_t* cols, int64_t* nnz);
 int hg_matrix_download_csr(hg_ctx* ctx, const hg_matrix* m, int64_t* rowptr, int32_t* colind,
