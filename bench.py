@@ -447,8 +447,8 @@ def main():
                 pass
     forms = config.get("spmv_form", {})
     knames = {"csr/idx32": "spmv_csr_kernel<32>", "csr/idx16": "spmv_csr16_kernel", "sell32/idx32": "spmv_sell32_kernel<4>",
-              "sell32/idx16": "spmv_sell16_kernel<4,false>", "sell32/idx8": "spmv_sell16_kernel<4,true>", "stream/idx32": "spmv_stream_kernel", "group/idx32": "spmv_group_kernel",
-              "group/idx16": "spmv_group16_kernel<4>"}
+              "sell32/idx16": "spmv_sell16_kernel<4, 0> (16-bit offsets)", "sell32/idx8": "spmv_sell16_kernel<4, 1> (byte offsets)", "stream/idx32": "spmv_stream_kernel", "group/idx32": "spmv_group_kernel",
+              "group/idx16": "spmv_group16_kernel<4, 1> (16-bit column differences)"}
     kname = " + ".join(f"{knames.get(forms.get(w), 'spmv')} ({w})" for w in ("A", "B"))
     step_bytes_8d = (12.0 * (r["nnzA"] + r["nnzB"]) + 8.0 * (r["m"] + r["n"] + 2) + 16.0 * r["m"] + 88.0 * r["n"]) * maxit + \
         32.0 * r["n"] * maxit * (maxit + 1) / 2.0
